@@ -1,0 +1,248 @@
+"""oracle — TEST INFRASTRUCTURE, not product code.
+
+ctypes loader for the CPU restatement of the reference's proving hot path
+(`oracle/*.c` → `oracle/libbforacle.so`).  Only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may import this package.
+
+PARITY UNPINNED: the reference (Rust + un-vendored Plonky3 @93967fce) holds no golden vectors for
+this path and cannot be built offline; the oracle is pinned against independent restatements
+(pure-Python big-int Poseidon2, O(n^2) DFT, open→verify round trips) — see DESIGN.md.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+P = 2130706433
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+
+class Mat(C.Structure):
+    _fields_ = [("data", u32p), ("rows", C.c_uint64), ("cols", C.c_uint64)]
+
+
+def build(force=False):
+    """(Re)build liboracle with the committed Makefile."""
+    so = os.path.join(_DIR, "libbforacle.so")
+    srcs = [os.path.join(_DIR, f) for f in os.listdir(_DIR) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _DIR, "libbforacle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.bfo_poseidon2_permute.argtypes = [u32p]
+        L.bfo_poseidon2_permute_many.argtypes = [u32p, C.c_uint64]
+        L.bfo_poseidon2_constants.argtypes = [u32p, u32p, u32p]
+        L.bfo_sponge_hash.argtypes = [u32p, C.c_uint64, u32p]
+        L.bfo_compress.argtypes = [u32p, u32p, u32p]
+        L.bfo_mmcs_commit.argtypes = [C.POINTER(Mat), C.c_int, u32p]
+        L.bfo_mmcs_commit.restype = C.c_void_p
+        L.bfo_tree_free.argtypes = [C.c_void_p]
+        L.bfo_tree_num_layers.argtypes = [C.c_void_p]
+        L.bfo_tree_layer_len.argtypes = [C.c_void_p, C.c_int]
+        L.bfo_tree_layer_len.restype = C.c_uint64
+        L.bfo_tree_layer.argtypes = [C.c_void_p, C.c_int]
+        L.bfo_tree_layer.restype = u32p
+        L.bfo_mmcs_open_batch.argtypes = [C.c_void_p, C.POINTER(Mat), C.c_int, C.c_uint64, u32p, u32p]
+        L.bfo_mmcs_verify_batch.argtypes = [u32p, u64p, u64p, C.c_int, C.c_uint64, u32p, u32p]
+        L.bfo_mmcs_verify_batch.restype = C.c_int
+        for f in (L.bfo_coset_lde_naive, L.bfo_coset_lde_batch, L.bfo_coset_lde_batch_bitrev):
+            f.argtypes = [u32p, C.c_uint64, C.c_uint64, C.c_uint, C.c_uint32, u32p]
+        L.bfo_dft_batch.argtypes = [u32p, C.c_uint64, C.c_uint64]
+        L.bfo_idft_batch.argtypes = [u32p, C.c_uint64, C.c_uint64]
+        L.bfo_pcs_commit.argtypes = [C.POINTER(Mat), u32p, C.c_int, C.c_uint, u32p]
+        L.bfo_pcs_commit.restype = C.c_void_p
+        L.bfo_pcs_data_free.argtypes = [C.c_void_p]
+        L.bfo_pcs_num_mats.argtypes = [C.c_void_p]
+        L.bfo_pcs_lde.argtypes = [C.c_void_p, C.c_int, u64p, u64p]
+        L.bfo_pcs_lde.restype = u32p
+        L.bfo_pcs_tree.argtypes = [C.c_void_p]
+        L.bfo_pcs_tree.restype = C.c_void_p
+        L.bfo_set_threads.argtypes = [C.c_int]
+        L.bfo_get_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(u32p)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def set_threads(n):
+    lib().bfo_set_threads(int(n))
+
+
+def get_threads():
+    return int(lib().bfo_get_threads())
+
+
+# ---- Poseidon2 ------------------------------------------------------------------------------
+def poseidon2_constants():
+    ei = np.zeros((4, 16), np.uint32)
+    it = np.zeros(13, np.uint32)
+    et = np.zeros((4, 16), np.uint32)
+    lib().bfo_poseidon2_constants(_p(ei), _p(it), _p(et))
+    return ei, it, et
+
+
+def permute(state):
+    s = _u32(state).copy()
+    assert s.shape == (16,)
+    lib().bfo_poseidon2_permute(_p(s))
+    return s
+
+
+def permute_many(states):
+    s = _u32(states).copy()
+    assert s.ndim == 2 and s.shape[1] == 16
+    lib().bfo_poseidon2_permute_many(_p(s), s.shape[0])
+    return s
+
+
+def sponge_hash(values):
+    v = _u32(values).ravel()
+    out = np.zeros(8, np.uint32)
+    lib().bfo_sponge_hash(_p(v) if v.size else None, v.size, _p(out))
+    return out
+
+
+def compress(left, right):
+    out = np.zeros(8, np.uint32)
+    l, r = _u32(left), _u32(right)
+    lib().bfo_compress(_p(l), _p(r), _p(out))
+    return out
+
+
+# ---- Merkle ---------------------------------------------------------------------------------
+def _mats(mats):
+    keep = [_u32(m) for m in mats]
+    arr = (Mat * len(keep))()
+    for i, m in enumerate(keep):
+        assert m.ndim == 2
+        arr[i] = Mat(_p(m), m.shape[0], m.shape[1])
+    return arr, keep
+
+
+class Tree:
+    """MerkleTreeMmcs prover data (digest layers) for a list of row-major matrices."""
+
+    def __init__(self, mats):
+        self._arr, self.mats = _mats(mats)
+        self.root = np.zeros(8, np.uint32)
+        self._h = lib().bfo_mmcs_commit(self._arr, len(self.mats), _p(self.root))
+        self._owned = True
+
+    @classmethod
+    def _borrow(cls, handle, mats):
+        t = cls.__new__(cls)
+        t._arr, t.mats = _mats(mats)
+        t._h = handle
+        t._owned = False
+        t.root = t.layers()[-1][0].copy()
+        return t
+
+    def layers(self):
+        L = lib()
+        out = []
+        for l in range(L.bfo_tree_num_layers(self._h)):
+            n = L.bfo_tree_layer_len(self._h, l)
+            ptr = L.bfo_tree_layer(self._h, l)
+            out.append(np.ctypeslib.as_array(ptr, shape=(n, 8)).copy())
+        return out
+
+    def open_batch(self, index):
+        total = sum(m.shape[1] for m in self.mats)
+        nl = lib().bfo_tree_num_layers(self._h) - 1
+        rows = np.zeros(max(total, 1), np.uint32)
+        sib = np.zeros((max(nl, 1), 8), np.uint32)
+        lib().bfo_mmcs_open_batch(self._h, self._arr, len(self.mats), int(index), _p(rows), _p(sib))
+        out, o = [], 0
+        for m in self.mats:
+            out.append(rows[o:o + m.shape[1]].copy())
+            o += m.shape[1]
+        return out, sib[:nl].copy()
+
+    def __del__(self):
+        if getattr(self, "_owned", False) and self._h:
+            lib().bfo_tree_free(self._h)
+            self._h = None
+
+
+def verify_batch(root, dims, index, opened_rows, siblings):
+    rows = np.array([d[0] for d in dims], np.uint64)
+    cols = np.array([d[1] for d in dims], np.uint64)
+    flat = _u32(np.concatenate([_u32(r).ravel() for r in opened_rows]) if opened_rows else np.zeros(0, np.uint32))
+    sib = _u32(siblings).reshape(-1)
+    root = _u32(root)
+    rc = lib().bfo_mmcs_verify_batch(_p(root), rows.ctypes.data_as(u64p), cols.ctypes.data_as(u64p), len(dims), int(index),
+                                     _p(flat), _p(sib) if sib.size else None)
+    return rc == 0
+
+
+# ---- DFT ------------------------------------------------------------------------------------
+def _lde(fn, mat, added_bits, shift):
+    m = _u32(mat)
+    rows, cols = m.shape
+    out = np.zeros((rows << added_bits, cols), np.uint32)
+    fn(_p(m), rows, cols, added_bits, int(shift), _p(out))
+    return out
+
+
+def coset_lde_naive(mat, added_bits=1, shift=3):
+    return _lde(lib().bfo_coset_lde_naive, mat, added_bits, shift)
+
+
+def coset_lde_batch(mat, added_bits=1, shift=3):
+    return _lde(lib().bfo_coset_lde_batch, mat, added_bits, shift)
+
+
+def coset_lde_batch_bitrev(mat, added_bits=1, shift=3):
+    return _lde(lib().bfo_coset_lde_batch_bitrev, mat, added_bits, shift)
+
+
+def dft_batch(mat):
+    m = _u32(mat).copy()
+    lib().bfo_dft_batch(_p(m), m.shape[0], m.shape[1])
+    return m
+
+
+def idft_batch(mat):
+    m = _u32(mat).copy()
+    lib().bfo_idft_batch(_p(m), m.shape[0], m.shape[1])
+    return m
+
+
+# ---- PCS commit -----------------------------------------------------------------------------
+class PcsData:
+    """TwoAdicFriPcs::commit result: bit-reversed LDEs + Merkle tree."""
+
+    def __init__(self, evals, domain_shifts=None, log_blowup=1):
+        self._arr, self.evals = _mats(evals)
+        n = len(self.evals)
+        sh = _u32(domain_shifts if domain_shifts is not None else np.ones(n))
+        self.root = np.zeros(8, np.uint32)
+        self._h = lib().bfo_pcs_commit(self._arr, _p(sh), n, log_blowup, _p(self.root))
+        self.ldes = []
+        for i in range(n):
+            r, c = C.c_uint64(), C.c_uint64()
+            ptr = lib().bfo_pcs_lde(self._h, i, C.byref(r), C.byref(c))
+            self.ldes.append(np.ctypeslib.as_array(ptr, shape=(r.value, c.value)))
+        self.tree = Tree._borrow(lib().bfo_pcs_tree(self._h), self.ldes)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.ldes = []
+            lib().bfo_pcs_data_free(self._h)
+            self._h = None
