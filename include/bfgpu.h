@@ -1,0 +1,150 @@
+/* bfgpu.h — C ABI of the B200-native proving backend for zkvm-brainfuck.
+ *
+ * This is the drop-in boundary: a Rust `bf-gpu-sys` crate binds these symbols
+ * and implements, on top of them, the traits the reference prover is generic over:
+ *
+ *   TwoAdicSubgroupDft<KoalaBear>      (alias `Dft`,     reference crates/stark/src/kb31_poseidon2.rs:30)
+ *   Mmcs<KoalaBear>                    (alias `ValMmcs`, reference crates/stark/src/kb31_poseidon2.rs:27-28)
+ *   Pcs<Challenge, Challenger>         (alias `Pcs`,     reference crates/stark/src/kb31_poseidon2.rs:32;
+ *                                       call sites crates/stark/src/prover.rs:227,334,365-373,411,461
+ *                                       and crates/stark/src/machine.rs:196)
+ *   MachineProver::{commit, open}      (reference crates/stark/src/prover.rs:27-150,209-553)
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative bfgpu_status on failure;
+ *    bfgpu_last_error(ctx) returns a human-readable message for the last failure on that context.
+ *    Nothing unwinds across the boundary.  (The reference's error type is the unit struct
+ *    `CpuProverError`, prover.rs:166-168; its callers unwrap.)
+ *  - host buffers are caller-owned and only borrowed for the duration of the call;
+ *    device objects are opaque handles released by the matching *_free.
+ *  - field elements cross as raw uint32_t.  `BFGPU_REPR_MONTY` (default for the Rust shim) is the
+ *    in-memory representation of `Vec<KoalaBear>` (Montgomery form, R = 2^32);
+ *    `BFGPU_REPR_CANONICAL` is the plain residue in [0, p) and is what the Python/ctypes test
+ *    harness uses.  Select with bfgpu_set_repr().
+ *  - matrices are ROW-MAJOR rows x cols, exactly like Plonky3's RowMajorMatrix<KoalaBear>.
+ *  - extension-field elements (BinomialExtensionField<KoalaBear,4>) are 4 consecutive words,
+ *    coefficients of X^0..X^3.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    BFGPU_ERR_CUDA.
+ */
+#ifndef BFGPU_H
+#define BFGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    BFGPU_OK = 0,
+    BFGPU_ERR_INVALID = -1, /* bad argument (shape not a power of two, null pointer, ...) */
+    BFGPU_ERR_CUDA = -2,    /* CUDA runtime error or no device */
+    BFGPU_ERR_OOM = -3,     /* device allocation failed */
+    BFGPU_ERR_STATE = -4    /* object used in the wrong state */
+} bfgpu_status;
+
+enum { BFGPU_REPR_CANONICAL = 0, BFGPU_REPR_MONTY = 1 };
+enum { BFGPU_MEM_HOST = 0, BFGPU_MEM_DEVICE = 1 };
+
+typedef struct bfgpu_ctx bfgpu_ctx;
+typedef struct bfgpu_tree bfgpu_tree;         /* Mmcs::ProverData  (MerkleTree)            */
+typedef struct bfgpu_pcs_data bfgpu_pcs_data; /* Pcs::ProverData   (LDE matrices + MerkleTree) */
+
+/* A row-major matrix of base-field words living in host or device memory. */
+typedef struct {
+    const uint32_t* data;
+    uint64_t rows;
+    uint64_t cols;
+} bfgpu_mat;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* Replaces the construction of the config object `KoalaBearPoseidon2::new()`
+ * (crates/stark/src/kb31_poseidon2.rs:73-85): builds the Poseidon2 constant bank (my_perm, :35-50),
+ * the twiddle table and the FRI parameters (default_fri_config, :54-64: log_blowup 1,
+ * num_queries from $FRI_QUERIES or 84, proof_of_work_bits 16). */
+int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out);
+void bfgpu_ctx_destroy(bfgpu_ctx* ctx);
+const char* bfgpu_last_error(const bfgpu_ctx* ctx);
+int32_t bfgpu_set_repr(bfgpu_ctx* ctx, int repr);
+/* where input matrices passed to the compute entry points live (default BFGPU_MEM_HOST) */
+int32_t bfgpu_set_input_space(bfgpu_ctx* ctx, int mem_space);
+/* run all work of this context on an existing CUDA stream (cudaStream_t); NULL = own stream */
+int32_t bfgpu_set_stream(bfgpu_ctx* ctx, void* cuda_stream);
+int32_t bfgpu_synchronize(bfgpu_ctx* ctx);
+int32_t bfgpu_set_fri_params(bfgpu_ctx* ctx, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits);
+/* number of this library's kernels launched on the context since creation (bench evidence) */
+uint64_t bfgpu_launch_count(const bfgpu_ctx* ctx);
+
+/* ---- measurement hooks (bench.py): per-phase device time via CUDA events on the context's stream -- */
+enum {
+    BFGPU_PHASE_H2D = 0,      /* host -> device copies of caller matrices                     */
+    BFGPU_PHASE_INGEST = 1,   /* row-major -> column-major Montgomery (+ bit-reversed gather)   */
+    BFGPU_PHASE_INTT = 2,     /* inverse NTT passes                                            */
+    BFGPU_PHASE_SCALE = 3,    /* coset shift / 1/n scaling and zero-free 2x expansion          */
+    BFGPU_PHASE_NTT = 4,      /* forward NTT passes                                            */
+    BFGPU_PHASE_LEAF = 5,     /* Poseidon2 sponge over LDE rows (first digest layer)           */
+    BFGPU_PHASE_COMPRESS = 6, /* Poseidon2 2-to-1 compression layers (+ injected rows)         */
+    BFGPU_PHASE_OTHER = 7,
+    BFGPU_NUM_PHASES = 8
+};
+/* start (on != 0, clears the accumulators) or stop collecting per-phase timings */
+int32_t bfgpu_profile_enable(bfgpu_ctx* ctx, int on);
+/* synchronises, then returns accumulated milliseconds and kernel-launch counts per phase */
+int32_t bfgpu_profile_read(bfgpu_ctx* ctx, float ms[BFGPU_NUM_PHASES], uint64_t launches[BFGPU_NUM_PHASES]);
+/* register-only integer microbenchmark (IMAD + IADD3/LOP3 mix, no memory traffic): measured
+ * thread-level integer instructions per second, the denominator for the Poseidon2 roofline */
+int32_t bfgpu_int32_peak_probe(bfgpu_ctx* ctx, double* giops);
+
+/* ---- Poseidon2 primitives (Perm / MyHash / MyCompress, kb31_poseidon2.rs:22-26) -------------- */
+/* n independent width-16 permutations, states row-major n x 16, in place */
+int32_t bfgpu_poseidon2_permute(bfgpu_ctx* ctx, uint32_t* states, uint64_t n);
+/* PaddingFreeSponge::hash_iter over each row of a rows x cols matrix -> rows x 8 digests */
+int32_t bfgpu_sponge_hash_rows(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* digests);
+/* TruncatedPermutation::compress on n pairs: left/right n x 8 -> out n x 8 */
+int32_t bfgpu_compress(bfgpu_ctx* ctx, const uint32_t* left, const uint32_t* right, uint64_t n, uint32_t* out);
+
+/* ---- TwoAdicSubgroupDft<KoalaBear> ----------------------------------------------------------- */
+/* coset_lde_batch(mat, added_bits, shift): evaluations of every column's interpolant (given on the
+ * order-`rows` subgroup, natural order) over shift*<w_{rows<<added_bits}>.  out is
+ * (rows<<added_bits) x cols; bit_reversed_rows != 0 gives the row order TwoAdicFriPcs::commit
+ * stores (`.bit_reverse_rows()`), 0 gives natural order as the trait method returns it. */
+int32_t bfgpu_coset_lde_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t added_bits, uint32_t shift,
+                              int bit_reversed_rows, uint32_t* out);
+int32_t bfgpu_dft_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out);  /* natural in / out */
+int32_t bfgpu_idft_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out); /* natural in / out */
+
+/* ---- Mmcs<KoalaBear> = MerkleTreeMmcs<.., MyHash, MyCompress, 8> ----------------------------- */
+/* Mmcs::commit: heights must be powers of two.  root is 8 words. */
+int32_t bfgpu_mmcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* mats, int32_t n, uint32_t root[8], bfgpu_tree** out);
+/* Mmcs::open_batch(index): opened_rows receives, back to back in input-matrix order, row
+ * `index >> (log_max_height - log_height_i)` of each matrix; siblings receives log_max_height
+ * digests (8 words each), leaf level first. */
+int32_t bfgpu_mmcs_open_batch(bfgpu_tree* tree, uint64_t index, uint32_t* opened_rows, uint32_t* siblings);
+/* introspection used by the parity tests */
+int32_t bfgpu_tree_num_layers(const bfgpu_tree* tree);
+uint64_t bfgpu_tree_layer_len(const bfgpu_tree* tree, int32_t layer);
+int32_t bfgpu_tree_get_layer(bfgpu_tree* tree, int32_t layer, uint32_t* digests /* len x 8 */);
+void bfgpu_tree_free(bfgpu_tree* tree);
+
+/* ---- Pcs = TwoAdicFriPcs<Val, Dft, ValMmcs, ChallengeMmcs> ----------------------------------- */
+/* Pcs::commit(Vec<(Domain, RowMajorMatrix<Val>)>) (prover.rs:227,334,411; machine.rs:196).
+ * domain_shifts[i] is the shift of matrix i's two-adic coset domain (NULL = all natural domains,
+ * shift 1); the LDE uses shift GENERATOR/domain_shift and the context's log_blowup.  The LDEs
+ * and the tree stay on the device inside *out. */
+int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, const uint32_t* domain_shifts, int32_t n,
+                         uint32_t root[8], bfgpu_pcs_data** out);
+int32_t bfgpu_pcs_num_matrices(const bfgpu_pcs_data* data);
+int32_t bfgpu_pcs_lde_dims(const bfgpu_pcs_data* data, int32_t idx, uint64_t* rows, uint64_t* cols);
+/* Pcs::get_evaluations_on_domain(data, idx, domain) for the disjoint domain of size rows<<log_blowup
+ * and shift GENERATOR (prover.rs:365-373): the whole LDE, rows in NATURAL order
+ * (bit_reversed_rows = 0) or as stored (1).  Test/debug path: the prover kernels read the device
+ * copy in place. */
+int32_t bfgpu_pcs_get_evaluations(bfgpu_pcs_data* data, int32_t idx, int bit_reversed_rows, uint32_t* out);
+bfgpu_tree* bfgpu_pcs_tree(bfgpu_pcs_data* data); /* borrowed; freed with the pcs data */
+void bfgpu_pcs_data_free(bfgpu_pcs_data* data);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFGPU_H */

@@ -60,6 +60,15 @@ static inline void external_linear(uint32_t s[16]) {
 
 /* internal linear layer 1 + Diag(V),
    V = [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 1/2^8, 1/8, 1/2^24, -1/2^8, -1/8, -1/16, -1/2^24] */
+/* 2^-k mod p for the diagonal entries, filled on first use */
+static uint32_t INV2[25];
+static void init_inv2(void) {
+    if (INV2[0]) return;
+    uint32_t v = 1;
+    for (int k = 1; k <= 24; k++) { v = kb_halve(v); INV2[k] = v; }
+    __atomic_store_n(&INV2[0], 1u, __ATOMIC_RELEASE);
+}
+
 static inline void internal_linear(uint32_t s[16]) {
     uint32_t sum = 0;
     for (int i = 0; i < 16; i++) sum = kb_add(sum, s[i]);
@@ -73,17 +82,18 @@ static inline void internal_linear(uint32_t s[16]) {
     t[6] = kb_neg(kb_halve(s[6]));
     t[7] = kb_neg(kb_add(kb_dbl(s[7]), s[7]));
     t[8] = kb_neg(kb_dbl(kb_dbl(s[8])));
-    t[9] = kb_div_2exp(s[9], 8);
-    t[10] = kb_div_2exp(s[10], 3);
-    t[11] = kb_div_2exp(s[11], 24);
-    t[12] = kb_neg(kb_div_2exp(s[12], 8));
-    t[13] = kb_neg(kb_div_2exp(s[13], 3));
-    t[14] = kb_neg(kb_div_2exp(s[14], 4));
-    t[15] = kb_neg(kb_div_2exp(s[15], 24));
+    t[9] = kb_mul(s[9], INV2[8]);
+    t[10] = kb_mul(s[10], INV2[3]);
+    t[11] = kb_mul(s[11], INV2[24]);
+    t[12] = kb_neg(kb_mul(s[12], INV2[8]));
+    t[13] = kb_neg(kb_mul(s[13], INV2[3]));
+    t[14] = kb_neg(kb_mul(s[14], INV2[4]));
+    t[15] = kb_neg(kb_mul(s[15], INV2[24]));
     for (int i = 0; i < 16; i++) s[i] = kb_add(t[i], sum);
 }
 
 void bfo_poseidon2_permute(uint32_t s[16]) {
+    init_inv2();
     external_linear(s);
     for (int r = 0; r < ROUNDS_F / 2; r++) {
         for (int i = 0; i < 16; i++) s[i] = sbox(kb_add(s[i], BF_RC_16_30[r][i]));

@@ -1,0 +1,314 @@
+"""zkvm-brainfuck_b200 — host-side mirror of the reference's proving interfaces over the CUDA C ABI.
+
+The reference (felicityin/zkvm-brainfuck) is Rust and no Rust toolchain exists in this image, so
+the production binding is the `extern "C"` surface in include/bfgpu.h (INTEGRATION.md shows the
+Rust FFI crate).  This package is the Python/ctypes harness over the SAME symbols, with the same
+names and argument meaning as the Plonky3 traits the reference is generic over:
+
+  Radix2Dit       ~ TwoAdicSubgroupDft<KoalaBear>   (kb31_poseidon2.rs:30)
+  MerkleTreeMmcs  ~ Mmcs<KoalaBear>                 (kb31_poseidon2.rs:27-28)
+  TwoAdicFriPcs   ~ Pcs<Challenge, Challenger>      (kb31_poseidon2.rs:32, prover.rs:227,...)
+
+There is no CPU fallback: importing works anywhere (so the ABI can be checked), but every compute
+call raises `BfGpuError` without a CUDA device and the library refuses to load if it was not built.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+P = 2130706433
+REPR_CANONICAL, REPR_MONTY = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+
+class BfGpuError(RuntimeError):
+    pass
+
+
+class Mat(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_uint64), ("cols", C.c_uint64)]
+
+
+_LIB = None
+SO_PATH = _build.SO
+
+# every symbol include/bfgpu.h declares: (restype, argtypes)
+ABI = {
+    "bfgpu_ctx_create": (C.c_int32, [C.c_int, C.POINTER(C.c_void_p)]),
+    "bfgpu_ctx_destroy": (None, [C.c_void_p]),
+    "bfgpu_last_error": (C.c_char_p, [C.c_void_p]),
+    "bfgpu_set_repr": (C.c_int32, [C.c_void_p, C.c_int]),
+    "bfgpu_set_input_space": (C.c_int32, [C.c_void_p, C.c_int]),
+    "bfgpu_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_synchronize": (C.c_int32, [C.c_void_p]),
+    "bfgpu_set_fri_params": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "bfgpu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "bfgpu_profile_enable": (C.c_int32, [C.c_void_p, C.c_int]),
+    "bfgpu_profile_read": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), _u64p]),
+    "bfgpu_int32_peak_probe": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
+    "bfgpu_poseidon2_permute": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "bfgpu_sponge_hash_rows": (C.c_int32, [C.c_void_p, C.POINTER(Mat), C.c_void_p]),
+    "bfgpu_compress": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "bfgpu_coset_lde_batch": (C.c_int32, [C.c_void_p, C.POINTER(Mat), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
+    "bfgpu_dft_batch": (C.c_int32, [C.c_void_p, C.POINTER(Mat), C.c_void_p]),
+    "bfgpu_idft_batch": (C.c_int32, [C.c_void_p, C.POINTER(Mat), C.c_void_p]),
+    "bfgpu_mmcs_commit": (C.c_int32, [C.c_void_p, C.POINTER(Mat), C.c_int32, _u32p, C.POINTER(C.c_void_p)]),
+    "bfgpu_mmcs_open_batch": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "bfgpu_tree_num_layers": (C.c_int32, [C.c_void_p]),
+    "bfgpu_tree_layer_len": (C.c_uint64, [C.c_void_p, C.c_int32]),
+    "bfgpu_tree_get_layer": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "bfgpu_tree_free": (None, [C.c_void_p]),
+    "bfgpu_pcs_commit": (C.c_int32, [C.c_void_p, C.POINTER(Mat), _u32p, C.c_int32, _u32p, C.POINTER(C.c_void_p)]),
+    "bfgpu_pcs_num_matrices": (C.c_int32, [C.c_void_p]),
+    "bfgpu_pcs_lde_dims": (C.c_int32, [C.c_void_p, C.c_int32, _u64p, _u64p]),
+    "bfgpu_pcs_get_evaluations": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]),
+    "bfgpu_pcs_tree": (C.c_void_p, [C.c_void_p]),
+    "bfgpu_pcs_data_free": (None, [C.c_void_p]),
+}
+
+
+def lib():
+    """Load libbfgpu.so (built in-tree by build.py / __graft_entry__.build()); never falls back."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise BfGpuError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(this backend has no CPU fallback)")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """`KoalaBearPoseidon2::new()` analogue (kb31_poseidon2.rs:73-85): owns the device context."""
+
+    def __init__(self, device=0, repr=REPR_CANONICAL):
+        self._h = C.c_void_p()
+        rc = lib().bfgpu_ctx_create(device, C.byref(self._h))
+        if rc != 0:
+            msg = lib().bfgpu_last_error(self._h).decode() if self._h else "context allocation failed"
+            if self._h:
+                lib().bfgpu_ctx_destroy(self._h)
+                self._h = None
+            raise BfGpuError(f"bfgpu_ctx_create failed ({rc}): {msg}")
+        self.check(lib().bfgpu_set_repr(self._h, repr))
+
+    def check(self, rc):
+        if rc != 0:
+            raise BfGpuError(f"bfgpu error {rc}: {lib().bfgpu_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream_handle):
+        self.check(lib().bfgpu_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def set_input_space(self, space):
+        self.check(lib().bfgpu_set_input_space(self._h, space))
+
+    def set_repr(self, repr):
+        self.check(lib().bfgpu_set_repr(self._h, repr))
+
+    def set_fri_params(self, log_blowup=1, num_queries=84, pow_bits=16):
+        self.check(lib().bfgpu_set_fri_params(self._h, log_blowup, num_queries, pow_bits))
+
+    def synchronize(self):
+        self.check(lib().bfgpu_synchronize(self._h))
+
+    PHASES = ["h2d", "ingest", "intt", "scale", "ntt", "leaf_hash", "compress", "other"]
+
+    def profile_enable(self, on=True):
+        self.check(lib().bfgpu_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> {phase: (milliseconds, launches)} accumulated since profile_enable(True)."""
+        ms = (C.c_float * 8)()
+        ln = (C.c_uint64 * 8)()
+        self.check(lib().bfgpu_profile_read(self._h, ms, ln))
+        return {n: (float(ms[i]), int(ln[i])) for i, n in enumerate(self.PHASES)}
+
+    def int32_peak_probe(self):
+        g = C.c_double()
+        self.check(lib().bfgpu_int32_peak_probe(self._h, C.byref(g)))
+        return g.value
+
+    @property
+    def launch_count(self):
+        return int(lib().bfgpu_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().bfgpu_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    # ---- Poseidon2 primitives -----------------------------------------------------------------
+    def permute(self, states):
+        s = _u32(states).copy()
+        assert s.ndim == 2 and s.shape[1] == 16
+        self.check(lib().bfgpu_poseidon2_permute(self._h, _ptr(s), s.shape[0]))
+        return s
+
+    def hash_rows(self, mat):
+        m = _u32(mat)
+        out = np.zeros((m.shape[0], 8), np.uint32)
+        cm = Mat(m.ctypes.data, m.shape[0], m.shape[1])
+        self.check(lib().bfgpu_sponge_hash_rows(self._h, C.byref(cm), _ptr(out)))
+        return out
+
+    def compress(self, left, right):
+        l, r = _u32(left), _u32(right)
+        out = np.zeros_like(l)
+        self.check(lib().bfgpu_compress(self._h, _ptr(l), _ptr(r), l.shape[0], _ptr(out)))
+        return out
+
+
+def _mats(mats):
+    keep = [_u32(m) for m in mats]
+    arr = (Mat * len(keep))()
+    for i, m in enumerate(keep):
+        if m.ndim != 2:
+            raise ValueError("matrices must be 2-D")
+        arr[i] = Mat(m.ctypes.data, m.shape[0], m.shape[1])
+    return arr, keep
+
+
+class Radix2Dit:
+    """TwoAdicSubgroupDft<KoalaBear> (the reference's `Dft`, kb31_poseidon2.rs:30)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def _call(self, fn, mat, out_rows, *extra):
+        m = _u32(mat)
+        out = np.zeros((out_rows, m.shape[1]), np.uint32)
+        cm = Mat(m.ctypes.data, m.shape[0], m.shape[1])
+        self.ctx.check(fn(self.ctx._h, C.byref(cm), *extra, _ptr(out)))
+        return out
+
+    def dft_batch(self, mat):
+        return self._call(lib().bfgpu_dft_batch, mat, np.shape(mat)[0])
+
+    def idft_batch(self, mat):
+        return self._call(lib().bfgpu_idft_batch, mat, np.shape(mat)[0])
+
+    def coset_lde_batch(self, mat, added_bits, shift, bit_reversed_rows=False):
+        return self._call(lib().bfgpu_coset_lde_batch, mat, np.shape(mat)[0] << added_bits, added_bits, int(shift),
+                          1 if bit_reversed_rows else 0)
+
+
+class MerkleTree:
+    """Mmcs::ProverData."""
+
+    def __init__(self, ctx, handle, dims, owned=True):
+        self.ctx, self._h, self.dims, self._owned = ctx, handle, dims, owned
+        self.root = None
+
+    def layers(self):
+        out = []
+        for l in range(lib().bfgpu_tree_num_layers(self._h)):
+            n = lib().bfgpu_tree_layer_len(self._h, l)
+            a = np.zeros((n, 8), np.uint32)
+            self.ctx.check(lib().bfgpu_tree_get_layer(self._h, l, _ptr(a)))
+            out.append(a)
+        return out
+
+    def free(self):
+        if self._owned and self._h:
+            lib().bfgpu_tree_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.free()
+
+
+class MerkleTreeMmcs:
+    """Mmcs<KoalaBear> = MerkleTreeMmcs<_, _, MyHash, MyCompress, 8> (kb31_poseidon2.rs:27-28)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def commit(self, mats):
+        arr, keep = _mats(mats)
+        root = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        self.ctx.check(lib().bfgpu_mmcs_commit(self.ctx._h, arr, len(keep), root.ctypes.data_as(_u32p), C.byref(h)))
+        t = MerkleTree(self.ctx, h, [m.shape for m in keep])
+        t.root = root
+        return root, t
+
+    def open_batch(self, index, tree):
+        total = sum(c for _, c in tree.dims)
+        nl = lib().bfgpu_tree_num_layers(tree._h) - 1
+        rows = np.zeros(max(total, 1), np.uint32)
+        sib = np.zeros((max(nl, 1), 8), np.uint32)
+        self.ctx.check(lib().bfgpu_mmcs_open_batch(tree._h, int(index), _ptr(rows), _ptr(sib)))
+        out, o = [], 0
+        for _, c in tree.dims:
+            out.append(rows[o:o + c].copy())
+            o += c
+        return out, sib[:nl].copy()
+
+
+class PcsProverData:
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        n = lib().bfgpu_pcs_num_matrices(handle)
+        self.dims = []
+        for i in range(n):
+            r, c = C.c_uint64(), C.c_uint64()
+            lib().bfgpu_pcs_lde_dims(handle, i, C.byref(r), C.byref(c))
+            self.dims.append((r.value, c.value))
+        self.tree = MerkleTree(ctx, lib().bfgpu_pcs_tree(handle), self.dims, owned=False)
+
+    def free(self):
+        if self._h:
+            lib().bfgpu_pcs_data_free(self._h)
+            self._h = None
+            self.tree._h = None
+
+    def __del__(self):
+        self.free()
+
+
+class TwoAdicFriPcs:
+    """Pcs (kb31_poseidon2.rs:32): commit / get_evaluations_on_domain (open: later rounds)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def commit(self, evaluations, domain_shifts=None):
+        """`pcs.commit(vec![(domain, matrix), ...])`; domain_shifts[i] = domain.shift (default 1)."""
+        arr, keep = _mats(evaluations)
+        root = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        sh = None
+        if domain_shifts is not None:
+            sh = _u32(domain_shifts)
+            assert sh.shape == (len(keep),)
+        self.ctx.check(lib().bfgpu_pcs_commit(self.ctx._h, arr, sh.ctypes.data_as(_u32p) if sh is not None else None, len(keep),
+                                              root.ctypes.data_as(_u32p), C.byref(h)))
+        return root, PcsProverData(self.ctx, h)
+
+    def get_evaluations_on_domain(self, data, idx, bit_reversed_rows=False):
+        r, c = data.dims[idx]
+        out = np.zeros((r, c), np.uint32)
+        self.ctx.check(lib().bfgpu_pcs_get_evaluations(data._h, idx, 1 if bit_reversed_rows else 0, _ptr(out)))
+        return out

@@ -1,0 +1,749 @@
+// bfgpu.cu — host side of the B200 proving backend: context, device-memory plumbing and the C ABI
+// declared in include/bfgpu.h.  One translation unit: the kernels live in the .cuh files included
+// below so that the Poseidon2 constant bank is a single __constant__ object.
+//
+// Mirrors, phase by phase, what the reference does on the CPU in `CpuProver::commit`
+// (reference crates/stark/src/prover.rs:209-236) through Plonky3's `TwoAdicFriPcs::commit`
+// (coset LDE + bit-reversed rows + MerkleTreeMmcs::commit).  There is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bfgpu.h"
+#include "kb31.cuh"
+#include "poseidon2.cuh"
+#include "rc_16_30.h"
+
+#include "kernels_hash.cuh"
+#include "kernels_ntt.cuh"
+
+// ------------------------------------------------------------------------------------------------
+struct DMat {  // column-major device matrix, Montgomery words
+    uint32_t* d = nullptr;
+    uint64_t rows = 0;
+    uint32_t cols = 0;
+};
+
+struct bfgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int repr = BFGPU_REPR_CANONICAL;
+    int input_space = BFGPU_MEM_HOST;
+    std::string err;
+    uint32_t* d_tw = nullptr;  // w^e, w of order 2^24, e < 2^23
+    uint32_t log_blowup = 1, num_queries = 84, pow_bits = 16;
+    uint64_t launches = 0;
+    // optional per-phase device timing (bfgpu_profile_*): CUDA events recorded on ctx->stream
+    bool profiling = false;
+    struct Span { int phase; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    float phase_ms[BFGPU_NUM_PHASES] = {0};
+    uint64_t phase_launches[BFGPU_NUM_PHASES] = {0};
+    int cur_phase = -1;
+};
+
+struct bfgpu_tree {
+    bfgpu_ctx* ctx = nullptr;
+    std::vector<DMat> mats;  // input order
+    bool owns_mats = false;
+    std::vector<uint32_t*> layers;  // layers[l]: layer_len[l] digests of 8 words
+    std::vector<uint64_t> layer_len;
+    unsigned log_max = 0;
+};
+
+struct bfgpu_pcs_data {
+    bfgpu_ctx* ctx = nullptr;
+    std::vector<DMat> ldes;  // bit-reversed rows
+    bfgpu_tree* tree = nullptr;
+};
+
+static int32_t fail(bfgpu_ctx* ctx, int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? BFGPU_ERR_OOM : BFGPU_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
+    } while (0)
+#define TRY(call)                   \
+    do {                            \
+        int32_t rc_ = (call);       \
+        if (rc_ != BFGPU_OK) return rc_; \
+    } while (0)
+#define LAUNCHED(ctx)                                                        \
+    do {                                                                     \
+        (ctx)->launches++;                                                   \
+        if ((ctx)->cur_phase >= 0) (ctx)->phase_launches[(ctx)->cur_phase]++; \
+    } while (0)
+
+// RAII phase marker: when profiling is on, brackets the enclosed launches with two events
+struct Phase {
+    bfgpu_ctx* ctx;
+    int prev;
+    size_t idx = (size_t)-1;
+    Phase(bfgpu_ctx* c, int phase) : ctx(c), prev(c->cur_phase) {
+        c->cur_phase = phase;
+        if (c->profiling) {
+            bfgpu_ctx::Span sp{phase, nullptr, nullptr};
+            cudaEventCreate(&sp.a);
+            cudaEventCreate(&sp.b);
+            cudaEventRecord(sp.a, c->stream);
+            idx = c->spans.size();
+            c->spans.push_back(sp);
+        }
+    }
+    ~Phase() {
+        if (idx != (size_t)-1) cudaEventRecord(ctx->spans[idx].b, ctx->stream);
+        ctx->cur_phase = prev;
+    }
+};
+
+static inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+static inline unsigned ilog2(uint64_t x) {
+    unsigned l = 0;
+    while ((1ull << l) < x) l++;
+    return l;
+}
+
+static int32_t dalloc(bfgpu_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 4;
+    CU(cudaMallocAsync(p, bytes, ctx->stream));
+    return BFGPU_OK;
+}
+static void dfree(bfgpu_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// ---- context ----------------------------------------------------------------------------------
+extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
+    if (!out) return BFGPU_ERR_INVALID;
+    *out = nullptr;
+    bfgpu_ctx* ctx = new bfgpu_ctx();
+    ctx->device = device;
+    *out = ctx;  // returned even on failure so the caller can read the message
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ctx, BFGPU_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback", cudaGetErrorString(e));
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // keep freed blocks cached in the stream-ordered pool: repeated commits reuse them
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
+
+    // Poseidon2 constant bank (kb31_poseidon2.rs:35-50): internal constants = column 0 of table rows
+    // 4..16; external initial = rows 0..3; external terminal = rows 17..20 (rows 4..7 after the drain).
+    p2::Consts h;
+    memset(&h, 0, sizeof h);
+    for (int r = 0; r < 4; r++)
+        for (int i = 0; i < 16; i++) {
+            h.ext[r][i] = kb::to_mont(BFGPU_RC_16_30[r][i]);
+            h.ext[4 + r][i] = kb::to_mont(BFGPU_RC_16_30[17 + r][i]);
+        }
+    for (int r = 0; r < 13; r++) h.internal[r] = kb::to_mont(BFGPU_RC_16_30[4 + r][0]);
+    {  // V = [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 1/2^8, 1/8, 1/2^24, -1/2^8, -1/8, -1/16, -1/2^24]
+        auto frac = [](int sign, unsigned k) {
+            uint32_t v = kb::ONE;
+            for (unsigned i = 0; i < k; i++) v = kb::halve(v);
+            return sign < 0 ? kb::neg(v) : v;
+        };
+        auto small = [](int v) { return v >= 0 ? kb::to_mont((uint32_t)v) : kb::neg(kb::to_mont((uint32_t)(-v))); };
+        uint32_t d[16] = {small(-2), small(1), small(2), frac(1, 1), small(3), small(4), frac(-1, 1), small(-3),
+                          small(-4), frac(1, 8), frac(1, 3), frac(1, 24), frac(-1, 8), frac(-1, 3), frac(-1, 4), frac(-1, 24)};
+        memcpy(h.diag, d, sizeof d);
+    }
+    CU(cudaMemcpyToSymbolAsync(p2::c_p2, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+
+    // twiddle table
+    CU(cudaMalloc(&ctx->d_tw, sizeof(uint32_t) << (nttk::TW_LOG - 1)));
+    nttk::k_build_twiddles<<<(1u << (nttk::TW_LOG - 1)) / 256, 256, 0, ctx->stream>>>(ctx->d_tw, kb::two_adic_generator(nttk::TW_LOG));
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    CU(cudaFuncSetAttribute(nttk::k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << (nttk::GMAX + nttk::LANES_LOG)));
+    CU(cudaFuncSetAttribute(nttk::k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << (nttk::GMAX + nttk::LANES_LOG)));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BFGPU_OK;
+}
+
+extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_tw) cudaFree(ctx->d_tw);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char* bfgpu_last_error(const bfgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int32_t bfgpu_set_repr(bfgpu_ctx* ctx, int repr) {
+    if (!ctx || (repr != BFGPU_REPR_CANONICAL && repr != BFGPU_REPR_MONTY)) return fail(ctx, BFGPU_ERR_INVALID, "bad repr");
+    ctx->repr = repr;
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_set_input_space(bfgpu_ctx* ctx, int s) {
+    if (!ctx || (s != BFGPU_MEM_HOST && s != BFGPU_MEM_DEVICE)) return fail(ctx, BFGPU_ERR_INVALID, "bad memory space");
+    ctx->input_space = s;
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_set_stream(bfgpu_ctx* ctx, void* s) {
+    if (!ctx) return BFGPU_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (s) {
+        ctx->stream = (cudaStream_t)s;
+        ctx->own_stream = false;
+    } else {
+        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_synchronize(bfgpu_ctx* ctx) {
+    if (!ctx) return BFGPU_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_set_fri_params(bfgpu_ctx* ctx, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits) {
+    if (!ctx || log_blowup == 0 || log_blowup > 4) return fail(ctx, BFGPU_ERR_INVALID, "bad FRI parameters");
+    ctx->log_blowup = log_blowup;
+    ctx->num_queries = num_queries;
+    ctx->pow_bits = pow_bits;
+    return BFGPU_OK;
+}
+extern "C" uint64_t bfgpu_launch_count(const bfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- measurement hooks -------------------------------------------------------------------------------
+extern "C" int32_t bfgpu_profile_enable(bfgpu_ctx* ctx, int on) {
+    if (!ctx) return BFGPU_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto& sp : ctx->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+    ctx->profiling = on != 0;
+    if (on)
+        for (int i = 0; i < BFGPU_NUM_PHASES; i++) {
+            ctx->phase_ms[i] = 0;
+            ctx->phase_launches[i] = 0;
+        }
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_profile_read(bfgpu_ctx* ctx, float ms[BFGPU_NUM_PHASES], uint64_t launches[BFGPU_NUM_PHASES]) {
+    if (!ctx || !ms) return BFGPU_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto& sp : ctx->spans) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ctx->phase_ms[sp.phase] += t;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+    for (int i = 0; i < BFGPU_NUM_PHASES; i++) {
+        ms[i] = ctx->phase_ms[i];
+        if (launches) launches[i] = ctx->phase_launches[i];
+    }
+    return BFGPU_OK;
+}
+
+// Integer-pipe probe: 8 independent chains per thread, each iteration 1 IMAD + 1 IADD3 + 1 LOP3 per
+// chain (the mix a Montgomery butterfly / Poseidon2 round issues), no memory traffic.
+__global__ void __launch_bounds__(256) k_int32_probe(uint32_t* out, uint32_t iters, uint32_t seed) {
+    uint32_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = seed + threadIdx.x * 8 + k;
+    uint32_t m = seed | 1u, c = seed ^ 0x9e3779b9u;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            a[k] = a[k] * m + c;        // IMAD
+            a[k] = a[k] + (a[k] >> 7);  // SHF + IADD
+            a[k] ^= c;                  // LOP3
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r ^= a[k];
+    if (r == 0x12345678u) out[0] = r;  // practically never; keeps the chains alive
+}
+extern "C" int32_t bfgpu_int32_peak_probe(bfgpu_ctx* ctx, double* giops) {
+    if (!ctx || !giops) return BFGPU_ERR_INVALID;
+    uint32_t* d = nullptr;
+    TRY(dalloc(ctx, (void**)&d, 4));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    const uint32_t iters = 4096, blocks = 148 * 8;
+    k_int32_probe<<<blocks, 256, 0, ctx->stream>>>(d, 64, 12345u);  // warm-up
+    CU(cudaEventRecord(a, ctx->stream));
+    k_int32_probe<<<blocks, 256, 0, ctx->stream>>>(d, iters, 12345u);
+    CU(cudaEventRecord(b, ctx->stream));
+    ctx->launches += 2;
+    CU(cudaEventSynchronize(b));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    dfree(ctx, d);
+    // 4 integer instructions per chain-iteration (IMAD, SHF, IADD, LOP3)
+    *giops = (double)blocks * 256 * iters * 8 * 4 / (ms * 1e-3) / 1e9;
+    return BFGPU_OK;
+}
+
+// ---- staging helpers ----------------------------------------------------------------------------
+// Bring a caller matrix (row-major, host or device, caller representation) into a fresh
+// column-major Montgomery device matrix, optionally gathering rows in bit-reversed order.
+static int32_t ingest(bfgpu_ctx* ctx, const bfgpu_mat& m, bool bitrev, DMat* out) {
+    out->rows = m.rows;
+    out->cols = (uint32_t)m.cols;
+    size_t bytes = (size_t)m.rows * m.cols * 4;
+    TRY(dalloc(ctx, (void**)&out->d, bytes));
+    if (bytes == 0) return BFGPU_OK;
+    const uint32_t* src = m.data;
+    uint32_t* staged = nullptr;
+    if (ctx->input_space == BFGPU_MEM_HOST) {
+        Phase ph(ctx, BFGPU_PHASE_H2D);
+        TRY(dalloc(ctx, (void**)&staged, bytes));
+        CU(cudaMemcpyAsync(staged, m.data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        src = staged;
+    }
+    Phase ph(ctx, BFGPU_PHASE_INGEST);
+    dim3 grid((unsigned)((m.rows + 31) / 32), (unsigned)((m.cols + 31) / 32)), block(32, 8);
+    nttk::k_ingest<<<grid, block, 0, ctx->stream>>>(src, out->d, m.rows, (uint32_t)m.cols, ilog2(m.rows), bitrev ? 1 : 0,
+                                                     ctx->repr == BFGPU_REPR_CANONICAL);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    dfree(ctx, staged);
+    return BFGPU_OK;
+}
+
+// column-major Montgomery device matrix -> caller's row-major host buffer
+static int32_t egress(bfgpu_ctx* ctx, const DMat& m, bool bitrev, uint32_t* host_out) {
+    size_t bytes = (size_t)m.rows * m.cols * 4;
+    if (bytes == 0) return BFGPU_OK;
+    uint32_t* tmp = nullptr;
+    TRY(dalloc(ctx, (void**)&tmp, bytes));
+    dim3 grid((unsigned)((m.rows + 31) / 32), (unsigned)((m.cols + 31) / 32)), block(32, 8);
+    nttk::k_egress<<<grid, block, 0, ctx->stream>>>(m.d, tmp, m.rows, m.cols, ilog2(m.rows), bitrev ? 1 : 0, ctx->repr == BFGPU_REPR_CANONICAL);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_out, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, tmp);
+    return BFGPU_OK;
+}
+
+static int32_t check_mat(bfgpu_ctx* ctx, const bfgpu_mat* m, bool need_pow2) {
+    if (!m) return fail(ctx, BFGPU_ERR_INVALID, "null matrix");
+    if (m->rows == 0 || m->cols == 0) return fail(ctx, BFGPU_ERR_INVALID, "empty matrix (%llu x %llu)", (unsigned long long)m->rows, (unsigned long long)m->cols);
+    if (!m->data) return fail(ctx, BFGPU_ERR_INVALID, "null matrix data");
+    if (need_pow2 && !is_pow2(m->rows)) return fail(ctx, BFGPU_ERR_INVALID, "matrix height %llu is not a power of two", (unsigned long long)m->rows);
+    if (m->rows > (1ull << 31) || m->cols > (1ull << 24)) return fail(ctx, BFGPU_ERR_INVALID, "matrix too large");
+    return BFGPU_OK;
+}
+
+// ---- NTT orchestration ----------------------------------------------------------------------------
+// Run all stages of a size-2^log_n transform on `ncols` column vectors (stride col_stride words).
+template <bool INVERSE>
+static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols) {
+    if (log_n == 0 || ncols == 0) return BFGPU_OK;
+    Phase ph(ctx, INVERSE ? BFGPU_PHASE_INTT : BFGPU_PHASE_NTT);
+    unsigned npass = (log_n + nttk::GMAX - 1) / nttk::GMAX;
+    unsigned base = log_n / npass, extra = log_n % npass;
+    unsigned g[8], p[8];
+    unsigned acc = 0;
+    for (unsigned i = 0; i < npass; i++) {  // low passes take the larger share, so every p > 0 is >= LANES_LOG
+        g[i] = base + (i < extra ? 1 : 0);
+        p[i] = acc;
+        acc += g[i];
+    }
+    for (unsigned s = 0; s < npass; s++) {
+        unsigned i = INVERSE ? s : npass - 1 - s;  // inverse DIT: low bits first; forward DIF: high bits first
+        unsigned lanes_log = p[i] == 0 ? std::min<unsigned>(nttk::LANES_LOG, log_n - g[i]) : nttk::LANES_LOG;
+        if (p[i] != 0 && p[i] < nttk::LANES_LOG) return fail(ctx, BFGPU_ERR_STATE, "internal: bad NTT pass plan");
+        dim3 grid(1u << (log_n - g[i] - lanes_log), ncols);
+        size_t smem = (size_t)4 << (g[i] + lanes_log);
+        nttk::k_ntt_pass<INVERSE><<<grid, nttk::NTT_THREADS, smem, ctx->stream>>>(data, col_stride, log_n, p[i], g[i], lanes_log, ctx->d_tw);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+    }
+    return BFGPU_OK;
+}
+
+// coset LDE of a caller matrix -> column-major device matrix with bit-reversed rows.
+// shift_mont: Montgomery form of the coset shift.
+static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bits, uint32_t shift_mont, DMat* out) {
+    unsigned log_n = ilog2(m.rows);
+    if (log_n + added_bits > kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
+    uint64_t n = m.rows, N = n << added_bits;
+    uint32_t ncosets = 1u << added_bits;
+    DMat coef;
+    TRY(ingest(ctx, m, /*bitrev=*/true, &coef));
+    TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols));
+    {
+        // per-coset scale vectors: pw[h*n + k] = (shift * w_N^{bitrev(h)})^k / n
+        Phase ph(ctx, BFGPU_PHASE_SCALE);
+        uint32_t* pw = nullptr;
+        TRY(dalloc(ctx, (void**)&pw, N * 4));
+        uint32_t ninv = kb::inv(kb::to_mont((uint32_t)(n % kb::P)));
+        uint32_t wN = kb::two_adic_generator(log_n + added_bits);
+        for (uint32_t h = 0; h < ncosets; h++) {
+            uint32_t sh = kb::mul(shift_mont, kb::pow(wN, kb::bitrev(h, added_bits)));
+            nttk::k_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pw + h * n, sh, ninv, n);
+            LAUNCHED(ctx);
+        }
+        CU(cudaGetLastError());
+        out->rows = N;
+        out->cols = coef.cols;
+        TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
+        dim3 grid((unsigned)((n + 255) / 256), coef.cols);
+        nttk::k_scale_cosets<<<grid, 256, 0, ctx->stream>>>(coef.d, out->d, pw, n, ncosets, coef.cols);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        dfree(ctx, coef.d);
+        dfree(ctx, pw);
+    }
+    TRY(run_ntt<false>(ctx, out->d, n, log_n, coef.cols * ncosets));
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_coset_lde_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t added_bits, uint32_t shift, int bit_reversed_rows,
+                                         uint32_t* out) {
+    if (!ctx || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    TRY(check_mat(ctx, mat, true));
+    uint32_t sm = ctx->repr == BFGPU_REPR_CANONICAL ? kb::to_mont(shift % kb::P) : shift;
+    DMat lde;
+    TRY(lde_device(ctx, *mat, added_bits, sm, &lde));
+    int32_t rc = egress(ctx, lde, !bit_reversed_rows, out);  // stored bit-reversed: un-reverse for natural order
+    dfree(ctx, lde.d);
+    return rc;
+}
+
+extern "C" int32_t bfgpu_dft_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out) {
+    if (!ctx || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    TRY(check_mat(ctx, mat, true));
+    DMat d;
+    TRY(ingest(ctx, *mat, false, &d));
+    TRY(run_ntt<false>(ctx, d.d, d.rows, ilog2(d.rows), d.cols));
+    int32_t rc = egress(ctx, d, true, out);
+    dfree(ctx, d.d);
+    return rc;
+}
+
+extern "C" int32_t bfgpu_idft_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out) {
+    if (!ctx || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    TRY(check_mat(ctx, mat, true));
+    DMat d;
+    TRY(ingest(ctx, *mat, true, &d));
+    TRY(run_ntt<true>(ctx, d.d, d.rows, ilog2(d.rows), d.cols));
+    uint64_t total = d.rows * d.cols;
+    nttk::k_scale<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d.d, total, kb::inv(kb::to_mont((uint32_t)(d.rows % kb::P))));
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    int32_t rc = egress(ctx, d, false, out);
+    dfree(ctx, d.d);
+    return rc;
+}
+
+// ---- Poseidon2 primitives --------------------------------------------------------------------------
+static int32_t convert_inplace(bfgpu_ctx* ctx, uint32_t* d, uint64_t n, bool to_mont) {
+    if (ctx->repr != BFGPU_REPR_CANONICAL || n == 0) return BFGPU_OK;
+    hashk::k_convert<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, n, to_mont ? 1 : 0);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_poseidon2_permute(bfgpu_ctx* ctx, uint32_t* states, uint64_t n) {
+    if (!ctx || (!states && n)) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    if (n == 0) return BFGPU_OK;
+    uint32_t* d = nullptr;
+    size_t bytes = n * 64;
+    if (ctx->input_space == BFGPU_MEM_HOST) {
+        TRY(dalloc(ctx, (void**)&d, bytes));
+        CU(cudaMemcpyAsync(d, states, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        d = states;
+    }
+    TRY(convert_inplace(ctx, d, n * 16, true));
+    hashk::k_permute_many<<<(unsigned)((n + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(d, n);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    TRY(convert_inplace(ctx, d, n * 16, false));
+    if (ctx->input_space == BFGPU_MEM_HOST) {
+        CU(cudaMemcpyAsync(states, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        dfree(ctx, d);
+    }
+    return BFGPU_OK;
+}
+
+// device array of column base pointers for a list of matrices (in the given order)
+static int32_t make_colptr(bfgpu_ctx* ctx, const std::vector<const DMat*>& mats, const uint32_t*** d_out, uint32_t* ncols_out) {
+    std::vector<const uint32_t*> h;
+    for (const DMat* m : mats)
+        for (uint32_t c = 0; c < m->cols; c++) h.push_back(m->d + (uint64_t)c * m->rows);
+    *ncols_out = (uint32_t)h.size();
+    TRY(dalloc(ctx, (void**)d_out, h.size() * sizeof(void*)));
+    if (!h.empty()) CU(cudaMemcpyAsync((void*)*d_out, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_sponge_hash_rows(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* digests) {
+    if (!ctx || !digests) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    TRY(check_mat(ctx, mat, false));
+    DMat d;
+    TRY(ingest(ctx, *mat, false, &d));
+    const uint32_t** colptr = nullptr;
+    uint32_t ncols = 0;
+    TRY(make_colptr(ctx, {&d}, &colptr, &ncols));
+    uint32_t* out = nullptr;
+    TRY(dalloc(ctx, (void**)&out, d.rows * 32));
+    hashk::k_leaf_hash<<<(unsigned)((d.rows + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(colptr, ncols, d.rows, out);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    TRY(convert_inplace(ctx, out, d.rows * 8, false));
+    CU(cudaMemcpyAsync(digests, out, d.rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, out);
+    dfree(ctx, (void*)colptr);
+    dfree(ctx, d.d);
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_compress(bfgpu_ctx* ctx, const uint32_t* left, const uint32_t* right, uint64_t n, uint32_t* out) {
+    if (!ctx || !left || !right || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    if (n == 0) return BFGPU_OK;
+    uint32_t *l = nullptr, *r = nullptr, *o = nullptr;
+    TRY(dalloc(ctx, (void**)&l, n * 32));
+    TRY(dalloc(ctx, (void**)&r, n * 32));
+    TRY(dalloc(ctx, (void**)&o, n * 32));
+    CU(cudaMemcpyAsync(l, left, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(r, right, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(convert_inplace(ctx, l, n * 8, true));
+    TRY(convert_inplace(ctx, r, n * 8, true));
+    hashk::k_compress_pairs<<<(unsigned)((n + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(l, r, o, n);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    TRY(convert_inplace(ctx, o, n * 8, false));
+    CU(cudaMemcpyAsync(out, o, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, l);
+    dfree(ctx, r);
+    dfree(ctx, o);
+    return BFGPU_OK;
+}
+
+// ---- MerkleTreeMmcs ----------------------------------------------------------------------------------
+static void tree_release(bfgpu_tree* t) {
+    if (!t) return;
+    for (uint32_t* l : t->layers) dfree(t->ctx, l);
+    if (t->owns_mats)
+        for (DMat& m : t->mats) dfree(t->ctx, m.d);
+    delete t;
+}
+
+// Build the tree over device matrices (input order preserved in t->mats).
+static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfgpu_tree** out) {
+    bfgpu_tree* t = new bfgpu_tree();
+    t->ctx = ctx;
+    t->mats = std::move(mats);
+    t->owns_mats = owns;
+    *out = t;
+    size_t n = t->mats.size();
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return t->mats[a].rows > t->mats[b].rows; });
+    uint64_t max_h = t->mats[order[0]].rows;
+    t->log_max = ilog2(max_h);
+    size_t pos = 0;
+    auto take_group = [&](uint64_t h) {
+        std::vector<const DMat*> g;
+        while (pos < n && t->mats[order[pos]].rows == h) g.push_back(&t->mats[order[pos++]]);
+        return g;
+    };
+    {
+        Phase ph(ctx, BFGPU_PHASE_LEAF);
+        auto g = take_group(max_h);
+        const uint32_t** colptr = nullptr;
+        uint32_t ncols = 0;
+        TRY(make_colptr(ctx, g, &colptr, &ncols));
+        uint32_t* layer = nullptr;
+        TRY(dalloc(ctx, (void**)&layer, max_h * 32));
+        t->layers.push_back(layer);
+        t->layer_len.push_back(max_h);
+        hashk::k_leaf_hash<<<(unsigned)((max_h + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(colptr, ncols, max_h, layer);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        dfree(ctx, (void*)colptr);
+    }
+    Phase ph(ctx, BFGPU_PHASE_COMPRESS);
+    for (unsigned l = 1; l <= t->log_max; l++) {
+        uint64_t len = max_h >> l;
+        auto g = take_group(len);
+        const uint32_t** colptr = nullptr;
+        uint32_t ncols = 0;
+        if (!g.empty()) TRY(make_colptr(ctx, g, &colptr, &ncols));
+        uint32_t* layer = nullptr;
+        TRY(dalloc(ctx, (void**)&layer, len * 32));
+        t->layers.push_back(layer);
+        t->layer_len.push_back(len);
+        hashk::k_compress_layer<<<(unsigned)((len + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(
+            t->layers[l - 1], layer, len, colptr, ncols);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        dfree(ctx, (void*)colptr);
+    }
+    if (pos != n) return fail(ctx, BFGPU_ERR_INVALID, "matrix heights are not powers of two below the tallest");
+    return BFGPU_OK;
+}
+
+static int32_t read_digest(bfgpu_ctx* ctx, const uint32_t* d, uint32_t out[8]) {
+    CU(cudaMemcpyAsync(out, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->repr == BFGPU_REPR_CANONICAL)
+        for (int i = 0; i < 8; i++) out[i] = kb::from_mont(out[i]);
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_mmcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* mats, int32_t n, uint32_t root[8], bfgpu_tree** out) {
+    if (!ctx || !mats || n <= 0 || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    for (int i = 0; i < n; i++) TRY(check_mat(ctx, &mats[i], true));
+    std::vector<DMat> d(n);
+    for (int i = 0; i < n; i++) TRY(ingest(ctx, mats[i], false, &d[i]));
+    bfgpu_tree* t = nullptr;
+    int32_t rc = build_tree(ctx, std::move(d), true, &t);
+    if (rc == BFGPU_OK) rc = read_digest(ctx, t->layers.back(), root);
+    if (rc != BFGPU_OK) {
+        tree_release(t);
+        return rc;
+    }
+    *out = t;
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_mmcs_open_batch(bfgpu_tree* t, uint64_t index, uint32_t* opened_rows, uint32_t* siblings) {
+    if (!t) return BFGPU_ERR_INVALID;
+    bfgpu_ctx* ctx = t->ctx;
+    if (!opened_rows || (!siblings && t->log_max)) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    if (index >= (1ull << t->log_max)) return fail(ctx, BFGPU_ERR_INVALID, "index %llu out of range", (unsigned long long)index);
+    std::vector<const uint32_t*> cp;
+    std::vector<uint64_t> ri;
+    for (const DMat& m : t->mats) {
+        uint64_t r = index >> (t->log_max - ilog2(m.rows));
+        for (uint32_t c = 0; c < m.cols; c++) {
+            cp.push_back(m.d + (uint64_t)c * m.rows);
+            ri.push_back(r);
+        }
+    }
+    uint32_t nc = (uint32_t)cp.size();
+    const uint32_t** d_cp = nullptr;
+    uint64_t* d_ri = nullptr;
+    uint32_t* d_out = nullptr;
+    TRY(dalloc(ctx, (void**)&d_cp, nc * sizeof(void*)));
+    TRY(dalloc(ctx, (void**)&d_ri, nc * 8));
+    TRY(dalloc(ctx, (void**)&d_out, nc * 4));
+    CU(cudaMemcpyAsync((void*)d_cp, cp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_ri, ri.data(), nc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    hashk::k_gather_row<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(d_cp, d_ri, nc, d_out, ctx->repr == BFGPU_REPR_CANONICAL);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(opened_rows, d_out, nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    for (unsigned l = 0; l < t->log_max; l++)
+        CU(cudaMemcpyAsync(siblings + 8 * l, t->layers[l] + 8 * ((index >> l) ^ 1), 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->repr == BFGPU_REPR_CANONICAL)
+        for (unsigned i = 0; i < 8 * t->log_max; i++) siblings[i] = kb::from_mont(siblings[i]);
+    dfree(ctx, (void*)d_cp);
+    dfree(ctx, d_ri);
+    dfree(ctx, d_out);
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_tree_num_layers(const bfgpu_tree* t) { return t ? (int32_t)t->layers.size() : 0; }
+extern "C" uint64_t bfgpu_tree_layer_len(const bfgpu_tree* t, int32_t l) {
+    return (t && l >= 0 && (size_t)l < t->layers.size()) ? t->layer_len[l] : 0;
+}
+extern "C" int32_t bfgpu_tree_get_layer(bfgpu_tree* t, int32_t l, uint32_t* digests) {
+    if (!t) return BFGPU_ERR_INVALID;
+    bfgpu_ctx* ctx = t->ctx;
+    if (l < 0 || (size_t)l >= t->layers.size() || !digests) return fail(ctx, BFGPU_ERR_INVALID, "bad layer");
+    uint64_t words = t->layer_len[l] * 8;
+    CU(cudaMemcpyAsync(digests, t->layers[l], words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->repr == BFGPU_REPR_CANONICAL)
+        for (uint64_t i = 0; i < words; i++) digests[i] = kb::from_mont(digests[i]);
+    return BFGPU_OK;
+}
+extern "C" void bfgpu_tree_free(bfgpu_tree* t) { tree_release(t); }
+
+// ---- TwoAdicFriPcs::commit ------------------------------------------------------------------------------
+extern "C" int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, const uint32_t* domain_shifts, int32_t n, uint32_t root[8],
+                                    bfgpu_pcs_data** out) {
+    if (!ctx || !evals || n <= 0 || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    for (int i = 0; i < n; i++) TRY(check_mat(ctx, &evals[i], true));
+    bfgpu_pcs_data* pd = new bfgpu_pcs_data();
+    pd->ctx = ctx;
+    pd->ldes.resize(n);
+    int32_t rc = BFGPU_OK;
+    uint32_t gen = kb::to_mont(kb::GEN);
+    for (int i = 0; i < n && rc == BFGPU_OK; i++) {
+        // shift = GENERATOR / domain.shift  (TwoAdicFriPcs::commit)
+        uint32_t shift = gen;
+        if (domain_shifts) {
+            uint32_t ds = ctx->repr == BFGPU_REPR_CANONICAL ? kb::to_mont(domain_shifts[i] % kb::P) : domain_shifts[i];
+            if (ds == 0) rc = fail(ctx, BFGPU_ERR_INVALID, "zero domain shift");
+            else shift = kb::mul(gen, kb::inv(ds));
+        }
+        if (rc == BFGPU_OK) rc = lde_device(ctx, evals[i], ctx->log_blowup, shift, &pd->ldes[i]);
+    }
+    if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree);
+    if (rc == BFGPU_OK) rc = read_digest(ctx, pd->tree->layers.back(), root);
+    if (rc != BFGPU_OK) {
+        bfgpu_pcs_data_free(pd);
+        return rc;
+    }
+    *out = pd;
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_pcs_num_matrices(const bfgpu_pcs_data* d) { return d ? (int32_t)d->ldes.size() : 0; }
+extern "C" int32_t bfgpu_pcs_lde_dims(const bfgpu_pcs_data* d, int32_t idx, uint64_t* rows, uint64_t* cols) {
+    if (!d || idx < 0 || (size_t)idx >= d->ldes.size()) return BFGPU_ERR_INVALID;
+    if (rows) *rows = d->ldes[idx].rows;
+    if (cols) *cols = d->ldes[idx].cols;
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_pcs_get_evaluations(bfgpu_pcs_data* d, int32_t idx, int bit_reversed_rows, uint32_t* out) {
+    if (!d) return BFGPU_ERR_INVALID;
+    bfgpu_ctx* ctx = d->ctx;
+    if (idx < 0 || (size_t)idx >= d->ldes.size() || !out) return fail(ctx, BFGPU_ERR_INVALID, "bad matrix index");
+    return egress(ctx, d->ldes[idx], !bit_reversed_rows, out);
+}
+extern "C" bfgpu_tree* bfgpu_pcs_tree(bfgpu_pcs_data* d) { return d ? d->tree : nullptr; }
+extern "C" void bfgpu_pcs_data_free(bfgpu_pcs_data* d) {
+    if (!d) return;
+    tree_release(d->tree);
+    for (DMat& m : d->ldes) dfree(d->ctx, m.d);
+    delete d;
+}

@@ -1,0 +1,126 @@
+// kernels_hash.cuh — Poseidon2 Merkle kernels (K2/K3 of SURVEY.md §2): one thread per leaf / node,
+// the 16-word state never leaves registers.
+//
+// Replaces MerkleTreeMmcs::commit as reached from Pcs::commit (reference
+// crates/stark/src/prover.rs:227,334,411; crates/stark/src/machine.rs:196): first digest layer =
+// PaddingFreeSponge over the concatenated same-height rows, upper layers = TruncatedPermutation
+// 2-to-1 compression with injection of shorter matrices' row digests.
+//
+// Device layout: matrices are COLUMN-major (column c of a matrix with `rows` rows starts at
+// base + c*rows), so thread r reading column c at row r is perfectly coalesced; digest layers are
+// arrays of 8-word digests (32 B, loaded/stored as 2 x uint4).
+#pragma once
+#include "poseidon2.cuh"
+
+namespace hashk {
+
+constexpr int HASH_THREADS = 128;
+
+// absorb the r-th row of the column list (overwrite-mode sponge, rate 8) into state s
+__device__ __forceinline__ void sponge_rows(uint32_t (&s)[16], const uint32_t* const* __restrict__ colptr, uint32_t ncols,
+                                            uint64_t r) {
+    uint32_t c0 = 0;
+    for (; c0 + 8 <= ncols; c0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = __ldg(colptr[c0 + k] + r);
+        p2::permute(s);
+    }
+    uint32_t rem = ncols - c0;
+    if (rem) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if ((uint32_t)k < rem) s[k] = __ldg(colptr[c0 + k] + r);
+        p2::permute(s);
+    }
+}
+
+__device__ __forceinline__ void store_digest(uint32_t* out, const uint32_t (&s)[16]) {
+    uint4* o = reinterpret_cast<uint4*>(out);
+    o[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+
+// first digest layer: digests[r] = sponge(row r of every column in colptr)
+__global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash(const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint64_t rows,
+                                                            uint32_t* __restrict__ digests) {
+    uint64_t r = blockIdx.x * (uint64_t)HASH_THREADS + threadIdx.x;
+    if (r >= rows) return;
+    uint32_t s[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) s[k] = 0;
+    sponge_rows(s, colptr, ncols, r);
+    store_digest(digests + 8 * r, s);
+}
+
+// next layer: out[i] = compress(prev[2i], prev[2i+1]); if ncols > 0 additionally
+// out[i] = compress(out[i], sponge(row i of the injected columns))
+__global__ void __launch_bounds__(HASH_THREADS) k_compress_layer(const uint32_t* __restrict__ prev, uint32_t* __restrict__ out, uint64_t len,
+                                                                 const uint32_t* const* __restrict__ colptr, uint32_t ncols) {
+    uint64_t i = blockIdx.x * (uint64_t)HASH_THREADS + threadIdx.x;
+    if (i >= len) return;
+    uint32_t s[16];
+    const uint4* in = reinterpret_cast<const uint4*>(prev + 16 * i);
+    uint4 a = in[0], b = in[1], c = in[2], d = in[3];
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+    s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    s[8] = c.x; s[9] = c.y; s[10] = c.z; s[11] = c.w;
+    s[12] = d.x; s[13] = d.y; s[14] = d.z; s[15] = d.w;
+    p2::permute(s);
+    if (ncols) {
+        uint32_t h[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) h[k] = 0;
+        sponge_rows(h, colptr, ncols, i);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[8 + k] = h[k];
+        p2::permute(s);
+    }
+    store_digest(out + 8 * i, s);
+}
+
+// n independent permutations, states row-major n x 16 (Montgomery form)
+__global__ void __launch_bounds__(HASH_THREADS) k_permute_many(uint32_t* __restrict__ st, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)HASH_THREADS + threadIdx.x;
+    if (i >= n) return;
+    uint4* p = reinterpret_cast<uint4*>(st + 16 * i);
+    uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+    uint32_t s[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+    p2::permute(s);
+    p[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    p[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    p[2] = make_uint4(s[8], s[9], s[10], s[11]);
+    p[3] = make_uint4(s[12], s[13], s[14], s[15]);
+}
+
+// compress n pairs: out[i] = permute(left[i] || right[i])[0..8]
+__global__ void __launch_bounds__(HASH_THREADS) k_compress_pairs(const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
+                                                                 uint32_t* __restrict__ out, uint64_t n) {
+    uint64_t i = blockIdx.x * (uint64_t)HASH_THREADS + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        s[k] = left[8 * i + k];
+        s[8 + k] = right[8 * i + k];
+    }
+    p2::permute(s);
+    store_digest(out + 8 * i, s);
+}
+
+// elementwise representation change (canonical <-> Montgomery) for small host-facing buffers
+__global__ void k_convert(uint32_t* __restrict__ data, uint64_t n, int to_mont) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    data[i] = to_mont ? kb::to_mont(data[i]) : kb::from_mont(data[i]);
+}
+
+// gather one row (index `row`) from a list of columns into a contiguous buffer
+__global__ void k_gather_row(const uint32_t* const* __restrict__ colptr, const uint64_t* __restrict__ rowidx, uint32_t ncols,
+                             uint32_t* __restrict__ out, int to_canonical) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    uint32_t v = colptr[c][rowidx[c]];
+    out[c] = to_canonical ? kb::from_mont(v) : v;
+}
+
+}  // namespace hashk

@@ -1,0 +1,97 @@
+// poseidon2.cuh — register-resident Poseidon2 (width 16, x^3, 8 external + 13 internal rounds) on
+// Montgomery-form KoalaBear words, plus the overwrite-mode sponge and the 2-to-1 compression.
+//
+// Replaces, on the device, what the reference reaches through `Perm = Poseidon2KoalaBear<16>`,
+// `MyHash = PaddingFreeSponge<Perm,16,8,8>` and `MyCompress = TruncatedPermutation<Perm,2,8,16>`
+// (reference crates/stark/src/kb31_poseidon2.rs:22-26,35-50; constants
+// crates/primitives/src/lib.rs:13-554).  The whole 16-word state lives in registers; round
+// constants sit in constant memory in Montgomery form and are consumed as c[bank][imm] operands
+// (the permutation is fully unrolled).
+#pragma once
+#include "kb31.cuh"
+
+namespace p2 {
+
+struct Consts {
+    uint32_t ext[8][16];    // external rounds: 0..3 initial, 4..7 terminal (Montgomery form)
+    uint32_t internal[16];  // 13 used
+    uint32_t diag[16];      // internal diagonal V (Montgomery form), see internal_linear()
+};
+
+#if defined(__CUDACC__)
+// single translation unit (bfgpu.cu): the constant bank is defined here
+__constant__ Consts c_p2;
+
+using kb::add;
+using kb::dbl;
+using kb::mul;
+using kb::sub;
+
+KB_D uint32_t sbox(uint32_t x) { return mul(mul(x, x), x); }
+
+// M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]]
+KB_D void mat4(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    // 9 additions + 2 doublings
+    uint32_t t01 = add(a, b), t23 = add(c, d);
+    uint32_t t0123 = add(t01, t23);
+    uint32_t t01123 = add(t0123, b), t01233 = add(t0123, d);
+    uint32_t nd = add(t01233, dbl(a));  // 3a + b + c + 2d
+    uint32_t nb = add(t01123, dbl(c));  // a + 2b + 3c + d
+    a = add(t01123, t01);               // 2a + 3b + c + d
+    c = add(t01233, t23);               // a + b + 2c + 3d
+    b = nb;
+    d = nd;
+}
+
+KB_D void external_linear(uint32_t (&s)[16]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) mat4(s[4 * k], s[4 * k + 1], s[4 * k + 2], s[4 * k + 3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t t = add(add(s[i], s[4 + i]), add(s[8 + i], s[12 + i]));
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[4 * k + i] = add(s[4 * k + i], t);
+    }
+}
+
+// 1 + Diag(V), V = [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 1/2^8, 1/8, 1/2^24, -1/2^8, -1/8, -1/16, -1/2^24]
+KB_D void internal_linear(uint32_t (&s)[16]) {
+    uint32_t part = add(add(add(s[1], s[2]), add(s[3], s[4])), add(add(s[5], s[6]), add(s[7], s[8])));
+    part = add(part, add(add(add(s[9], s[10]), add(s[11], s[12])), add(add(s[13], s[14]), s[15])));
+    uint32_t sum = add(part, s[0]);
+    s[0] = sub(part, s[0]);
+    s[1] = add(s[1], sum);
+    s[2] = add(dbl(s[2]), sum);
+    s[3] = add(kb::halve(s[3]), sum);
+    s[4] = add(add(dbl(s[4]), s[4]), sum);
+    s[5] = add(dbl(dbl(s[5])), sum);
+    s[6] = sub(sum, kb::halve(s[6]));
+    s[7] = sub(sum, add(dbl(s[7]), s[7]));
+    s[8] = sub(sum, dbl(dbl(s[8])));
+#pragma unroll
+    for (int i = 9; i < 16; i++) s[i] = add(mul(s[i], c_p2.diag[i]), sum);
+}
+
+KB_D void permute(uint32_t (&s)[16]) {
+    external_linear(s);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = sbox(add(s[i], c_p2.ext[r][i]));
+        external_linear(s);
+    }
+#pragma unroll
+    for (int r = 0; r < 13; r++) {
+        s[0] = sbox(add(s[0], c_p2.internal[r]));
+        internal_linear(s);
+    }
+#pragma unroll
+    for (int r = 4; r < 8; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = sbox(add(s[i], c_p2.ext[r][i]));
+        external_linear(s);
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace p2
