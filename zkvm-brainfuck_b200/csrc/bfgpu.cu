@@ -22,6 +22,9 @@
 
 #include "kernels_hash.cuh"
 #include "kernels_ntt.cuh"
+#include "kernels_ntt2.cuh"
+#include <map>
+#include <unordered_map>
 
 // ------------------------------------------------------------------------------------------------
 struct DMat {  // column-major device matrix, Montgomery words
@@ -47,6 +50,16 @@ struct bfgpu_ctx {
     float phase_ms[BFGPU_NUM_PHASES] = {0};
     uint64_t phase_launches[BFGPU_NUM_PHASES] = {0};
     int cur_phase = -1;
+    // cached radix-16 pass plans (twiddle tables) per (log_n, inverse)
+    struct NttPass { unsigned p, g; ntt2::Tw* twA; ntt2::Tw* twB; };
+    std::map<std::pair<unsigned, bool>, std::vector<NttPass>> plans;
+    // size-exact caching allocator: every buffer is used on ctx->stream only, so a block freed by
+    // dfree() can be handed out again immediately (stream order protects it).  Identical commits
+    // reuse identical blocks; the CUDA async pool fragmented (a 4 GiB request carved out of the 8 GiB
+    // block forced a fresh 8 GiB mapping every step).
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;
+    size_t cached_bytes = 0;
 };
 
 struct bfgpu_tree {
@@ -121,14 +134,45 @@ static inline unsigned ilog2(uint64_t x) {
     return l;
 }
 
+static void trim_cache(bfgpu_ctx* ctx) {
+    if (ctx->free_blocks.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+    ctx->free_blocks.clear();
+    ctx->cached_bytes = 0;
+}
 static int32_t dalloc(bfgpu_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
-    if (bytes == 0) bytes = 4;
-    CU(cudaMallocAsync(p, bytes, ctx->stream));
+    bytes = (std::max<size_t>(bytes, 4) + 255) & ~(size_t)255;
+    auto it = ctx->free_blocks.find(bytes);
+    if (it != ctx->free_blocks.end()) {
+        *p = it->second;
+        ctx->free_blocks.erase(it);
+        ctx->cached_bytes -= bytes;
+    } else {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaErrorMemoryAllocation) {  // give cached blocks back to the driver and retry once
+            cudaGetLastError();
+            trim_cache(ctx);
+            e = cudaMalloc(p, bytes);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            *p = nullptr;
+            return fail(ctx, e == cudaErrorMemoryAllocation ? BFGPU_ERR_OOM : BFGPU_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    ctx->live[*p] = bytes;
     return BFGPU_OK;
 }
 static void dfree(bfgpu_ctx* ctx, void* p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    auto it = ctx->live.find(p);
+    if (it == ctx->live.end()) return;
+    size_t bytes = it->second;
+    ctx->live.erase(it);
+    ctx->free_blocks.emplace(bytes, p);
+    ctx->cached_bytes += bytes;
 }
 
 // ---- context ----------------------------------------------------------------------------------
@@ -144,11 +188,6 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
         return fail(ctx, BFGPU_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback", cudaGetErrorString(e));
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    // keep freed blocks cached in the stream-ordered pool: repeated commits reuse them
-    cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
-    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
 
     // Poseidon2 constant bank (kb31_poseidon2.rs:35-50): internal constants = column 0 of table rows
@@ -179,6 +218,16 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     nttk::k_build_twiddles<<<(1u << (nttk::TW_LOG - 1)) / 256, 256, 0, ctx->stream>>>(ctx->d_tw, kb::two_adic_generator(nttk::TW_LOG));
     LAUNCHED(ctx);
     CU(cudaGetLastError());
+    {  // 16th roots of unity (canonical) with Shoup quotients, forward and inverse
+        ntt2::Tw h16[2][8];
+        uint32_t w16 = kb::two_adic_generator(4), w16i = kb::inv(w16);
+        for (int j = 0; j < 8; j++) {
+            uint32_t f = kb::from_mont(kb::pow(w16, j)), b = kb::from_mont(kb::pow(w16i, j));
+            h16[0][j] = {f, (uint32_t)(((uint64_t)f << 32) / kb::P)};
+            h16[1][j] = {b, (uint32_t)(((uint64_t)b << 32) / kb::P)};
+        }
+        CU(cudaMemcpyToSymbolAsync(ntt2::c_w16, h16, sizeof h16, 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CU(cudaFuncSetAttribute(nttk::k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << (nttk::GMAX + nttk::LANES_LOG)));
     CU(cudaFuncSetAttribute(nttk::k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << (nttk::GMAX + nttk::LANES_LOG)));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -189,6 +238,13 @@ extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
     if (!ctx) return;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
+    trim_cache(ctx);
+    for (auto& kv : ctx->live) cudaFree(kv.first);
+    for (auto& kv : ctx->plans)
+        for (auto& ps : kv.second) {
+            if (ps.twA) cudaFree(ps.twA);
+            if (ps.twB) cudaFree(ps.twB);
+        }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -361,11 +417,9 @@ static int32_t check_mat(bfgpu_ctx* ctx, const bfgpu_mat* m, bool need_pow2) {
 }
 
 // ---- NTT orchestration ----------------------------------------------------------------------------
-// Run all stages of a size-2^log_n transform on `ncols` column vectors (stride col_stride words).
+// Fallback for short columns (< 2^12): shared-memory radix-2 passes (kernels_ntt.cuh).
 template <bool INVERSE>
-static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols) {
-    if (log_n == 0 || ncols == 0) return BFGPU_OK;
-    Phase ph(ctx, INVERSE ? BFGPU_PHASE_INTT : BFGPU_PHASE_NTT);
+static int32_t run_ntt_small(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols) {
     unsigned npass = (log_n + nttk::GMAX - 1) / nttk::GMAX;
     unsigned base = log_n / npass, extra = log_n % npass;
     unsigned g[8], p[8];
@@ -382,6 +436,78 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
         dim3 grid(1u << (log_n - g[i] - lanes_log), ncols);
         size_t smem = (size_t)4 << (g[i] + lanes_log);
         nttk::k_ntt_pass<INVERSE><<<grid, nttk::NTT_THREADS, smem, ctx->stream>>>(data, col_stride, log_n, p[i], g[i], lanes_log, ctx->d_tw);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+    }
+    return BFGPU_OK;
+}
+
+// Pass plan + twiddle tables of the radix-16 kernels for columns of 2^log_n points (cached).
+static int32_t get_plan(bfgpu_ctx* ctx, unsigned log_n, bool inverse, const std::vector<bfgpu_ctx::NttPass>** out) {
+    auto key = std::make_pair(log_n, inverse);
+    auto it = ctx->plans.find(key);
+    if (it == ctx->plans.end()) {
+        std::vector<bfgpu_ctx::NttPass> passes;
+        unsigned npass = (log_n + 7) / 8, base = log_n / npass, extra = log_n % npass, acc = 0;
+        uint32_t wmax = kb::two_adic_generator(kb::TWO_ADICITY);
+        for (unsigned i = 0; i < npass; i++) {
+            bfgpu_ctx::NttPass ps{acc, base + (i < extra ? 1 : 0), nullptr, nullptr};
+            acc += ps.g;
+            unsigned G1 = ps.g - 4;
+            if (G1 > 0) {
+                uint32_t nq = (1u << G1) - 1, M = 1u << (ps.p + 4);
+                CU(cudaMalloc(&ps.twA, (size_t)nq * M * sizeof(ntt2::Tw)));
+                uint64_t total = (uint64_t)nq * M;
+                ntt2::k_build_tw<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ps.twA, nq, M, ps.p + ps.g, inverse, wmax);
+                LAUNCHED(ctx);
+            }
+            if (ps.p > 0) {
+                uint32_t nq = 15, M = 1u << ps.p;
+                CU(cudaMalloc(&ps.twB, (size_t)nq * M * sizeof(ntt2::Tw)));
+                uint64_t total = (uint64_t)nq * M;
+                ntt2::k_build_tw<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ps.twB, nq, M, ps.p + 4, inverse, wmax);
+                LAUNCHED(ctx);
+            }
+            CU(cudaGetLastError());
+            passes.push_back(ps);
+        }
+        it = ctx->plans.emplace(key, std::move(passes)).first;
+    }
+    *out = &it->second;
+    return BFGPU_OK;
+}
+
+template <bool INVERSE, int G1>
+static void launch_pass(bfgpu_ctx* ctx, const ntt2::PassArgs& a, dim3 grid) {
+    ntt2::k_pass<INVERSE, G1><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
+}
+
+// Run all stages of a size-2^log_n transform on `ncols` column vectors (stride col_stride words).
+template <bool INVERSE>
+static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols) {
+    if (log_n == 0 || ncols == 0) return BFGPU_OK;
+    Phase ph(ctx, INVERSE ? BFGPU_PHASE_INTT : BFGPU_PHASE_NTT);
+    if (log_n < 12) return run_ntt_small<INVERSE>(ctx, data, col_stride, log_n, ncols);
+    const std::vector<bfgpu_ctx::NttPass>* plan = nullptr;
+    TRY(get_plan(ctx, log_n, INVERSE, &plan));
+    size_t np = plan->size();
+    for (size_t s = 0; s < np; s++) {
+        const auto& ps = (*plan)[INVERSE ? s : np - 1 - s];  // inverse DIT: low bits first; forward DIF: high bits first
+        uint32_t tiles = 1u << (log_n - ps.g - 4);
+        // enough CTAs to fill the machine several times, but >= 8 columns per CTA to amortise the twiddle loads
+        uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
+        uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, ncols), (ncols + want_groups - 1) / want_groups);
+        cpc = std::min<uint32_t>(cpc, 64);
+        ntt2::PassArgs a{data, col_stride, ncols, cpc, ps.p, ps.p != 0 ? 1u : 0u, ps.twA, ps.twB};
+        dim3 grid(tiles, (ncols + cpc - 1) / cpc);
+        switch (ps.g - 4) {
+            case 0: launch_pass<INVERSE, 0>(ctx, a, grid); break;
+            case 1: launch_pass<INVERSE, 1>(ctx, a, grid); break;
+            case 2: launch_pass<INVERSE, 2>(ctx, a, grid); break;
+            case 3: launch_pass<INVERSE, 3>(ctx, a, grid); break;
+            case 4: launch_pass<INVERSE, 4>(ctx, a, grid); break;
+            default: return fail(ctx, BFGPU_ERR_STATE, "internal: bad pass size %u", ps.g);
+        }
         LAUNCHED(ctx);
         CU(cudaGetLastError());
     }

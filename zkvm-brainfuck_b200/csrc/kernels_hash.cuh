@@ -19,17 +19,18 @@ constexpr int HASH_THREADS = 128;
 // absorb the r-th row of the column list (overwrite-mode sponge, rate 8) into state s
 __device__ __forceinline__ void sponge_rows(uint32_t (&s)[16], const uint32_t* const* __restrict__ colptr, uint32_t ncols,
                                             uint64_t r) {
-    uint32_t c0 = 0;
-    for (; c0 + 8 <= ncols; c0 += 8) {
+    // single permute() call site (the permutation body must stay small enough for the I-cache);
+    // the last block may be partial: it overwrites only its prefix of the state
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < ncols; c0 += 8) {
+        if (c0 + 8 <= ncols) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) s[k] = __ldg(colptr[c0 + k] + r);
-        p2::permute(s);
-    }
-    uint32_t rem = ncols - c0;
-    if (rem) {
+            for (int k = 0; k < 8; k++) s[k] = __ldg(colptr[c0 + k] + r);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            if ((uint32_t)k < rem) s[k] = __ldg(colptr[c0 + k] + r);
+            for (int k = 0; k < 8; k++)
+                if (c0 + k < ncols) s[k] = __ldg(colptr[c0 + k] + r);
+        }
         p2::permute(s);
     }
 }

@@ -72,7 +72,38 @@ KB_D void internal_linear(uint32_t (&s)[16]) {
     for (int i = 9; i < 16; i++) s[i] = add(mul(s[i], c_p2.diag[i]), sum);
 }
 
+// Rounds are kept as rolled loops on purpose: the fully unrolled permutation is ~64 KB of SASS and
+// stalls on instruction fetch (ncu: stalled_no_instruction dominant, profiles/r1_leaf_hash_v1.md);
+// one external-round body + one internal-round body stay resident in the instruction cache.
+// BARRIER: __syncthreads() at every round boundary keeps the warps of a CTA at the same PC so that
+// they share instruction-cache lines (all threads of the CTA must call permute the same number of
+// times).
+template <bool BARRIER = false>
 KB_D void permute(uint32_t (&s)[16]) {
+    external_linear(s);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            const uint32_t* rc = c_p2.ext[half * 4 + r];
+            if (BARRIER) __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 16; i++) s[i] = sbox(add(s[i], rc[i]));
+            external_linear(s);
+        }
+        if (half == 0) {
+#pragma unroll 1
+            for (int r = 0; r < 13; r++) {
+                if (BARRIER) __syncthreads();
+                s[0] = sbox(add(s[0], c_p2.internal[r]));
+                internal_linear(s);
+            }
+        }
+    }
+}
+
+// fully unrolled variant (kept for the instruction-cache experiment in tools/p2_bench.cu)
+KB_D void permute_unrolled(uint32_t (&s)[16]) {
     external_linear(s);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
