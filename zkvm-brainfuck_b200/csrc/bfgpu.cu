@@ -210,6 +210,10 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
         uint32_t d[16] = {small(-2), small(1), small(2), frac(1, 1), small(3), small(4), frac(-1, 1), small(-3),
                           small(-4), frac(1, 8), frac(1, 3), frac(1, 24), frac(-1, 8), frac(-1, 3), frac(-1, 4), frac(-1, 24)};
         memcpy(h.diag, d, sizeof d);
+        for (int i = 0; i < 16; i++) {
+            h.diag_w[i] = kb::from_mont(d[i]);
+            h.diag_wp[i] = (uint32_t)(((uint64_t)h.diag_w[i] << 32) / kb::P);
+        }
     }
     CU(cudaMemcpyToSymbolAsync(p2::c_p2, &h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -483,11 +487,19 @@ static void launch_pass(bfgpu_ctx* ctx, const ntt2::PassArgs& a, dim3 grid) {
 }
 
 // Run all stages of a size-2^log_n transform on `ncols` column vectors (stride col_stride words).
+// Fused coset epilogue (inverse only, log_n >= NTT2_MIN_LOG): see ntt2::PassArgs::pw.
+struct CosetEpilogue {
+    const uint32_t* pw = nullptr;
+    uint32_t* out = nullptr;
+    uint32_t ncosets = 0;
+};
+constexpr unsigned NTT2_MIN_LOG = 12;
+
 template <bool INVERSE>
-static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols) {
+static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols, CosetEpilogue epi = CosetEpilogue()) {
     if (log_n == 0 || ncols == 0) return BFGPU_OK;
     Phase ph(ctx, INVERSE ? BFGPU_PHASE_INTT : BFGPU_PHASE_NTT);
-    if (log_n < 12) return run_ntt_small<INVERSE>(ctx, data, col_stride, log_n, ncols);
+    if (log_n < NTT2_MIN_LOG) return run_ntt_small<INVERSE>(ctx, data, col_stride, log_n, ncols);
     const std::vector<bfgpu_ctx::NttPass>* plan = nullptr;
     TRY(get_plan(ctx, log_n, INVERSE, &plan));
     size_t np = plan->size();
@@ -498,7 +510,12 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
         uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
         uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, ncols), (ncols + want_groups - 1) / want_groups);
         cpc = std::min<uint32_t>(cpc, 64);
-        ntt2::PassArgs a{data, col_stride, ncols, cpc, ps.p, ps.p != 0 ? 1u : 0u, ps.twA, ps.twB};
+        ntt2::PassArgs a{data, col_stride, ncols, cpc, ps.p, ps.p != 0 ? 1u : 0u, ps.twA, ps.twB, nullptr, nullptr, 0, log_n};
+        if (INVERSE && s + 1 == np && epi.pw) {
+            a.pw = epi.pw;
+            a.out = epi.out;
+            a.ncosets = epi.ncosets;
+        }
         dim3 grid(tiles, (ncols + cpc - 1) / cpc);
         switch (ps.g - 4) {
             case 0: launch_pass<INVERSE, 0>(ctx, a, grid); break;
@@ -523,11 +540,10 @@ static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bit
     uint32_t ncosets = 1u << added_bits;
     DMat coef;
     TRY(ingest(ctx, m, /*bitrev=*/true, &coef));
-    TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols));
+    // per-coset scale vectors: pw[h*n + k] = (shift * w_N^{bitrev(h)})^k / n
+    uint32_t* pw = nullptr;
     {
-        // per-coset scale vectors: pw[h*n + k] = (shift * w_N^{bitrev(h)})^k / n
         Phase ph(ctx, BFGPU_PHASE_SCALE);
-        uint32_t* pw = nullptr;
         TRY(dalloc(ctx, (void**)&pw, N * 4));
         uint32_t ninv = kb::inv(kb::to_mont((uint32_t)(n % kb::P)));
         uint32_t wN = kb::two_adic_generator(log_n + added_bits);
@@ -537,16 +553,27 @@ static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bit
             LAUNCHED(ctx);
         }
         CU(cudaGetLastError());
-        out->rows = N;
-        out->cols = coef.cols;
-        TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
+    }
+    out->rows = N;
+    out->cols = coef.cols;
+    TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
+    if (log_n >= NTT2_MIN_LOG) {
+        // scaling and 2^added_bits-fold expansion fused into the last inverse pass
+        CosetEpilogue epi;
+        epi.pw = pw;
+        epi.out = out->d;
+        epi.ncosets = ncosets;
+        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols, epi));
+    } else {
+        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols));
+        Phase ph(ctx, BFGPU_PHASE_SCALE);
         dim3 grid((unsigned)((n + 255) / 256), coef.cols);
         nttk::k_scale_cosets<<<grid, 256, 0, ctx->stream>>>(coef.d, out->d, pw, n, ncosets, coef.cols);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
-        dfree(ctx, coef.d);
-        dfree(ctx, pw);
     }
+    dfree(ctx, coef.d);
+    dfree(ctx, pw);
     TRY(run_ntt<false>(ctx, out->d, n, log_n, coef.cols * ncosets));
     return BFGPU_OK;
 }

@@ -131,6 +131,13 @@ struct PassArgs {
     uint32_t strided;     // p != 0
     const Tw* twA;        // [(2^G1 - 1)][2^(p+4)]  exponent q*m, transform size 2^(p+g)
     const Tw* twB;        // [15][2^p]              exponent q*lo, transform size 2^(p+4); null when p == 0
+    // optional fused epilogue of the LAST inverse pass (coset scaling + blow-up): when pw != null the
+    // result is not written back in place but as out[c][h*n + k] = x[k] * pw[h*n + k] for h < ncosets
+    // (pw = (shift_h)^k / n in Montgomery form), out columns being ncosets*n words long.
+    const uint32_t* pw;
+    uint32_t* out;
+    uint32_t ncosets;
+    uint32_t log_n;
 };
 
 // G1 in 0..4 (g = G1 + 4).  Threads per CTA = 2^g.
@@ -177,24 +184,41 @@ __global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
     const uint32_t c_end = min(A.ncols, c_begin + A.cols_per_cta);
     uint32_t v[16];
     int buf = 0;
-    for (uint32_t c = c_begin; c < c_end; c++, buf ^= 1) {
-        uint32_t* col = A.data + (uint64_t)c * A.col_stride + base;
-        uint32_t* s = sm[buf];
-        // ---- stage in (coalesced): element f of the tile ---------------------------------------
+    // Software pipeline: the tile of column c+1 is loaded into registers (nx) while column c is being
+    // transformed, so HBM latency overlaps the butterflies inside one CTA.  (cp.async 4-byte LDGSTS
+    // was measured slower: 16 LDGSTS per thread per column saturate the LSU issue rate.)
+    uint32_t nx[16];
+    auto load_tile = [&](uint32_t c) {
+        const uint32_t* col = A.data + (uint64_t)c * A.col_stride + base;
         if (A.strided) {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 uint32_t f = t + i * NT;  // d = f >> 4, lane = f & 15
-                s[(f >> 4) * ROW + (f & 15)] = col[((uint64_t)(f >> 4) << p) + (f & 15)];
+                nx[i] = col[((uint64_t)(f >> 4) << p) + (f & 15)];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) nx[i] = col[t + i * NT];  // lane = f >> g, d = f & (NT-1)
+        }
+    };
+    if (c_begin < c_end) load_tile(c_begin);
+    for (uint32_t c = c_begin; c < c_end; c++, buf ^= 1) {
+        uint32_t* s = sm[buf];
+        if (A.strided) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint32_t f = t + i * NT;
+                s[(f >> 4) * ROW + (f & 15)] = nx[i];
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                uint32_t f = t + i * NT;  // lane = f >> g, d = f & (NT-1)
-                s[(f & (NT - 1)) * ROW + (f >> g)] = col[f];
+                uint32_t f = t + i * NT;
+                s[(f & (NT - 1)) * ROW + (f >> g)] = nx[i];
             }
         }
-        __syncthreads();
+        if (c + 1 < c_end) load_tile(c + 1);
+        __syncthreads();  // tile c visible (double buffering: iteration c-1 read the other buffer)
         // forward: phase A (high bits) then B; inverse: B then A
 #pragma unroll
         for (int ph = 0; ph < 2; ph++) {
@@ -227,23 +251,35 @@ __global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
 #pragma unroll
                 for (int b = 0; b < 16; b++) s[((a << G2) | b) * ROW + lane] = v[b];
             }
-            __syncthreads();
+            if (G1 > 0 || ph == 1 || !INV) __syncthreads();
         }
         // ---- stage out ----------------------------------------------------------------------------
-        if (A.strided) {
+        if (INV && A.pw != nullptr) {
+            const uint64_t n = 1ull << A.log_n;
+            uint32_t* ocol = A.out + (uint64_t)c * (n * A.ncosets);
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 uint32_t f = t + i * NT;
-                col[((uint64_t)(f >> 4) << p) + (f & 15)] = s[(f >> 4) * ROW + (f & 15)];
+                uint64_t idx = A.strided ? base + ((uint64_t)(f >> 4) << p) + (f & 15) : base + f;
+                uint32_t x = A.strided ? s[(f >> 4) * ROW + (f & 15)] : s[(f & (NT - 1)) * ROW + (f >> g)];
+                for (uint32_t h = 0; h < A.ncosets; h++) ocol[h * n + idx] = kb::mul(x, __ldg(A.pw + h * n + idx));
             }
         } else {
+            uint32_t* col = A.data + (uint64_t)c * A.col_stride + base;
+            if (A.strided) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                uint32_t f = t + i * NT;
-                col[f] = s[(f & (NT - 1)) * ROW + (f >> g)];
+                for (int i = 0; i < 16; i++) {
+                    uint32_t f = t + i * NT;
+                    col[((uint64_t)(f >> 4) << p) + (f & 15)] = s[(f >> 4) * ROW + (f & 15)];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    uint32_t f = t + i * NT;
+                    col[f] = s[(f & (NT - 1)) * ROW + (f >> g)];
+                }
             }
         }
-        // next iteration writes the other buffer; the two barriers above order its reuse
     }
 }
 

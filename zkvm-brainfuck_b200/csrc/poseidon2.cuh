@@ -15,7 +15,9 @@ namespace p2 {
 struct Consts {
     uint32_t ext[8][16];    // external rounds: 0..3 initial, 4..7 terminal (Montgomery form)
     uint32_t internal[16];  // 13 used
-    uint32_t diag[16];      // internal diagonal V (Montgomery form), see internal_linear()
+    uint32_t diag[16];      // internal diagonal V (Montgomery form), kept for reference/tests
+    uint32_t diag_w[16];    // V as plain residues and
+    uint32_t diag_wp[16];   // their Shoup quotients floor(V * 2^32 / p): x~ * V = (x V)~ without a Montgomery reduction
 };
 
 #if defined(__CUDACC__)
@@ -27,7 +29,25 @@ using kb::dbl;
 using kb::mul;
 using kb::sub;
 
-KB_D uint32_t sbox(uint32_t x) { return mul(mul(x, x), x); }
+// x^3 with one correction instead of two: the square is left in (-p, p) and the second product is a
+// signed Montgomery product (|x2 * x| < p^2 < 2^31 p keeps the result in (-p, p)).
+KB_D uint32_t sbox(uint32_t x) {
+    uint64_t t = (uint64_t)x * x;
+    uint32_t m = (uint32_t)t * kb::PINV;
+    uint32_t u = __umulhi(m, kb::P);
+    int32_t x2 = (int32_t)((uint32_t)(t >> 32) - u);
+    int64_t t2 = (int64_t)x2 * (int32_t)x;
+    int32_t m2 = (int32_t)((uint32_t)t2 * kb::PINV);
+    int32_t u2 = __mulhi(m2, (int32_t)kb::P);
+    uint32_t r = (uint32_t)((int32_t)(t2 >> 32) - u2);
+    return kb::umin_(r, r + kb::P);
+}
+// x * V[i] via Shoup's precomputed quotient (IMAD.HI + 2 IMAD + one min)
+KB_D uint32_t mul_diag(uint32_t x, int i) {
+    uint32_t q = __umulhi(x, c_p2.diag_wp[i]);
+    uint32_t r = x * c_p2.diag_w[i] - q * kb::P;
+    return kb::umin_(r, r - kb::P);
+}
 
 // M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]]
 KB_D void mat4(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
@@ -69,7 +89,7 @@ KB_D void internal_linear(uint32_t (&s)[16]) {
     s[7] = sub(sum, add(dbl(s[7]), s[7]));
     s[8] = sub(sum, dbl(dbl(s[8])));
 #pragma unroll
-    for (int i = 9; i < 16; i++) s[i] = add(mul(s[i], c_p2.diag[i]), sum);
+    for (int i = 9; i < 16; i++) s[i] = add(mul_diag(s[i], i), sum);
 }
 
 // Rounds are kept as rolled loops on purpose: the fully unrolled permutation is ~64 KB of SASS and
