@@ -86,7 +86,14 @@ enum {
     BFGPU_PHASE_LEAF = 5,     /* Poseidon2 sponge over LDE rows (first digest layer)           */
     BFGPU_PHASE_COMPRESS = 6, /* Poseidon2 2-to-1 compression layers (+ injected rows)         */
     BFGPU_PHASE_OTHER = 7,
-    BFGPU_NUM_PHASES = 8
+    BFGPU_PHASE_OPEN_EVAL = 8,   /* barycentric evaluation of all columns at the opening points     */
+    BFGPU_PHASE_OPEN_REDUCE = 9, /* per-height reduced openings                                     */
+    BFGPU_PHASE_FRI = 10,        /* FRI commit phase: fold + Merkle commit per round                */
+    BFGPU_PHASE_POW = 11,        /* proof-of-work grind                                             */
+    BFGPU_PHASE_QUERY = 12,      /* query gathers                                                   */
+    BFGPU_PHASE_PERM = 13,       /* LogUp permutation trace                                         */
+    BFGPU_PHASE_QUOTIENT = 14,   /* quotient values                                                 */
+    BFGPU_NUM_PHASES = 16
 };
 /* start (on != 0, clears the accumulators) or stop collecting per-phase timings */
 int32_t bfgpu_profile_enable(bfgpu_ctx* ctx, int on);
@@ -143,6 +150,49 @@ int32_t bfgpu_pcs_lde_dims(const bfgpu_pcs_data* data, int32_t idx, uint64_t* ro
 int32_t bfgpu_pcs_get_evaluations(bfgpu_pcs_data* data, int32_t idx, int bit_reversed_rows, uint32_t* out);
 bfgpu_tree* bfgpu_pcs_tree(bfgpu_pcs_data* data); /* borrowed; freed with the pcs data */
 void bfgpu_pcs_data_free(bfgpu_pcs_data* data);
+
+/* ---- Challenger = DuplexChallenger<Val, Perm, 16, 8> (kb31_poseidon2.rs:31,126-128) ------------ */
+/* Host-side sponge (the transcript is sequential and tiny); the library advances it exactly as the
+ * reference's prover does (prover.rs:266-272,337-340,354,412-415,595-601 and inside Pcs::open).  A
+ * Rust shim keeps its own DuplexChallenger authoritative by copying the public fields
+ * (sponge_state, input_buffer, output_buffer) in and out with the import/export calls. */
+typedef struct bfgpu_challenger bfgpu_challenger;
+int32_t bfgpu_challenger_create(bfgpu_ctx* ctx, bfgpu_challenger** out);
+int32_t bfgpu_challenger_clone(const bfgpu_challenger* ch, bfgpu_challenger** out);
+void bfgpu_challenger_free(bfgpu_challenger* ch);
+int32_t bfgpu_challenger_observe(bfgpu_challenger* ch, const uint32_t* values, uint64_t n);
+int32_t bfgpu_challenger_sample(bfgpu_challenger* ch, uint32_t* out, uint64_t n); /* n base samples (4 = one ext element) */
+int32_t bfgpu_challenger_sample_bits(bfgpu_challenger* ch, uint32_t bits, uint32_t* out);
+/* state = 16 words, input/output buffers up to 8 words each (caller representation) */
+int32_t bfgpu_challenger_export(const bfgpu_challenger* ch, uint32_t state[16], uint32_t input[8], uint32_t* n_input,
+                                uint32_t output[8], uint32_t* n_output);
+int32_t bfgpu_challenger_import(bfgpu_challenger* ch, const uint32_t state[16], const uint32_t* input, uint32_t n_input,
+                                const uint32_t* output, uint32_t n_output);
+
+/* ---- Pcs::open (prover.rs:460-470) ---------------------------------------------------------------- */
+/* One entry per commitment ("round"): the prover data and, for every matrix of that commitment in
+ * commit order, its opening points (num_points[i] extension elements, 4 words each, concatenated). */
+typedef struct {
+    bfgpu_pcs_data* data;
+    const uint32_t* num_points;
+    const uint32_t* points;
+} bfgpu_open_round;
+typedef struct bfgpu_opening bfgpu_opening; /* OpenedValues + FriProof */
+/* Evaluates every column at its points (barycentric, low coset), observes the opened values,
+ * samples alpha, builds the per-height reduced openings, runs the FRI commit phase (fold + commit per
+ * round, roots observed / betas sampled on `ch`), grinds the proof of work (the smallest witness; any
+ * valid one is accepted by the verifier; pass fixed_pow_witness >= 0 to reuse a known one) and answers
+ * the queries. */
+int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int32_t n_rounds, bfgpu_challenger* ch,
+                       int64_t fixed_pow_witness, bfgpu_opening** out);
+/* Flat u32 serialisation (caller representation):
+ *   for round, matrix, point: width x 4 words of opened values
+ *   n_commit_phase_commits, then 8 words per commit; final_poly (4); pow_witness (1, canonical); n_queries
+ *   per query: index; per round: opened row of every matrix (sum of widths), siblings (8 x log2(max height));
+ *              per FRI layer i: sibling_value (4), opening proof (8 x log2(layer leaves)) */
+uint64_t bfgpu_opening_size(const bfgpu_opening* o);
+int32_t bfgpu_opening_read(const bfgpu_opening* o, uint32_t* out);
+void bfgpu_opening_free(bfgpu_opening* o);
 
 #ifdef __cplusplus
 }

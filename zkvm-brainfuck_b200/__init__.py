@@ -70,7 +70,23 @@ ABI = {
     "bfgpu_pcs_get_evaluations": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]),
     "bfgpu_pcs_tree": (C.c_void_p, [C.c_void_p]),
     "bfgpu_pcs_data_free": (None, [C.c_void_p]),
+    "bfgpu_challenger_create": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bfgpu_challenger_clone": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bfgpu_challenger_free": (None, [C.c_void_p]),
+    "bfgpu_challenger_observe": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "bfgpu_challenger_sample": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "bfgpu_challenger_sample_bits": (C.c_int32, [C.c_void_p, C.c_uint32, _u32p]),
+    "bfgpu_challenger_export": (C.c_int32, [C.c_void_p, _u32p, _u32p, _u32p, _u32p, _u32p]),
+    "bfgpu_challenger_import": (C.c_int32, [C.c_void_p, _u32p, _u32p, C.c_uint32, _u32p, C.c_uint32]),
+    "bfgpu_pcs_open": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "bfgpu_opening_size": (C.c_uint64, [C.c_void_p]),
+    "bfgpu_opening_read": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_opening_free": (None, [C.c_void_p]),
 }
+
+
+class OpenRound(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("num_points", _u32p), ("points", _u32p)]
 
 
 def lib():
@@ -130,15 +146,16 @@ class Context:
     def synchronize(self):
         self.check(lib().bfgpu_synchronize(self._h))
 
-    PHASES = ["h2d", "ingest", "intt", "scale", "ntt", "leaf_hash", "compress", "other"]
+    PHASES = ["h2d", "ingest", "intt", "scale", "ntt", "leaf_hash", "compress", "other", "open_eval", "open_reduce", "fri",
+              "pow", "query", "perm", "quotient", "reserved"]
 
     def profile_enable(self, on=True):
         self.check(lib().bfgpu_profile_enable(self._h, 1 if on else 0))
 
     def profile_read(self):
         """-> {phase: (milliseconds, launches)} accumulated since profile_enable(True)."""
-        ms = (C.c_float * 8)()
-        ln = (C.c_uint64 * 8)()
+        ms = (C.c_float * 16)()
+        ln = (C.c_uint64 * 16)()
         self.check(lib().bfgpu_profile_read(self._h, ms, ln))
         return {n: (float(ms[i]), int(ln[i])) for i, n in enumerate(self.PHASES)}
 
@@ -288,8 +305,123 @@ class PcsProverData:
         self.free()
 
 
+class Challenger:
+    """DuplexChallenger<Val, Perm, 16, 8> (kb31_poseidon2.rs:31); host-side sponge inside the library."""
+
+    def __init__(self, ctx, _handle=None):
+        self.ctx = ctx
+        if _handle is None:
+            _handle = C.c_void_p()
+            ctx.check(lib().bfgpu_challenger_create(ctx._h, C.byref(_handle)))
+        self._h = _handle
+
+    def clone(self):
+        h = C.c_void_p()
+        self.ctx.check(lib().bfgpu_challenger_clone(self._h, C.byref(h)))
+        return Challenger(self.ctx, h)
+
+    def observe(self, v):
+        self.observe_slice([v])
+
+    def observe_slice(self, vs):
+        a = _u32(np.asarray(vs).ravel())
+        self.ctx.check(lib().bfgpu_challenger_observe(self._h, _ptr(a), a.size))
+
+    observe_digest = observe_slice
+    observe_ext = observe_slice
+
+    def sample(self):
+        out = np.zeros(1, np.uint32)
+        self.ctx.check(lib().bfgpu_challenger_sample(self._h, _ptr(out), 1))
+        return int(out[0])
+
+    def sample_ext(self):
+        out = np.zeros(4, np.uint32)
+        self.ctx.check(lib().bfgpu_challenger_sample(self._h, _ptr(out), 4))
+        return out.astype(np.uint64)
+
+    def sample_bits(self, bits):
+        out = C.c_uint32()
+        self.ctx.check(lib().bfgpu_challenger_sample_bits(self._h, bits, C.byref(out)))
+        return out.value
+
+    def export(self):
+        st, ib, ob = np.zeros(16, np.uint32), np.zeros(8, np.uint32), np.zeros(8, np.uint32)
+        ni, no = C.c_uint32(), C.c_uint32()
+        self.ctx.check(lib().bfgpu_challenger_export(self._h, st.ctypes.data_as(_u32p), ib.ctypes.data_as(_u32p), C.byref(ni),
+                                                     ob.ctypes.data_as(_u32p), C.byref(no)))
+        return st, ib[:ni.value].copy(), ob[:no.value].copy()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().bfgpu_challenger_free(self._h)
+            self._h = None
+
+
 class TwoAdicFriPcs:
-    """Pcs (kb31_poseidon2.rs:32): commit / get_evaluations_on_domain (open: later rounds)."""
+    """Pcs (kb31_poseidon2.rs:32): commit / get_evaluations_on_domain / open."""
+
+    def open(self, rounds, challenger, pow_witness=None):
+        """`pcs.open(vec![(&data, points), ...], &mut challenger)` (prover.rs:460-470).
+        rounds: [(PcsProverData, [[ext point, ...] per matrix])].  Returns (opened_values, fri_proof) in the
+        nested as opened[round][matrix][point] -> (width, 4) and a FriProof-shaped dict."""
+        n = len(rounds)
+        arr = (OpenRound * n)()
+        keep = []
+        for i, (data, points) in enumerate(rounds):
+            assert len(points) == len(data.dims)
+            npts = _u32([len(p) for p in points])
+            flat = _u32(np.concatenate([np.asarray(z, np.uint64).ravel() for p in points for z in p]) if any(len(p) for p in points) else np.zeros(0))
+            keep += [npts, flat]
+            arr[i] = OpenRound(data._h, npts.ctypes.data_as(_u32p), flat.ctypes.data_as(_u32p))
+        h = C.c_void_p()
+        self.ctx.check(lib().bfgpu_pcs_open(self.ctx._h, arr, n, challenger._h, -1 if pow_witness is None else int(pow_witness), C.byref(h)))
+        size = lib().bfgpu_opening_size(h)
+        buf = np.zeros(size, np.uint32)
+        self.ctx.check(lib().bfgpu_opening_read(h, _ptr(buf)))
+        lib().bfgpu_opening_free(h)
+        return self._parse_opening(buf, rounds)
+
+    @staticmethod
+    def _parse_opening(buf, rounds):
+        pos = 0
+
+        def take(k):
+            nonlocal pos
+            v = buf[pos:pos + k]
+            pos += k
+            return v
+
+        opened = []
+        for data, points in rounds:
+            rv = []
+            for (rows, cols), pts in zip(data.dims, points):
+                rv.append([take(cols * 4).astype(np.uint64).reshape(cols, 4) for _ in pts])
+            opened.append(rv)
+        ncommit = int(take(1)[0])
+        commits = [take(8).copy() for _ in range(ncommit)]
+        final_poly = take(4).astype(np.uint64)
+        pow_witness = int(take(1)[0])
+        nq = int(take(1)[0])
+        log_blowup = 1
+        log_max_height = ncommit + log_blowup
+        queries = []
+        for _ in range(nq):
+            index = int(take(1)[0])
+            input_proof = []
+            for data, _pts in rounds:
+                log_max_h = max(r for r, _ in data.dims).bit_length() - 1
+                rows = [take(c).copy() for _, c in data.dims]
+                sib = take(8 * log_max_h).reshape(log_max_h, 8).copy()
+                input_proof.append(dict(opened_values=rows, opening_proof=sib))
+            steps = []
+            for i in range(ncommit):
+                sv = take(4).astype(np.uint64)
+                nl = log_max_height - 1 - i
+                steps.append(dict(sibling_value=sv, opening_proof=take(8 * nl).reshape(nl, 8).copy()))
+            queries.append(dict(index=index, input_proof=input_proof, commit_phase_openings=steps))
+        assert pos == len(buf), (pos, len(buf))
+        return opened, dict(commit_phase_commits=commits, query_proofs=queries, final_poly=final_poly, pow_witness=pow_witness)
 
     def __init__(self, ctx):
         self.ctx = ctx

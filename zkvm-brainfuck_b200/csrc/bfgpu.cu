@@ -27,10 +27,12 @@
 #include <unordered_map>
 
 // ------------------------------------------------------------------------------------------------
-struct DMat {  // column-major device matrix, Montgomery words
+struct DMat {  // device matrix, Montgomery words; element (r, c) = d[r * rs + c * col_stride()]
     uint32_t* d = nullptr;
     uint64_t rows = 0;
     uint32_t cols = 0;
+    uint32_t rs = 1;  // 1: column-major (the default everywhere); cols: row-major (FRI layer matrices)
+    uint64_t col_stride() const { return rs == 1 ? rows : 1; }
 };
 
 struct bfgpu_ctx {
@@ -653,7 +655,7 @@ extern "C" int32_t bfgpu_poseidon2_permute(bfgpu_ctx* ctx, uint32_t* states, uin
 static int32_t make_colptr(bfgpu_ctx* ctx, const std::vector<const DMat*>& mats, const uint32_t*** d_out, uint32_t* ncols_out) {
     std::vector<const uint32_t*> h;
     for (const DMat* m : mats)
-        for (uint32_t c = 0; c < m->cols; c++) h.push_back(m->d + (uint64_t)c * m->rows);
+        for (uint32_t c = 0; c < m->cols; c++) h.push_back(m->d + (uint64_t)c * m->col_stride());
     *ncols_out = (uint32_t)h.size();
     TRY(dalloc(ctx, (void**)d_out, h.size() * sizeof(void*)));
     if (!h.empty()) CU(cudaMemcpyAsync((void*)*d_out, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
@@ -670,7 +672,7 @@ extern "C" int32_t bfgpu_sponge_hash_rows(bfgpu_ctx* ctx, const bfgpu_mat* mat, 
     TRY(make_colptr(ctx, {&d}, &colptr, &ncols));
     uint32_t* out = nullptr;
     TRY(dalloc(ctx, (void**)&out, d.rows * 32));
-    hashk::k_leaf_hash<<<(unsigned)((d.rows + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(colptr, ncols, d.rows, out);
+    hashk::k_leaf_hash<<<(unsigned)((d.rows + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(colptr, ncols, d.rows, out, 1);
     LAUNCHED(ctx);
     CU(cudaGetLastError());
     TRY(convert_inplace(ctx, out, d.rows * 8, false));
@@ -743,7 +745,7 @@ static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfg
         TRY(dalloc(ctx, (void**)&layer, max_h * 32));
         t->layers.push_back(layer);
         t->layer_len.push_back(max_h);
-        hashk::k_leaf_hash<<<(unsigned)((max_h + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(colptr, ncols, max_h, layer);
+        hashk::k_leaf_hash<<<(unsigned)((max_h + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(colptr, ncols, max_h, layer, g[0]->rs);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
         dfree(ctx, (void*)colptr);
@@ -760,7 +762,7 @@ static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfg
         t->layers.push_back(layer);
         t->layer_len.push_back(len);
         hashk::k_compress_layer<<<(unsigned)((len + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(
-            t->layers[l - 1], layer, len, colptr, ncols);
+            t->layers[l - 1], layer, len, colptr, ncols, g.empty() ? 1u : g[0]->rs);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
         dfree(ctx, (void*)colptr);
@@ -804,8 +806,8 @@ extern "C" int32_t bfgpu_mmcs_open_batch(bfgpu_tree* t, uint64_t index, uint32_t
     for (const DMat& m : t->mats) {
         uint64_t r = index >> (t->log_max - ilog2(m.rows));
         for (uint32_t c = 0; c < m.cols; c++) {
-            cp.push_back(m.d + (uint64_t)c * m.rows);
-            ri.push_back(r);
+            cp.push_back(m.d + (uint64_t)c * m.col_stride());
+            ri.push_back(r * m.rs);
         }
     }
     uint32_t nc = (uint32_t)cp.size();
@@ -899,4 +901,444 @@ extern "C" void bfgpu_pcs_data_free(bfgpu_pcs_data* d) {
     tree_release(d->tree);
     for (DMat& m : d->ldes) dfree(d->ctx, m.d);
     delete d;
+}
+
+// =====================================================================================================
+// Challenger + Pcs::open
+// =====================================================================================================
+#include "challenger.h"
+#include "kernels_open.cuh"
+
+#include <array>
+
+// the challenger handle remembers the context only for the caller-representation conversions
+struct bfgpu_challenger_box {
+    bfgpu_challenger ch;
+    bfgpu_ctx* ctx;
+};
+static inline bfgpu_challenger_box* box(bfgpu_challenger* c) { return reinterpret_cast<bfgpu_challenger_box*>(c); }
+static inline const bfgpu_challenger_box* box(const bfgpu_challenger* c) { return reinterpret_cast<const bfgpu_challenger_box*>(c); }
+static inline uint32_t in_word(const bfgpu_ctx* ctx, uint32_t v) { return ctx->repr == BFGPU_REPR_CANONICAL ? kb::to_mont(v % kb::P) : v; }
+static inline uint32_t out_word(const bfgpu_ctx* ctx, uint32_t v) { return ctx->repr == BFGPU_REPR_CANONICAL ? kb::from_mont(v) : v; }
+
+extern "C" int32_t bfgpu_challenger_create(bfgpu_ctx* ctx, bfgpu_challenger** out) {
+    if (!ctx || !out) return BFGPU_ERR_INVALID;
+    auto* b = new bfgpu_challenger_box();
+    b->ctx = ctx;
+    *out = reinterpret_cast<bfgpu_challenger*>(b);
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_challenger_clone(const bfgpu_challenger* ch, bfgpu_challenger** out) {
+    if (!ch || !out) return BFGPU_ERR_INVALID;
+    *out = reinterpret_cast<bfgpu_challenger*>(new bfgpu_challenger_box(*box(ch)));
+    return BFGPU_OK;
+}
+extern "C" void bfgpu_challenger_free(bfgpu_challenger* ch) { delete box(ch); }
+extern "C" int32_t bfgpu_challenger_observe(bfgpu_challenger* ch, const uint32_t* values, uint64_t n) {
+    if (!ch || (!values && n)) return BFGPU_ERR_INVALID;
+    for (uint64_t i = 0; i < n; i++) box(ch)->ch.observe(in_word(box(ch)->ctx, values[i]));
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_challenger_sample(bfgpu_challenger* ch, uint32_t* out, uint64_t n) {
+    if (!ch || !out) return BFGPU_ERR_INVALID;
+    for (uint64_t i = 0; i < n; i++) out[i] = out_word(box(ch)->ctx, box(ch)->ch.sample());
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_challenger_sample_bits(bfgpu_challenger* ch, uint32_t bits, uint32_t* out) {
+    if (!ch || !out || bits > 31) return BFGPU_ERR_INVALID;
+    *out = box(ch)->ch.sample_bits(bits);
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_challenger_export(const bfgpu_challenger* ch, uint32_t state[16], uint32_t input[8], uint32_t* n_input,
+                                           uint32_t output[8], uint32_t* n_output) {
+    if (!ch || !state || !input || !n_input || !output || !n_output) return BFGPU_ERR_INVALID;
+    const auto* b = box(ch);
+    for (int i = 0; i < 16; i++) state[i] = out_word(b->ctx, b->ch.state[i]);
+    *n_input = (uint32_t)b->ch.input.size();
+    for (size_t i = 0; i < b->ch.input.size(); i++) input[i] = out_word(b->ctx, b->ch.input[i]);
+    *n_output = (uint32_t)b->ch.output.size();
+    for (size_t i = 0; i < b->ch.output.size(); i++) output[i] = out_word(b->ctx, b->ch.output[i]);
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_challenger_import(bfgpu_challenger* ch, const uint32_t state[16], const uint32_t* input, uint32_t n_input,
+                                           const uint32_t* output, uint32_t n_output) {
+    if (!ch || !state || n_input > 8 || n_output > 8) return BFGPU_ERR_INVALID;
+    auto* b = box(ch);
+    for (int i = 0; i < 16; i++) b->ch.state[i] = in_word(b->ctx, state[i]);
+    b->ch.input.clear();
+    b->ch.output.clear();
+    for (uint32_t i = 0; i < n_input; i++) b->ch.input.push_back(in_word(b->ctx, input[i]));
+    for (uint32_t i = 0; i < n_output; i++) b->ch.output.push_back(in_word(b->ctx, output[i]));
+    return BFGPU_OK;
+}
+
+struct bfgpu_opening {
+    std::vector<uint32_t> flat;
+};
+extern "C" uint64_t bfgpu_opening_size(const bfgpu_opening* o) { return o ? o->flat.size() : 0; }
+extern "C" int32_t bfgpu_opening_read(const bfgpu_opening* o, uint32_t* out) {
+    if (!o || !out) return BFGPU_ERR_INVALID;
+    memcpy(out, o->flat.data(), o->flat.size() * 4);
+    return BFGPU_OK;
+}
+extern "C" void bfgpu_opening_free(bfgpu_opening* o) { delete o; }
+
+static kb::Ext ext_pow(kb::Ext a, uint64_t e) {
+    kb::Ext r = kb::ext_one();
+    while (e) {
+        if (e & 1) r = kb::ext_mul(r, a);
+        a = kb::ext_sqr(a);
+        e >>= 1;
+    }
+    return r;
+}
+struct ExtKey {
+    unsigned log_h;
+    std::array<uint32_t, 4> z;
+    bool operator<(const ExtKey& o) const { return log_h != o.log_h ? log_h < o.log_h : z < o.z; }
+};
+
+extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int32_t n_rounds, bfgpu_challenger* chh,
+                                  int64_t fixed_pow_witness, bfgpu_opening** out) {
+    if (!ctx || !rounds || n_rounds <= 0 || !chh || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    bfgpu_challenger& ch = box(chh)->ch;
+    const uint32_t gen = kb::to_mont(kb::GEN);
+    const unsigned log_blowup = ctx->log_blowup;
+    auto res = new bfgpu_opening();
+    std::vector<uint32_t>& flat = res->flat;
+    struct Guard {
+        bfgpu_opening* r;
+        bool keep = false;
+        ~Guard() { if (!keep) delete r; }
+    } guard{res};
+
+    // ---- (i) opened values: barycentric evaluation over the low coset of every matrix -----------------
+    struct MatPts {
+        const DMat* m;
+        std::vector<kb::Ext> pts;
+        std::vector<std::vector<kb::Ext>> ys;  // [point][col]
+    };
+    std::vector<std::vector<MatPts>> R(n_rounds);
+    unsigned log_global_max = 0;
+    for (int r = 0; r < n_rounds; r++) {
+        if (!rounds[r].data || !rounds[r].num_points) return fail(ctx, BFGPU_ERR_INVALID, "null round");
+        const uint32_t* pp = rounds[r].points;
+        for (size_t i = 0; i < rounds[r].data->ldes.size(); i++) {
+            MatPts mp;
+            mp.m = &rounds[r].data->ldes[i];
+            for (uint32_t t = 0; t < rounds[r].num_points[i]; t++, pp += 4)
+                mp.pts.push_back(kb::Ext{{in_word(ctx, pp[0]), in_word(ctx, pp[1]), in_word(ctx, pp[2]), in_word(ctx, pp[3])}});
+            log_global_max = std::max(log_global_max, ilog2(mp.m->rows));
+            R[r].push_back(std::move(mp));
+        }
+    }
+    {
+        Phase ph(ctx, BFGPU_PHASE_OPEN_EVAL);
+        std::map<ExtKey, uint32_t*> wcache;
+        auto weights = [&](unsigned log_h, const kb::Ext& z, uint32_t** w) -> int32_t {
+            ExtKey key{log_h, {z.c[0], z.c[1], z.c[2], z.c[3]}};
+            auto it = wcache.find(key);
+            if (it == wcache.end()) {
+                uint32_t* d = nullptr;
+                TRY(dalloc(ctx, (void**)&d, (size_t)16 << log_h));
+                uint32_t h = 1u << log_h;
+                openk::k_bary_weights<<<(h + 255) / 256, 256, 0, ctx->stream>>>(d, log_h, gen, z, ctx->d_tw);
+                LAUNCHED(ctx);
+                CU(cudaGetLastError());
+                it = wcache.emplace(key, d).first;
+            }
+            *w = it->second;
+            return BFGPU_OK;
+        };
+        for (auto& rv : R)
+            for (auto& mp : rv) {
+                const DMat& m = *mp.m;
+                uint32_t h = (uint32_t)(m.rows >> log_blowup);
+                unsigned log_h = ilog2(h);
+                uint32_t nchunks = (h + openk::BARY_ROWS - 1) / openk::BARY_ROWS;
+                mp.ys.resize(mp.pts.size());
+                for (size_t t0 = 0; t0 < mp.pts.size(); t0 += 2) {
+                    uint32_t np = (uint32_t)std::min<size_t>(2, mp.pts.size() - t0);
+                    uint32_t *w0 = nullptr, *w1 = nullptr;
+                    TRY(weights(log_h, mp.pts[t0], &w0));
+                    if (np == 2) TRY(weights(log_h, mp.pts[t0 + 1], &w1));
+                    uint32_t *partial = nullptr, *sums = nullptr;
+                    size_t nsum = (size_t)m.cols * np * 4;
+                    TRY(dalloc(ctx, (void**)&partial, nsum * nchunks * 4));
+                    TRY(dalloc(ctx, (void**)&sums, nsum * 4));
+                    dim3 grid(nchunks, (m.cols + openk::BARY_COLS - 1) / openk::BARY_COLS);
+                    if (np == 1) openk::k_bary_dot<1><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(m.d, m.rows, m.cols, h, w0, w1, partial, nchunks);
+                    else openk::k_bary_dot<2><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(m.d, m.rows, m.cols, h, w0, w1, partial, nchunks);
+                    LAUNCHED(ctx);
+                    openk::k_bary_finish<<<(unsigned)((nsum + 127) / 128), 128, 0, ctx->stream>>>(partial, sums, m.cols, nchunks, np);
+                    LAUNCHED(ctx);
+                    CU(cudaGetLastError());
+                    std::vector<uint32_t> hs(nsum);
+                    CU(cudaMemcpyAsync(hs.data(), sums, nsum * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                    dfree(ctx, partial);
+                    dfree(ctx, sums);
+                    for (uint32_t t = 0; t < np; t++) {
+                        // p(z) = (z^h - s^h) / (h s^(h-1)) * sum
+                        const kb::Ext& z = mp.pts[t0 + t];
+                        kb::Ext zer = ext_pow(z, h);
+                        zer.c[0] = kb::sub(zer.c[0], kb::pow(gen, h));
+                        uint32_t den = kb::mul(kb::pow(gen, h - 1), kb::to_mont(h % kb::P));
+                        kb::Ext scale = kb::ext_scale(zer, kb::inv(den));
+                        auto& ys = mp.ys[t0 + t];
+                        ys.resize(m.cols);
+                        for (uint32_t c = 0; c < m.cols; c++) {
+                            const uint32_t* sp = &hs[((size_t)c * np + t) * 4];
+                            ys[c] = kb::ext_mul(scale, kb::Ext{{sp[0], sp[1], sp[2], sp[3]}});
+                        }
+                    }
+                }
+            }
+        for (auto& kv : wcache) dfree(ctx, kv.second);
+    }
+    // opened values go to the proof and (Plonky3 "write evaluations to challenger") into the transcript
+    for (auto& rv : R)
+        for (auto& mp : rv)
+            for (auto& ys : mp.ys)
+                for (auto& y : ys) {
+                    for (int k = 0; k < 4; k++) flat.push_back(out_word(ctx, y.c[k]));
+                    ch.observe_ext(y);
+                }
+    const kb::Ext alpha = ch.sample_ext();
+
+    // ---- (ii) reduced openings per LDE height ------------------------------------------------------------
+    std::map<unsigned, uint32_t*, std::greater<unsigned>> reduced;  // log height -> ext vector, tallest first
+    {
+        Phase ph(ctx, BFGPU_PHASE_OPEN_REDUCE);
+        uint32_t maxw = 1;
+        for (auto& rv : R)
+            for (auto& mp : rv) maxw = std::max(maxw, mp.m->cols);
+        std::vector<kb::Ext> apow(maxw);
+        apow[0] = kb::ext_one();
+        for (uint32_t k = 1; k < maxw; k++) apow[k] = kb::ext_mul(apow[k - 1], alpha);
+        uint32_t* d_apow = nullptr;
+        TRY(dalloc(ctx, (void**)&d_apow, (size_t)maxw * 16));
+        CU(cudaMemcpyAsync(d_apow, apow.data(), (size_t)maxw * 16, cudaMemcpyHostToDevice, ctx->stream));
+        struct Group {
+            std::vector<openk::RoMat> mats;
+            std::vector<kb::Ext> pts;
+            uint64_t num_reduced = 0;
+        };
+        std::map<unsigned, Group> groups;
+        for (auto& rv : R)
+            for (auto& mp : rv) {
+                unsigned lh = ilog2(mp.m->rows);
+                Group& g = groups[lh];
+                openk::RoMat rm;
+                memset(&rm, 0, sizeof rm);
+                rm.d = mp.m->d;
+                rm.width = mp.m->cols;
+                if (mp.pts.size() > 2) return fail(ctx, BFGPU_ERR_INVALID, "more than two opening points per matrix are not supported");
+                rm.npoints = (uint32_t)mp.pts.size();
+                for (size_t t = 0; t < mp.pts.size(); t++) {
+                    size_t pi = 0;
+                    for (; pi < g.pts.size(); pi++)
+                        if (!memcmp(g.pts[pi].c, mp.pts[t].c, 16)) break;
+                    if (pi == g.pts.size()) g.pts.push_back(mp.pts[t]);
+                    if (g.pts.size() > 4) return fail(ctx, BFGPU_ERR_INVALID, "more than four distinct opening points per height are not supported");
+                    rm.pt[t] = (uint32_t)pi;
+                    kb::Ext yr = kb::ext_zero();
+                    for (uint32_t k = 0; k < mp.m->cols; k++) yr = kb::ext_add(yr, kb::ext_mul(apow[k], mp.ys[t][k]));
+                    kb::Ext ao = ext_pow(alpha, g.num_reduced);
+                    memcpy(rm.yred[t], yr.c, 16);
+                    memcpy(rm.aoff[t], ao.c, 16);
+                    g.num_reduced += mp.m->cols;
+                }
+                g.mats.push_back(rm);
+            }
+        for (auto& kv : groups) {
+            unsigned lh = kv.first;
+            Group& g = kv.second;
+            openk::RoMat* d_m = nullptr;
+            uint32_t *d_z = nullptr, *ro = nullptr;
+            TRY(dalloc(ctx, (void**)&d_m, g.mats.size() * sizeof(openk::RoMat)));
+            TRY(dalloc(ctx, (void**)&d_z, g.pts.size() * 16));
+            TRY(dalloc(ctx, (void**)&ro, (size_t)16 << lh));
+            CU(cudaMemcpyAsync(d_m, g.mats.data(), g.mats.size() * sizeof(openk::RoMat), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(d_z, g.pts.data(), g.pts.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
+            openk::k_reduce_openings<<<((1u << lh) + 127) / 128, 128, 0, ctx->stream>>>(d_m, (uint32_t)g.mats.size(), d_z, (uint32_t)g.pts.size(), d_apow, lh,
+                                                                                         gen, ctx->d_tw, ro);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(ctx->stream));  // host vectors above must outlive the copies
+            dfree(ctx, d_m);
+            dfree(ctx, d_z);
+            reduced[lh] = ro;
+        }
+        dfree(ctx, d_apow);
+    }
+
+    // ---- (iii) FRI commit phase ------------------------------------------------------------------------------
+    struct Layer {
+        uint32_t* vec;  // folded input of this layer: len ext elements = len/2 rows of 8 words
+        uint64_t len;
+        bfgpu_tree* tree;
+    };
+    std::vector<Layer> layers;
+    auto release_layers = [&]() {
+        for (auto& L : layers) {
+            tree_release(L.tree);
+            dfree(ctx, L.vec);
+        }
+        for (auto& kv : reduced) dfree(ctx, kv.second);
+    };
+    uint32_t final_poly[4];
+    const unsigned log_max_height = reduced.begin()->first;
+    {
+        Phase ph(ctx, BFGPU_PHASE_FRI);
+        auto it = reduced.begin();
+        uint32_t* folded = it->second;
+        uint64_t len = 1ull << it->first;
+        it->second = nullptr;
+        ++it;
+        std::vector<std::array<uint32_t, 8>> commits;
+        while (len > (1ull << log_blowup)) {
+            DMat leaves;
+            leaves.d = folded;
+            leaves.rows = len / 2;
+            leaves.cols = 8;
+            leaves.rs = 8;
+            bfgpu_tree* t = nullptr;
+            int32_t rc = build_tree(ctx, {leaves}, false, &t);
+            layers.push_back({folded, len, t});
+            if (rc != BFGPU_OK) { release_layers(); return rc; }
+            std::array<uint32_t, 8> root;
+            CU(cudaMemcpyAsync(root.data(), t->layers.back(), 32, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            ch.observe_slice(root.data(), 8);
+            commits.push_back(root);
+            kb::Ext beta = ch.sample_ext();
+            kb::Ext half_beta = kb::ext_scale(beta, kb::halve(kb::ONE));
+            uint64_t nlen = len / 2;
+            unsigned log_nlen = ilog2(nlen);
+            uint32_t* next = nullptr;
+            TRY(dalloc(ctx, (void**)&next, nlen * 16));
+            const uint32_t* add = nullptr;
+            if (it != reduced.end() && (1ull << it->first) == nlen) add = it->second;
+            openk::k_fri_fold<<<(unsigned)((nlen + 127) / 128), 128, 0, ctx->stream>>>(folded, next, add, log_nlen, half_beta, ctx->d_tw);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            if (add) {
+                dfree(ctx, it->second);
+                it->second = nullptr;
+                ++it;
+            }
+            folded = next;
+            len = nlen;
+        }
+        if (it != reduced.end()) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "FRI inputs left over after the commit phase"); }
+        std::vector<uint32_t> fin(len * 4);
+        CU(cudaMemcpyAsync(fin.data(), folded, len * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        dfree(ctx, folded);
+        for (uint64_t i = 1; i < len; i++)
+            if (memcmp(&fin[0], &fin[4 * i], 16)) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "FRI final layer is not constant: a committed matrix is not low-degree"); }
+        memcpy(final_poly, fin.data(), 16);
+        ch.observe_slice(final_poly, 4);
+        flat.push_back((uint32_t)commits.size());
+        for (auto& c : commits)
+            for (int k = 0; k < 8; k++) flat.push_back(out_word(ctx, c[k]));
+        for (int k = 0; k < 4; k++) flat.push_back(out_word(ctx, final_poly[k]));
+    }
+
+    // ---- (iv) proof of work ----------------------------------------------------------------------------------
+    uint32_t witness = 0;
+    {
+        Phase ph(ctx, BFGPU_PHASE_POW);
+        if (fixed_pow_witness >= 0) {
+            witness = (uint32_t)fixed_pow_witness;
+        } else {
+            uint32_t st[16];
+            memcpy(st, ch.state, sizeof st);
+            for (size_t i = 0; i < ch.input.size(); i++) st[i] = ch.input[i];
+            uint32_t pos = (uint32_t)ch.input.size();
+            uint32_t* d_st = nullptr;
+            unsigned int* d_best = nullptr;
+            TRY(dalloc(ctx, (void**)&d_st, 64));
+            TRY(dalloc(ctx, (void**)&d_best, 4));
+            CU(cudaMemcpyAsync(d_st, st, 64, cudaMemcpyHostToDevice, ctx->stream));
+            const uint32_t batch = 1u << 20, mask = (1u << ctx->pow_bits) - 1;
+            unsigned int best = 0xffffffffu;
+            for (uint64_t start = 0; start < kb::P && best == 0xffffffffu; start += batch) {
+                CU(cudaMemcpyAsync(d_best, &best, 4, cudaMemcpyHostToDevice, ctx->stream));
+                uint32_t count = (uint32_t)std::min<uint64_t>(batch, kb::P - start);
+                openk::k_pow_grind<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_st, pos, mask, (uint32_t)start, count, d_best);
+                LAUNCHED(ctx);
+                CU(cudaGetLastError());
+                CU(cudaMemcpyAsync(&best, d_best, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+            }
+            dfree(ctx, d_st);
+            dfree(ctx, d_best);
+            if (best == 0xffffffffu) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "proof-of-work search failed"); }
+            witness = best;
+        }
+        if (!ch.check_witness(ctx->pow_bits, kb::to_mont(witness))) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "invalid proof-of-work witness %u", witness); }
+        flat.push_back(witness);
+    }
+
+    // ---- (v) queries: every opened word is gathered by one kernel ---------------------------------------------
+    {
+        Phase ph(ctx, BFGPU_PHASE_QUERY);
+        flat.push_back(ctx->num_queries);
+        std::vector<const uint32_t*> src;
+        std::vector<std::pair<size_t, uint32_t>> index_slots;  // position in flat of each query's index (already written)
+        size_t base = flat.size();
+        std::vector<uint32_t> indices(ctx->num_queries);
+        // first pass: lay out the pointer list in serialisation order, reserving one slot per index word
+        for (uint32_t q = 0; q < ctx->num_queries; q++) {
+            uint32_t index = ch.sample_bits(log_max_height);
+            indices[q] = index;
+            src.push_back(nullptr);  // placeholder for the index word
+            for (int r = 0; r < n_rounds; r++) {
+                const bfgpu_tree* t = rounds[r].data->tree;
+                uint64_t ridx = index >> (log_global_max - t->log_max);
+                for (const DMat& m : t->mats) {
+                    uint64_t row = ridx >> (t->log_max - ilog2(m.rows));
+                    for (uint32_t c = 0; c < m.cols; c++) src.push_back(m.d + (uint64_t)c * m.col_stride() + row * m.rs);
+                }
+                for (unsigned l = 0; l < t->log_max; l++)
+                    for (int k = 0; k < 8; k++) src.push_back(t->layers[l] + 8 * ((ridx >> l) ^ 1) + k);
+            }
+            for (size_t i = 0; i < layers.size(); i++) {
+                uint64_t idx_i = index >> i, pair = idx_i >> 1;
+                for (int k = 0; k < 4; k++) src.push_back(layers[i].vec + 8 * pair + 4 * ((idx_i ^ 1) & 1) + k);
+                const bfgpu_tree* t = layers[i].tree;
+                for (unsigned l = 0; l < t->log_max; l++)
+                    for (int k = 0; k < 8; k++) src.push_back(t->layers[l] + 8 * ((pair >> l) ^ 1) + k);
+            }
+        }
+        // placeholders point at a device word holding zero; the index words are patched on the host
+        uint32_t* d_zero = nullptr;
+        TRY(dalloc(ctx, (void**)&d_zero, 4));
+        CU(cudaMemsetAsync(d_zero, 0, 4, ctx->stream));
+        size_t per_query = src.size() / ctx->num_queries;
+        for (uint32_t q = 0; q < ctx->num_queries; q++) src[q * per_query] = d_zero;
+        const uint32_t** d_src = nullptr;
+        uint32_t* d_out = nullptr;
+        TRY(dalloc(ctx, (void**)&d_src, src.size() * sizeof(void*)));
+        TRY(dalloc(ctx, (void**)&d_out, src.size() * 4));
+        CU(cudaMemcpyAsync((void*)d_src, src.data(), src.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+        openk::k_gather_words<<<(unsigned)((src.size() + 255) / 256), 256, 0, ctx->stream>>>(d_src, d_out, src.size(), ctx->repr == BFGPU_REPR_CANONICAL);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        flat.resize(base + src.size());
+        CU(cudaMemcpyAsync(flat.data() + base, d_out, src.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t q = 0; q < ctx->num_queries; q++) flat[base + q * per_query] = indices[q];
+        dfree(ctx, d_zero);
+        dfree(ctx, (void*)d_src);
+        dfree(ctx, d_out);
+        (void)index_slots;
+    }
+    release_layers();
+    guard.keep = true;
+    *out = res;
+    return BFGPU_OK;
 }

@@ -17,6 +17,7 @@ namespace hashk {
 constexpr int HASH_THREADS = 128;
 
 // absorb the r-th row of the column list (overwrite-mode sponge, rate 8) into state s
+// (r is the ELEMENT offset of the row inside each column: row index * row stride)
 __device__ __forceinline__ void sponge_rows(uint32_t (&s)[16], const uint32_t* const* __restrict__ colptr, uint32_t ncols,
                                             uint64_t r) {
     // single permute() call site (the permutation body must stay small enough for the I-cache);
@@ -42,21 +43,23 @@ __device__ __forceinline__ void store_digest(uint32_t* out, const uint32_t (&s)[
 }
 
 // first digest layer: digests[r] = sponge(row r of every column in colptr)
+// row_stride: words between consecutive rows inside a column (1 for column-major matrices, the row
+// length for row-major ones such as the FRI layer matrices)
 __global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash(const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint64_t rows,
-                                                            uint32_t* __restrict__ digests) {
+                                                            uint32_t* __restrict__ digests, uint32_t row_stride) {
     uint64_t r = blockIdx.x * (uint64_t)HASH_THREADS + threadIdx.x;
     if (r >= rows) return;
     uint32_t s[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) s[k] = 0;
-    sponge_rows(s, colptr, ncols, r);
+    sponge_rows(s, colptr, ncols, r * row_stride);
     store_digest(digests + 8 * r, s);
 }
 
 // next layer: out[i] = compress(prev[2i], prev[2i+1]); if ncols > 0 additionally
 // out[i] = compress(out[i], sponge(row i of the injected columns))
 __global__ void __launch_bounds__(HASH_THREADS) k_compress_layer(const uint32_t* __restrict__ prev, uint32_t* __restrict__ out, uint64_t len,
-                                                                 const uint32_t* const* __restrict__ colptr, uint32_t ncols) {
+                                                                 const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint32_t row_stride) {
     uint64_t i = blockIdx.x * (uint64_t)HASH_THREADS + threadIdx.x;
     if (i >= len) return;
     uint32_t s[16];
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(HASH_THREADS) k_compress_layer(const uint32_t*
         uint32_t h[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) h[k] = 0;
-        sponge_rows(h, colptr, ncols, i);
+        sponge_rows(h, colptr, ncols, i * row_stride);
 #pragma unroll
         for (int k = 0; k < 8; k++) s[8 + k] = h[k];
         p2::permute(s);

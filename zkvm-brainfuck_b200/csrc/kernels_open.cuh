@@ -1,0 +1,186 @@
+// kernels_open.cuh — kernels behind `TwoAdicFriPcs::open` (K6-K9 of SURVEY.md §2).
+//
+// Replaces the CPU work of `pcs.open(...)` as called from the reference
+// (crates/stark/src/prover.rs:460-470): barycentric evaluation of every committed column at the
+// opening points, the per-height reduced openings, the FRI commit phase folds, the proof-of-work
+// search and the query gathers.  Algorithms restated from Plonky3 p3-fri v0.1.0.
+// All matrices are the column-major Montgomery LDEs with bit-reversed rows left on the device by
+// `bfgpu_pcs_commit`; extension elements are 4 consecutive words.
+#pragma once
+#include "kb31.cuh"
+#include "poseidon2.cuh"
+
+namespace openk {
+
+using kb::Ext;
+
+__device__ __forceinline__ Ext ld_ext(const uint32_t* p) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    return Ext{{v.x, v.y, v.z, v.w}};
+}
+__device__ __forceinline__ void st_ext(uint32_t* p, Ext e) { *reinterpret_cast<uint4*>(p) = make_uint4(e.c[0], e.c[1], e.c[2], e.c[3]); }
+
+// w_{2^log_n}^j for j < 2^log_n from the table tw[e] = w_{2^24}^e, e < 2^23
+__device__ __forceinline__ uint32_t root_pow(const uint32_t* __restrict__ tw, unsigned log_n, uint32_t j) {
+    if (log_n == 0) return kb::ONE;
+    uint32_t half = 1u << (log_n - 1);
+    uint32_t jj = j & (half - 1);
+    uint32_t v = __ldg(tw + ((uint64_t)jj << (kb::TWO_ADICITY - log_n)));
+    return (j & half) ? kb::neg(v) : v;
+}
+
+// ---- barycentric weights: w[r] = g^{br(r)} / (z - s g^{br(r)}),  r < h = 2^log_h ---------------------
+// (rows of the low coset of a stored LDE are in bit-reversed order; s = coset shift, Montgomery)
+__global__ void k_bary_weights(uint32_t* __restrict__ w, unsigned log_h, uint32_t shift, Ext z, const uint32_t* __restrict__ tw) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (1u << log_h)) return;
+    uint32_t g = root_pow(tw, log_h, kb::bitrev(r, log_h));
+    Ext d = z;
+    d.c[0] = kb::sub(d.c[0], kb::mul(shift, g));
+    st_ext(w + 4 * (uint64_t)r, kb::ext_scale(kb::ext_inv(d), g));
+}
+
+// partial[(c * nchunks + chunk) * NP + t] = sum over the chunk's rows of col_c[r] * w_t[r]
+constexpr int BARY_THREADS = 256, BARY_ROWS = 4096, BARY_COLS = 4;
+template <int NP>
+__global__ void __launch_bounds__(BARY_THREADS) k_bary_dot(const uint32_t* __restrict__ mat, uint64_t col_stride, uint32_t ncols, uint32_t h,
+                                                           const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
+                                                           uint32_t* __restrict__ partial, uint32_t nchunks) {
+    const uint32_t chunk = blockIdx.x, c0 = blockIdx.y * BARY_COLS;
+    Ext acc[BARY_COLS][NP];
+#pragma unroll
+    for (int c = 0; c < BARY_COLS; c++)
+#pragma unroll
+        for (int t = 0; t < NP; t++) acc[c][t] = kb::ext_zero();
+    uint32_t r_end = min(h, (chunk + 1) * BARY_ROWS);
+    for (uint32_t r = chunk * BARY_ROWS + threadIdx.x; r < r_end; r += BARY_THREADS) {
+        Ext w[NP];
+        w[0] = ld_ext(w0 + 4 * (uint64_t)r);
+        if (NP > 1) w[NP - 1] = ld_ext(w1 + 4 * (uint64_t)r);
+#pragma unroll
+        for (int c = 0; c < BARY_COLS; c++) {
+            if (c0 + c < ncols) {
+                uint32_t v = mat[(uint64_t)(c0 + c) * col_stride + r];
+#pragma unroll
+                for (int t = 0; t < NP; t++) acc[c][t] = kb::ext_add(acc[c][t], kb::ext_scale(w[t], v));
+            }
+        }
+    }
+    __shared__ uint32_t red[BARY_THREADS / 32][BARY_COLS * NP * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < BARY_COLS; c++)
+#pragma unroll
+        for (int t = 0; t < NP; t++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t v = acc[c][t].c[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = kb::add(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0) red[warp][(c * NP + t) * 4 + k] = v;
+            }
+    __syncthreads();
+    if (threadIdx.x < BARY_COLS * NP * 4) {
+        uint32_t v = 0;
+        for (int wv = 0; wv < BARY_THREADS / 32; wv++) v = kb::add(v, red[wv][threadIdx.x]);
+        int c = threadIdx.x / (NP * 4), rem = threadIdx.x % (NP * 4);
+        if (c0 + c < ncols) partial[(((uint64_t)(c0 + c) * nchunks + chunk) * NP) * 4 + rem] = v;
+    }
+}
+
+// out[i] = sum over chunks of partial[i][chunk]   (i over ncols*NP*4 words; layout as above)
+__global__ void k_bary_finish(const uint32_t* __restrict__ partial, uint32_t* __restrict__ out, uint32_t ncols, uint32_t nchunks, uint32_t np) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncols * np * 4) return;
+    uint32_t c = i / (np * 4), rem = i % (np * 4);
+    uint32_t v = 0;
+    for (uint32_t ch = 0; ch < nchunks; ch++) v = kb::add(v, partial[(((uint64_t)c * nchunks + ch) * np) * 4 + rem]);
+    out[i] = v;
+}
+
+// ---- reduced openings of one height group ---------------------------------------------------------------
+struct RoMat {
+    const uint32_t* d;  // column-major LDE, `rows` rows
+    uint32_t width;
+    uint32_t npoints;    // 1 or 2
+    uint32_t pt[2];      // index into the group's point list
+    uint32_t yred[2][4];  // sum_k alpha^k y_k   for each point
+    uint32_t aoff[2][4];  // alpha^(columns already reduced at this height)
+};
+// ro[r] = sum_{mat, point} aoff * (yred - sum_k alpha^k M[r][k]) / (z_point - x_r),  x_r = shift * w_H^{br(r)}
+__global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict__ mats, uint32_t nmats, const uint32_t* __restrict__ zs /* npts x 4 */,
+                                                         uint32_t npts, const uint32_t* __restrict__ apow /* ext alpha^k */, unsigned log_h,
+                                                         uint32_t shift, const uint32_t* __restrict__ tw, uint32_t* __restrict__ ro) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (1u << log_h)) return;
+    uint32_t x = kb::mul(shift, root_pow(tw, log_h, kb::bitrev(r, log_h)));
+    Ext inv[4];
+    for (uint32_t t = 0; t < npts && t < 4; t++) {
+        Ext d = ld_ext(zs + 4 * t);
+        d.c[0] = kb::sub(d.c[0], x);
+        inv[t] = kb::ext_inv(d);
+    }
+    Ext acc = kb::ext_zero();
+    for (uint32_t m = 0; m < nmats; m++) {
+        const RoMat& M = mats[m];
+        Ext rr = kb::ext_zero();
+        const uint32_t* col = M.d + r;
+        for (uint32_t k = 0; k < M.width; k++) {
+            uint32_t v = col[(uint64_t)k << log_h];
+            rr = kb::ext_add(rr, kb::ext_scale(ld_ext(apow + 4 * k), v));
+        }
+        for (uint32_t t = 0; t < M.npoints; t++) {
+            Ext y = Ext{{M.yred[t][0], M.yred[t][1], M.yred[t][2], M.yred[t][3]}};
+            Ext a = Ext{{M.aoff[t][0], M.aoff[t][1], M.aoff[t][2], M.aoff[t][3]}};
+            Ext q = kb::ext_mul(kb::ext_sub(y, rr), inv[M.pt[t]]);
+            acc = kb::ext_add(acc, kb::ext_mul(a, q));
+        }
+    }
+    st_ext(ro + 4 * (uint64_t)r, acc);
+}
+
+// ---- FRI fold: out[i] = (1/2 + b g^-br(i)) in[2i] + (1/2 - b g^-br(i)) in[2i+1] (+ add[i]),  b = beta/2 -----
+__global__ void k_fri_fold(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h /* out length */,
+                           Ext half_beta, const uint32_t* __restrict__ tw) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << log_h)) return;
+    // g = generator of order 2^(log_h+1); g^-j = w^(2^(log_h+1) - j)
+    uint32_t j = kb::bitrev(i, log_h);
+    uint32_t ginv = j ? root_pow(tw, log_h + 1, (1u << (log_h + 1)) - j) : kb::ONE;
+    Ext lo = ld_ext(in + 8 * (uint64_t)i), hi = ld_ext(in + 8 * (uint64_t)i + 4);
+    Ext pw = kb::ext_scale(half_beta, ginv);
+    const uint32_t half = kb::halve(kb::ONE);
+    Ext a = pw, b = kb::ext_neg(pw);
+    a.c[0] = kb::add(a.c[0], half);
+    b.c[0] = kb::add(b.c[0], half);
+    Ext o = kb::ext_add(kb::ext_mul(a, lo), kb::ext_mul(b, hi));
+    if (add) o = kb::ext_add(o, ld_ext(add + 4 * (uint64_t)i));
+    st_ext(out + 4 * (uint64_t)i, o);
+}
+
+// ---- proof of work: smallest w in [start, start+count) with (permute(state | w at pos)[7] & mask) == 0 ------
+__global__ void __launch_bounds__(128) k_pow_grind(const uint32_t* __restrict__ state16, uint32_t pos, uint32_t mask, uint32_t start, uint32_t count,
+                                                   unsigned int* __restrict__ best) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t w = start + i;  // canonical candidate
+    uint32_t s[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) s[k] = state16[k];
+    uint32_t wm = kb::to_mont(w);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if ((uint32_t)k == pos) s[k] = wm;
+    p2::permute(s);
+    if ((kb::from_mont(s[7]) & mask) == 0) atomicMin(best, w);
+}
+
+// ---- query gathers: out[i] = *src[i] (optionally converted to canonical) -----------------------------------
+__global__ void k_gather_words(const uint32_t* const* __restrict__ src, uint32_t* __restrict__ out, uint64_t n, int to_canonical) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = *src[i];
+    out[i] = to_canonical ? kb::from_mont(v) : v;
+}
+
+}  // namespace openk
