@@ -194,6 +194,38 @@ uint64_t bfgpu_opening_size(const bfgpu_opening* o);
 int32_t bfgpu_opening_read(const bfgpu_opening* o, uint32_t* out);
 void bfgpu_opening_free(bfgpu_opening* o);
 
+/* ---- MachineProver<SC, BfAir> (prover.rs:27-150): setup / commit / open ------------------------------ */
+/* The eight chips of the machine (crates/core/machine/src/brainfuck/mod.rs:53-81) are compiled into the
+ * library as generated constraint / LogUp programs (csrc/gen_air.cuh from air/chips.py). */
+int32_t bfgpu_machine_num_chips(void);
+int32_t bfgpu_machine_chip_info(int32_t i, const char** name, int32_t* main_width, int32_t* prep_width, int32_t* perm_ext_width,
+                                int32_t* local_only);
+typedef struct bfgpu_pk bfgpu_pk;                   /* DeviceProvingKey: preprocessed traces + LDE + Merkle tree */
+typedef struct bfgpu_shard bfgpu_shard;             /* ShardMainData: main traces + LDE + Merkle tree             */
+typedef struct bfgpu_shard_proof bfgpu_shard_proof; /* ShardProof                                                  */
+/* StarkMachine::setup (machine.rs:154-224): named preprocessed traces (chip name -> matrix); they are sorted by
+ * (height desc, name) and committed.  commit receives the preprocessed commitment. */
+int32_t bfgpu_machine_setup(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* prep_traces, int32_t n, uint32_t commit[8],
+                            bfgpu_pk** out);
+/* StarkProvingKey::observe_into (prover.rs:595-601) */
+int32_t bfgpu_pk_observe_into(const bfgpu_pk* pk, bfgpu_challenger* ch);
+void bfgpu_pk_free(bfgpu_pk* pk);
+/* MachineProver::commit (prover.rs:209-236): named main traces of the included chips */
+int32_t bfgpu_machine_commit(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* traces, int32_t n, uint32_t root[8],
+                             bfgpu_shard** out);
+void bfgpu_shard_free(bfgpu_shard* shard);
+/* MachineProver::open (prover.rs:242-553): LogUp permutation traces, their commitment, quotient values and
+ * commitment, and the PCS opening, advancing `ch` exactly like the reference transcript.
+ * Serialisation of the proof (flat u32, caller representation):
+ *   main root (8), permutation root (8), quotient root (8), n_chips,
+ *   per chip in commit order: chip index (bfgpu_machine_chip_info), log_degree, cumulative_sum (4),
+ *   then the bfgpu_opening layout for the rounds [preprocessed, main, permutation, quotient]. */
+int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const bfgpu_shard* shard, bfgpu_challenger* ch,
+                           int64_t fixed_pow_witness, bfgpu_shard_proof** out);
+uint64_t bfgpu_shard_proof_size(const bfgpu_shard_proof* p);
+int32_t bfgpu_shard_proof_read(const bfgpu_shard_proof* p, uint32_t* out);
+void bfgpu_shard_proof_free(bfgpu_shard_proof* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,18 @@ ABI = {
     "bfgpu_opening_size": (C.c_uint64, [C.c_void_p]),
     "bfgpu_opening_read": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "bfgpu_opening_free": (None, [C.c_void_p]),
+    "bfgpu_machine_num_chips": (C.c_int32, []),
+    "bfgpu_machine_chip_info": (C.c_int32, [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32)]),
+    "bfgpu_machine_setup": (C.c_int32, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(Mat), C.c_int32, _u32p, C.POINTER(C.c_void_p)]),
+    "bfgpu_pk_observe_into": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_pk_free": (None, [C.c_void_p]),
+    "bfgpu_machine_commit": (C.c_int32, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(Mat), C.c_int32, _u32p, C.POINTER(C.c_void_p)]),
+    "bfgpu_shard_free": (None, [C.c_void_p]),
+    "bfgpu_machine_open": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "bfgpu_shard_proof_size": (C.c_uint64, [C.c_void_p]),
+    "bfgpu_shard_proof_read": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_shard_proof_free": (None, [C.c_void_p]),
 }
 
 
@@ -444,3 +456,134 @@ class TwoAdicFriPcs:
         out = np.zeros((r, c), np.uint32)
         self.ctx.check(lib().bfgpu_pcs_get_evaluations(data._h, idx, 1 if bit_reversed_rows else 0, _ptr(out)))
         return out
+
+
+def machine_chips():
+    """[(name, main_width, prep_width, perm_ext_width, local_only)] in BfAir::chips() order."""
+    out = []
+    for i in range(lib().bfgpu_machine_num_chips()):
+        name = C.c_char_p()
+        mw, pw, ew, lo = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        lib().bfgpu_machine_chip_info(i, C.byref(name), C.byref(mw), C.byref(pw), C.byref(ew), C.byref(lo))
+        out.append((name.value.decode(), mw.value, pw.value, ew.value, bool(lo.value)))
+    return out
+
+
+class _Named:
+    def __init__(self, ctx, handle, free, names, heights):
+        self.ctx, self._h, self._free, self.names, self.heights = ctx, handle, free, names, heights
+
+    def free(self):
+        if self._h:
+            self._free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.free()
+
+
+def _named_mats(named):
+    names = [k for k, _ in named]
+    arr, keep = _mats([v for _, v in named])
+    cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    return cn, arr, keep
+
+
+class CudaProver:
+    """`MachineProver<KoalaBearPoseidon2, BfAir>` on the GPU (reference trait: crates/stark/src/prover.rs:27-150;
+    CPU implementation it replaces: `CpuProver`, prover.rs:162-582)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.chips = machine_chips()
+
+    def _sorted(self, traces):
+        return sorted(traces.items(), key=lambda kv: (-kv[1].shape[0], kv[0]))
+
+    def setup(self, prep_traces):
+        """StarkMachine::setup: {chip name: preprocessed trace} -> (proving key handle, commitment)."""
+        named = list(prep_traces.items())
+        cn, arr, keep = _named_mats(named)
+        commit = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        self.ctx.check(lib().bfgpu_machine_setup(self.ctx._h, cn, arr, len(named), commit.ctypes.data_as(_u32p), C.byref(h)))
+        srt = self._sorted(prep_traces)
+        pk = _Named(self.ctx, h, lib().bfgpu_pk_free, [k for k, _ in srt], [v.shape[0] for _, v in srt])
+        pk.commit = commit
+        pk.widths = [v.shape[1] for _, v in srt]
+        return pk
+
+    def commit(self, traces):
+        """MachineProver::commit: {chip name: main trace} -> ShardMainData handle (root in .commit)."""
+        named = list(traces.items())
+        cn, arr, keep = _named_mats(named)
+        root = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        self.ctx.check(lib().bfgpu_machine_commit(self.ctx._h, cn, arr, len(named), root.ctypes.data_as(_u32p), C.byref(h)))
+        srt = self._sorted(traces)
+        sd = _Named(self.ctx, h, lib().bfgpu_shard_free, [k for k, _ in srt], [v.shape[0] for _, v in srt])
+        sd.commit = root
+        return sd
+
+    def open(self, pk, shard, challenger, pow_witness=None):
+        """MachineProver::open -> ShardProof as nested dicts (commitment, opened_values per chip, opening_proof, chip_ordering)."""
+        h = C.c_void_p()
+        self.ctx.check(lib().bfgpu_machine_open(self.ctx._h, pk._h, shard._h, challenger._h, -1 if pow_witness is None else int(pow_witness), C.byref(h)))
+        size = lib().bfgpu_shard_proof_size(h)
+        buf = np.zeros(size, np.uint32)
+        self.ctx.check(lib().bfgpu_shard_proof_read(h, _ptr(buf)))
+        lib().bfgpu_shard_proof_free(h)
+        return self._parse(buf, pk, shard)
+
+    def prove(self, pk, traces, challenger, pow_witness=None):
+        """MachineProver::prove (prover.rs:560-582) minus trace generation: observe pk, commit, open on a clone."""
+        lib().bfgpu_pk_observe_into(pk._h, challenger._h)
+        shard = self.commit(traces)
+        proof = self.open(pk, shard, challenger.clone(), pow_witness)
+        shard.free()
+        return proof
+
+    def _parse(self, buf, pk, shard):
+        info = {n: (mw, pw, ew, lo) for n, mw, pw, ew, lo in self.chips}
+        com = dict(main=buf[0:8].copy(), permutation=buf[8:16].copy(), quotient=buf[16:24].copy())
+        n = int(buf[24])
+        pos = 25
+        meta = []
+        for _ in range(n):
+            meta.append((self.chips[int(buf[pos])][0], int(buf[pos + 1]), buf[pos + 2:pos + 6].astype(np.uint64)))
+            pos += 6
+
+        class _D:  # dims carrier for the opening parser
+            pass
+
+        def dims(heights, widths):
+            d = _D()
+            d.dims = [(2 * h, w) for h, w in zip(heights, widths)]
+            return d
+
+        names = [m[0] for m in meta]
+        heights = [1 << m[1] for m in meta]
+        pts = lambda lo: [None] if lo else [None, None]
+        rounds = [
+            (dims(pk.heights, pk.widths), [pts(info[k][3]) for k in pk.names]),
+            (dims(heights, [info[k][0] for k in names]), [pts(info[k][3]) for k in names]),
+            (dims(heights, [4 * info[k][2] for k in names]), [[None, None] for _ in names]),
+            (dims([h for h in heights for _ in range(2)], [4] * (2 * n)), [[None] for _ in range(2 * n)]),
+        ]
+        opened, fri = TwoAdicFriPcs._parse_opening(buf[pos:], rounds)
+        prep_v, main_v, perm_v, quot_v = opened
+        chips_out = []
+        for i, (name, log_degree, csum) in enumerate(meta):
+            lo = info[name][3]
+
+            def lv(vals, both):
+                return dict(local=vals[0], next=vals[1] if both else np.zeros_like(vals[0]))
+
+            if name in pk.names:
+                k = pk.names.index(name)
+                prep = lv(prep_v[k], not info[pk.names[k]][3])
+            else:
+                prep = dict(local=np.zeros((0, 4), np.uint64), next=np.zeros((0, 4), np.uint64))
+            chips_out.append(dict(preprocessed=prep, main=lv(main_v[i], not lo), permutation=lv(perm_v[i], True),
+                                  quotient=[quot_v[2 * i][0], quot_v[2 * i + 1][0]], cumulative_sum=csum, log_degree=log_degree))
+        return dict(commitment=com, opened_values=chips_out, opening_proof=fri, chip_ordering={k: i for i, k in enumerate(names)})

@@ -535,13 +535,13 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
 
 // coset LDE of a caller matrix -> column-major device matrix with bit-reversed rows.
 // shift_mont: Montgomery form of the coset shift.
-static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bits, uint32_t shift_mont, DMat* out) {
-    unsigned log_n = ilog2(m.rows);
+// coset LDE of a column-major device matrix whose rows are already in bit-reversed order (consumed) ->
+// column-major device matrix with bit-reversed rows.  shift_mont: Montgomery form of the coset shift.
+static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, uint32_t shift_mont, DMat* out) {
+    unsigned log_n = ilog2(coef.rows);
     if (log_n + added_bits > kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
-    uint64_t n = m.rows, N = n << added_bits;
+    uint64_t n = coef.rows, N = n << added_bits;
     uint32_t ncosets = 1u << added_bits;
-    DMat coef;
-    TRY(ingest(ctx, m, /*bitrev=*/true, &coef));
     // per-coset scale vectors: pw[h*n + k] = (shift * w_N^{bitrev(h)})^k / n
     uint32_t* pw = nullptr;
     {
@@ -578,6 +578,20 @@ static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bit
     dfree(ctx, pw);
     TRY(run_ntt<false>(ctx, out->d, n, log_n, coef.cols * ncosets));
     return BFGPU_OK;
+}
+
+// coset LDE of a caller matrix.  keep != null: also return a copy of the ingested trace (column-major,
+// bit-reversed rows), which the LogUp kernel reads later.
+static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bits, uint32_t shift_mont, DMat* out, DMat* keep = nullptr) {
+    DMat coef;
+    TRY(ingest(ctx, m, /*bitrev=*/true, &coef));
+    if (keep) {
+        *keep = coef;
+        size_t bytes = (size_t)coef.rows * coef.cols * 4;
+        TRY(dalloc(ctx, (void**)&keep->d, bytes));
+        CU(cudaMemcpyAsync(keep->d, coef.d, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return lde_from_bitrev(ctx, coef, added_bits, shift_mont, out);
 }
 
 extern "C" int32_t bfgpu_coset_lde_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t added_bits, uint32_t shift, int bit_reversed_rows,
@@ -1340,5 +1354,379 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
     release_layers();
     guard.keep = true;
     *out = res;
+    return BFGPU_OK;
+}
+
+// =====================================================================================================
+// MachineProver: setup / commit / open over the eight-chip Brainfuck machine
+// (reference crates/stark/src/machine.rs:154-224, crates/stark/src/prover.rs:209-236,242-553)
+// =====================================================================================================
+#include "kernels_air.cuh"
+
+struct bfgpu_pk {
+    bfgpu_ctx* ctx = nullptr;
+    std::vector<std::string> names;  // sorted by (height desc, name)
+    std::vector<int> chip;           // index into air::CHIPS
+    std::vector<DMat> traces;        // ingested traces: column-major, bit-reversed rows (read by the LogUp kernel)
+    bfgpu_pcs_data* data = nullptr;
+    uint32_t commit[8];              // Montgomery
+};
+struct bfgpu_shard {
+    bfgpu_ctx* ctx = nullptr;
+    std::vector<std::string> names;
+    std::vector<int> chip;
+    std::vector<DMat> traces;
+    bfgpu_pcs_data* data = nullptr;
+    uint32_t commit[8];
+};
+struct bfgpu_shard_proof {
+    std::vector<uint32_t> flat;
+};
+
+static int chip_index(const char* name) {
+    for (int i = 0; i < air::NUM_CHIPS; i++)
+        if (!strcmp(name, air::CHIPS[i].name)) return i;
+    return -1;
+}
+
+// sort by (Reverse(height), name) (prover.rs:214, machine.rs:182-183), ingest + LDE + Merkle, keep the traces
+static int32_t machine_commit(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* mats, int32_t n, bool preprocessed,
+                              std::vector<std::string>* out_names, std::vector<int>* out_chip, std::vector<DMat>* out_traces,
+                              bfgpu_pcs_data** out_data, uint32_t root_mont[8]) {
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) {
+        TRY(check_mat(ctx, &mats[i], true));
+        int ci = chip_index(names[i]);
+        if (ci < 0) return fail(ctx, BFGPU_ERR_INVALID, "unknown chip '%s'", names[i]);
+        uint32_t want = preprocessed ? air::CHIPS[ci].prep_w : air::CHIPS[ci].main_w;
+        if (mats[i].cols != want) return fail(ctx, BFGPU_ERR_INVALID, "chip %s: trace width %llu, expected %u", names[i], (unsigned long long)mats[i].cols, want);
+        order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (mats[a].rows != mats[b].rows) return mats[a].rows > mats[b].rows;
+        return strcmp(names[a], names[b]) < 0;
+    });
+    bfgpu_pcs_data* pd = new bfgpu_pcs_data();
+    pd->ctx = ctx;
+    pd->ldes.resize(n);
+    out_traces->resize(n);
+    int32_t rc = BFGPU_OK;
+    const uint32_t gen = kb::to_mont(kb::GEN);
+    for (int k = 0; k < n && rc == BFGPU_OK; k++) {
+        int i = order[k];
+        out_names->push_back(names[i]);
+        out_chip->push_back(chip_index(names[i]));
+        rc = lde_device(ctx, mats[i], ctx->log_blowup, gen, &pd->ldes[k], &(*out_traces)[k]);
+    }
+    if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree);
+    if (rc == BFGPU_OK) {
+        CU(cudaMemcpyAsync(root_mont, pd->tree->layers.back(), 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (rc != BFGPU_OK) {
+        bfgpu_pcs_data_free(pd);
+        for (DMat& m : *out_traces) dfree(ctx, m.d);
+        return rc;
+    }
+    *out_data = pd;
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_machine_setup(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* prep_traces, int32_t n, uint32_t commit[8],
+                                       bfgpu_pk** out) {
+    if (!ctx || !names || !prep_traces || n <= 0 || !commit || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    auto* pk = new bfgpu_pk();
+    pk->ctx = ctx;
+    int32_t rc = machine_commit(ctx, names, prep_traces, n, true, &pk->names, &pk->chip, &pk->traces, &pk->data, pk->commit);
+    if (rc != BFGPU_OK) {
+        delete pk;
+        return rc;
+    }
+    for (int i = 0; i < 8; i++) commit[i] = out_word(ctx, pk->commit[i]);
+    *out = pk;
+    return BFGPU_OK;
+}
+extern "C" void bfgpu_pk_free(bfgpu_pk* pk) {
+    if (!pk) return;
+    bfgpu_pcs_data_free(pk->data);
+    for (DMat& m : pk->traces) dfree(pk->ctx, m.d);
+    delete pk;
+}
+// StarkProvingKey::observe_into (prover.rs:595-601): the commitment then 7 zero elements
+extern "C" int32_t bfgpu_pk_observe_into(const bfgpu_pk* pk, bfgpu_challenger* ch) {
+    if (!pk || !ch) return BFGPU_ERR_INVALID;
+    box(ch)->ch.observe_slice(pk->commit, 8);
+    for (int i = 0; i < 7; i++) box(ch)->ch.observe(0);
+    return BFGPU_OK;
+}
+
+extern "C" int32_t bfgpu_machine_commit(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* traces, int32_t n, uint32_t root[8],
+                                        bfgpu_shard** out) {
+    if (!ctx || !names || !traces || n <= 0 || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    auto* sd = new bfgpu_shard();
+    sd->ctx = ctx;
+    int32_t rc = machine_commit(ctx, names, traces, n, false, &sd->names, &sd->chip, &sd->traces, &sd->data, sd->commit);
+    if (rc != BFGPU_OK) {
+        delete sd;
+        return rc;
+    }
+    for (int i = 0; i < 8; i++) root[i] = out_word(ctx, sd->commit[i]);
+    *out = sd;
+    return BFGPU_OK;
+}
+extern "C" void bfgpu_shard_free(bfgpu_shard* sd) {
+    if (!sd) return;
+    bfgpu_pcs_data_free(sd->data);
+    for (DMat& m : sd->traces) dfree(sd->ctx, m.d);
+    delete sd;
+}
+
+// inclusive scan of n ext elements in place (recursive block scan)
+static int32_t scan_ext(bfgpu_ctx* ctx, uint32_t* data, uint64_t n) {
+    uint64_t nb = (n + air::SCAN_BLOCK - 1) / air::SCAN_BLOCK;
+    if (nb <= 1) {
+        air::k_scan_blocks<<<1, air::SCAN_THREADS, 0, ctx->stream>>>((uint4*)data, n, nullptr);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        return BFGPU_OK;
+    }
+    uint32_t* totals = nullptr;
+    TRY(dalloc(ctx, (void**)&totals, nb * 16));
+    air::k_scan_blocks<<<(unsigned)nb, air::SCAN_THREADS, 0, ctx->stream>>>((uint4*)data, n, (uint4*)totals);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    TRY(scan_ext(ctx, totals, nb));
+    air::k_scan_add<<<(unsigned)((n + air::SCAN_THREADS - 1) / air::SCAN_THREADS), air::SCAN_THREADS, 0, ctx->stream>>>((uint4*)data, n, (const uint4*)totals);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    dfree(ctx, totals);
+    return BFGPU_OK;
+}
+
+// commit to device matrices given column-major with bit-reversed rows (consumed); lde shift per matrix
+static int32_t commit_bitrev_device(bfgpu_ctx* ctx, std::vector<DMat>& coefs, const std::vector<uint32_t>& shift_mont, bfgpu_pcs_data** out,
+                                    uint32_t root_mont[8]) {
+    bfgpu_pcs_data* pd = new bfgpu_pcs_data();
+    pd->ctx = ctx;
+    pd->ldes.resize(coefs.size());
+    int32_t rc = BFGPU_OK;
+    for (size_t i = 0; i < coefs.size() && rc == BFGPU_OK; i++) {
+        rc = lde_from_bitrev(ctx, coefs[i], ctx->log_blowup, shift_mont[i], &pd->ldes[i]);
+        coefs[i].d = nullptr;
+    }
+    if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree);
+    if (rc == BFGPU_OK) {
+        CU(cudaMemcpyAsync(root_mont, pd->tree->layers.back(), 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (rc != BFGPU_OK) {
+        bfgpu_pcs_data_free(pd);
+        return rc;
+    }
+    *out = pd;
+    return BFGPU_OK;
+}
+
+// CpuProver::open (prover.rs:242-553)
+extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const bfgpu_shard* sd, bfgpu_challenger* chh, int64_t fixed_pow_witness,
+                                      bfgpu_shard_proof** out) {
+    if (!ctx || !pk || !sd || !chh || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    bfgpu_challenger& ch = box(chh)->ch;
+    const size_t nchips = sd->names.size();
+    const uint32_t gen = kb::to_mont(kb::GEN);
+    if (ctx->log_blowup != 1) return fail(ctx, BFGPU_ERR_INVALID, "the machine prover requires log_blowup = 1 (kb31_poseidon2.rs:63)");
+    // pk matrix index of every chip (or -1)
+    std::vector<int> pk_idx(nchips, -1);
+    for (size_t i = 0; i < nchips; i++)
+        for (size_t k = 0; k < pk->names.size(); k++)
+            if (pk->names[k] == sd->names[i]) pk_idx[i] = (int)k;
+    for (size_t i = 0; i < nchips; i++) {
+        const air::ChipInfo& ci = air::CHIPS[sd->chip[i]];
+        if (ci.log_quotient_degree != 1) return fail(ctx, BFGPU_ERR_STATE, "chip %s: unsupported quotient degree", ci.name);
+        if (ci.prep_w && (pk_idx[i] < 0 || pk->traces[pk_idx[i]].rows != sd->traces[i].rows))
+            return fail(ctx, BFGPU_ERR_INVALID, "chip %s: preprocessed trace missing or of a different height", ci.name);
+    }
+    // ---- transcript: main commitment, LogUp challenges (prover.rs:266-272) ----------------------------------------
+    ch.observe_slice(sd->commit, 8);
+    air::Challenges chal;
+    chal.alpha = ch.sample_ext();
+    kb::Ext beta = ch.sample_ext();
+    chal.beta_pow[0] = kb::ext_one();
+    for (int k = 1; k < 8; k++) chal.beta_pow[k] = kb::ext_mul(chal.beta_pow[k - 1], beta);
+    chal.cumulative_sum = kb::ext_zero();
+
+    // ---- permutation traces (prover.rs:280-296 -> permutation.rs:75-148) --------------------------------------------
+    std::vector<DMat> perm(nchips);
+    std::vector<kb::Ext> csum(nchips);
+    {
+        Phase ph(ctx, BFGPU_PHASE_PERM);
+        for (size_t i = 0; i < nchips; i++) {
+            const air::ChipInfo& ci = air::CHIPS[sd->chip[i]];
+            const DMat& main = sd->traces[i];
+            uint64_t n = main.rows;
+            unsigned log_n = ilog2(n);
+            perm[i].rows = n;
+            perm[i].cols = 4 * ci.perm_w;
+            TRY(dalloc(ctx, (void**)&perm[i].d, n * perm[i].cols * 4));
+            uint32_t* rowsum = nullptr;
+            TRY(dalloc(ctx, (void**)&rowsum, n * 16));
+            const uint32_t* prep = pk_idx[i] >= 0 ? pk->traces[pk_idx[i]].d : nullptr;
+            air::k_perm_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(sd->chip[i], main.d, prep, log_n, chal, ci.perm_w, perm[i].d, rowsum);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            TRY(scan_ext(ctx, rowsum, n));
+            air::k_scan_fixup<<<(unsigned)((n + air::SCAN_THREADS - 1) / air::SCAN_THREADS), air::SCAN_THREADS, 0, ctx->stream>>>(
+                (const uint4*)rowsum, n, nullptr, log_n, perm[i].d + (uint64_t)4 * (ci.perm_w - 1) * n);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(csum[i].c, rowsum + 4 * (n - 1), 16, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            dfree(ctx, rowsum);
+        }
+    }
+    bfgpu_pcs_data* perm_data = nullptr;
+    uint32_t perm_root[8];
+    {
+        std::vector<uint32_t> shifts(nchips, gen);
+        TRY(commit_bitrev_device(ctx, perm, shifts, &perm_data, perm_root));
+    }
+    struct Cleanup {
+        bfgpu_pcs_data *a = nullptr, *b = nullptr;
+        ~Cleanup() { bfgpu_pcs_data_free(a); bfgpu_pcs_data_free(b); }
+    } cleanup;
+    cleanup.a = perm_data;
+    ch.observe_slice(perm_root, 8);
+    for (size_t i = 0; i < nchips; i++) ch.observe_ext(csum[i]);
+
+    // ---- quotient values (prover.rs:343-388 -> quotient.rs:18-165) ---------------------------------------------------
+    const kb::Ext alpha = ch.sample_ext();
+    std::vector<DMat> qchunks;
+    std::vector<uint32_t> qshifts;
+    {
+        Phase ph(ctx, BFGPU_PHASE_QUOTIENT);
+        std::vector<kb::Ext> apow(air::MAX_CONSTRAINTS);
+        apow[0] = kb::ext_one();
+        for (int k = 1; k < air::MAX_CONSTRAINTS; k++) apow[k] = kb::ext_mul(apow[k - 1], alpha);
+        kb::Ext* d_apow = nullptr;
+        TRY(dalloc(ctx, (void**)&d_apow, apow.size() * sizeof(kb::Ext)));
+        CU(cudaMemcpyAsync(d_apow, apow.data(), apow.size() * sizeof(kb::Ext), cudaMemcpyHostToDevice, ctx->stream));
+        for (size_t i = 0; i < nchips; i++) {
+            const air::ChipInfo& ci = air::CHIPS[sd->chip[i]];
+            unsigned log_n = ilog2(sd->traces[i].rows);
+            uint64_t n = 1ull << log_n;
+            air::QuotientArgs qa;
+            qa.chip = sd->chip[i];
+            qa.main = sd->data->ldes[i].d;
+            qa.prep = pk_idx[i] >= 0 ? pk->data->ldes[pk_idx[i]].d : nullptr;
+            qa.perm = perm_data->ldes[i].d;
+            qa.log_n = log_n;
+            qa.lqd = 1;
+            qa.shift = gen;
+            qa.g_inv = kb::inv(kb::two_adic_generator(log_n));
+            uint32_t sn = kb::pow(gen, n);
+            qa.zh[0] = kb::sub(sn, kb::ONE);
+            qa.zh[1] = kb::sub(kb::neg(sn), kb::ONE);
+            qa.zh_inv[0] = kb::inv(qa.zh[0]);
+            qa.zh_inv[1] = kb::inv(qa.zh[1]);
+            qa.apow = d_apow;
+            qa.tw = ctx->d_tw;
+            uint32_t* q = nullptr;
+            TRY(dalloc(ctx, (void**)&q, 2 * n * 16));
+            qa.out = q;
+            air::Challenges c2 = chal;
+            c2.cumulative_sum = csum[i];
+            air::k_quotient<<<(unsigned)((2 * n + 127) / 128), 128, 0, ctx->stream>>>(qa, c2);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            // split_evals / split_domains (prover.rs:391-402): chunk c lives on the coset 3 w_{2n}^c H, LDE shift = GEN / that
+            uint32_t w2n = kb::two_adic_generator(log_n + 1);
+            for (int c = 0; c < 2; c++) {
+                DMat m;
+                m.rows = n;
+                m.cols = 4;
+                TRY(dalloc(ctx, (void**)&m.d, n * 16));
+                CU(cudaMemcpyAsync(m.d, q + (uint64_t)c * 4 * n, n * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+                qchunks.push_back(m);
+                qshifts.push_back(c == 0 ? kb::ONE : kb::inv(w2n));
+            }
+            dfree(ctx, q);
+            (void)ci;
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+        dfree(ctx, d_apow);
+    }
+    bfgpu_pcs_data* quot_data = nullptr;
+    uint32_t quot_root[8];
+    TRY(commit_bitrev_device(ctx, qchunks, qshifts, &quot_data, quot_root));
+    cleanup.b = quot_data;
+    ch.observe_slice(quot_root, 8);
+
+    // ---- opening points (prover.rs:415-458) and Pcs::open -----------------------------------------------------------------
+    const kb::Ext zeta = ch.sample_ext();
+    auto push_ext = [&](std::vector<uint32_t>& v, const kb::Ext& e) {
+        for (int k = 0; k < 4; k++) v.push_back(out_word(ctx, e.c[k]));
+    };
+    auto next_point = [&](unsigned log_n) { return kb::ext_scale(zeta, kb::two_adic_generator(log_n)); };
+    std::vector<uint32_t> np[4], pts[4];
+    for (size_t k = 0; k < pk->names.size(); k++) {
+        bool both = !air::CHIPS[pk->chip[k]].local_only;
+        np[0].push_back(both ? 2 : 1);
+        push_ext(pts[0], zeta);
+        if (both) push_ext(pts[0], next_point(ilog2(pk->traces[k].rows)));
+    }
+    for (size_t i = 0; i < nchips; i++) {
+        unsigned log_n = ilog2(sd->traces[i].rows);
+        bool both = !air::CHIPS[sd->chip[i]].local_only;
+        np[1].push_back(both ? 2 : 1);
+        push_ext(pts[1], zeta);
+        if (both) push_ext(pts[1], next_point(log_n));
+        np[2].push_back(2);
+        push_ext(pts[2], zeta);
+        push_ext(pts[2], next_point(log_n));
+        for (int c = 0; c < 2; c++) {
+            np[3].push_back(1);
+            push_ext(pts[3], zeta);
+        }
+    }
+    bfgpu_open_round rounds[4] = {{pk->data, np[0].data(), pts[0].data()},
+                                  {sd->data, np[1].data(), pts[1].data()},
+                                  {perm_data, np[2].data(), pts[2].data()},
+                                  {quot_data, np[3].data(), pts[3].data()}};
+    bfgpu_opening* op = nullptr;
+    TRY(bfgpu_pcs_open(ctx, rounds, 4, chh, fixed_pow_witness, &op));
+
+    // ---- ShardProof (types.rs:32-73): commitments, per-chip (index, log_degree, cumulative sum), opening -------------------
+    auto* proof = new bfgpu_shard_proof();
+    auto& flat = proof->flat;
+    for (int k = 0; k < 8; k++) flat.push_back(out_word(ctx, sd->commit[k]));
+    for (int k = 0; k < 8; k++) flat.push_back(out_word(ctx, perm_root[k]));
+    for (int k = 0; k < 8; k++) flat.push_back(out_word(ctx, quot_root[k]));
+    flat.push_back((uint32_t)nchips);
+    for (size_t i = 0; i < nchips; i++) {
+        flat.push_back((uint32_t)sd->chip[i]);
+        flat.push_back(ilog2(sd->traces[i].rows));
+        for (int k = 0; k < 4; k++) flat.push_back(out_word(ctx, csum[i].c[k]));
+    }
+    flat.insert(flat.end(), op->flat.begin(), op->flat.end());
+    bfgpu_opening_free(op);
+    *out = proof;
+    return BFGPU_OK;
+}
+extern "C" uint64_t bfgpu_shard_proof_size(const bfgpu_shard_proof* p) { return p ? p->flat.size() : 0; }
+extern "C" int32_t bfgpu_shard_proof_read(const bfgpu_shard_proof* p, uint32_t* out) {
+    if (!p || !out) return BFGPU_ERR_INVALID;
+    memcpy(out, p->flat.data(), p->flat.size() * 4);
+    return BFGPU_OK;
+}
+extern "C" void bfgpu_shard_proof_free(bfgpu_shard_proof* p) { delete p; }
+extern "C" int32_t bfgpu_machine_num_chips(void) { return air::NUM_CHIPS; }
+extern "C" int32_t bfgpu_machine_chip_info(int32_t i, const char** name, int32_t* main_w, int32_t* prep_w, int32_t* perm_w, int32_t* local_only) {
+    if (i < 0 || i >= air::NUM_CHIPS) return BFGPU_ERR_INVALID;
+    if (name) *name = air::CHIPS[i].name;
+    if (main_w) *main_w = air::CHIPS[i].main_w;
+    if (prep_w) *prep_w = air::CHIPS[i].prep_w;
+    if (perm_w) *perm_w = air::CHIPS[i].perm_w;
+    if (local_only) *local_only = air::CHIPS[i].local_only;
     return BFGPU_OK;
 }
