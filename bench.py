@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cols", type=int, default=256)
     ap.add_argument("--cpu-log-rows", type=int, default=16, help="bounded CPU sample height (log2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prove", action="store_true", help="skip the end-to-end shard-prove timings (BASELINE configs 1-3)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -82,6 +83,52 @@ def cpu_commit_sample(log_rows, cols, steps, warmup):
             times.append(dt)
     sec = sum(times) / len(times)
     return algorithmic_bytes(1 << log_rows, cols) / sec / 1e9, sec, oracle.get_threads()
+
+
+def prove_timings(ctx, bf, with_cpu):
+    """End-to-end shard proofs (MachineProver::prove minus trace generation) of BASELINE configs 1-3 on this GPU:
+    host traces in, proof out, wall-clock of the public API call, best of 3 after one warm-up."""
+    import importlib
+    import numpy as np
+    ex = importlib.import_module("zkvm-brainfuck_b200.machine.executor")
+    tg = importlib.import_module("zkvm-brainfuck_b200.machine.tracegen")
+    gold = os.path.join(ROOT, "tests", "golden")
+    progs = {"fibo_stdin17 (config 1, test_e2e_core)": (open(os.path.join(gold, "fibo.bf")).read(), [17]),
+             "hello (config 2)": (open(os.path.join(gold, "hello.bf")).read(), []),
+             "loop 2^20 Cpu rows (config 3)": ("-[>-[>+>+>+<<<-]<-]", [])}
+    prover = bf.CudaProver(ctx)
+    out = {}
+    for name, (code, stdin) in progs.items():
+        prog = ex.Program(code)
+        rec = ex.execute(prog, stdin)
+        traces, preps = tg.generate_traces(rec), tg.preprocessed_traces(prog)
+        pk = prover.setup(preps)
+        times = []
+        for _ in range(4):
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            proof = prover.prove(pk, traces, bf.Challenger(ctx))
+            times.append((time.perf_counter() - t0) * 1e3)
+        best = min(times[1:])
+        entry = {"cycles": rec.cycles, "cpu_rows": int(traces["Cpu"].shape[0]), "committed_main_cells": int(sum(v.size for v in traces.values())),
+                 "prove_ms": best, "trace_rows_per_s": float(traces["Cpu"].shape[0]) / (best * 1e-3), "khz": rec.cycles / best,
+                 "main_root": [int(x) for x in proof["commitment"]["main"]]}
+        if with_cpu and name.startswith("hello"):
+            # CPU oracle of the same proof (numpy + C, single process): parity check + a rough CPU figure
+            from oracle import prover as PR, stark as S
+            chips = importlib.import_module("zkvm-brainfuck_b200.air.chips").machine_chips()
+            t0 = time.perf_counter()
+            opk = PR.setup(chips, preps)
+            och = S.Challenger()
+            PR.observe_pk(opk, och)
+            ref = PR.prove_shard(chips, opk, traces, och.clone())
+            entry["cpu_oracle_prove_ms"] = (time.perf_counter() - t0) * 1e3
+            entry["proof_matches_cpu_oracle"] = bool(all((np.asarray(proof["commitment"][k]) == ref["commitment"][k]).all() for k in ("main", "permutation", "quotient"))
+                                                     and (np.asarray(proof["opening_proof"]["final_poly"]) == ref["opening_proof"]["final_poly"]).all()
+                                                     and proof["opening_proof"]["pow_witness"] == ref["opening_proof"]["pow_witness"])
+        out[name] = entry
+        pk.free()
+    return out
 
 
 def run_reference(args, rank):
@@ -286,6 +333,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if world == 1 and not args.no_prove:
+            line["prove"] = prove_timings(ctx, bf, not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             gbs, sec, threads = cpu_commit_sample(args.cpu_log_rows, W, 1, 1)
             line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",

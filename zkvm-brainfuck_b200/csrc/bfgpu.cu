@@ -485,7 +485,8 @@ static int32_t get_plan(bfgpu_ctx* ctx, unsigned log_n, bool inverse, const std:
 
 template <bool INVERSE, int G1>
 static void launch_pass(bfgpu_ctx* ctx, const ntt2::PassArgs& a, dim3 grid) {
-    ntt2::k_pass<INVERSE, G1><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
+    if (a.p == 0) ntt2::k_pass<INVERSE, G1, true><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
+    else ntt2::k_pass<INVERSE, G1, false><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
 }
 
 // Run all stages of a size-2^log_n transform on `ncols` column vectors (stride col_stride words).
@@ -512,7 +513,7 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
         uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
         uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, ncols), (ncols + want_groups - 1) / want_groups);
         cpc = std::min<uint32_t>(cpc, 64);
-        ntt2::PassArgs a{data, col_stride, ncols, cpc, ps.p, ps.p != 0 ? 1u : 0u, ps.twA, ps.twB, nullptr, nullptr, 0, log_n};
+        ntt2::PassArgs a{data, col_stride, ncols, cpc, ps.p, ps.twA, ps.twB, nullptr, nullptr, 0, log_n};
         if (INVERSE && s + 1 == np && epi.pw) {
             a.pw = epi.pw;
             a.out = epi.out;

@@ -6,27 +6,31 @@
 // One pass executes g <= 8 radix-2 stages (index bits [p, p+g)) as two register phases:
 //   phase A: radix 2^G1 on the top G1 = g-4 bits of the pass digit,
 //   phase B: radix 2^G2 on the low G2 = 4 bits,
-// with one shared-memory exchange in between.  A CTA owns one tile position (2^g digits x 16 lanes)
+// with ONE shared-memory exchange in between.  A CTA owns one tile position (2^g digits x 16 lanes)
 // and loops over a group of columns: every column at that position uses the same twiddles, so the
 // 15 + 15 inter-phase twiddles per thread are loaded once (coalesced, from a per-pass table) and kept
 // in registers for the whole loop.  Inside a radix-16 the twiddles are the eight 16th roots of unity,
 // held in constant memory.
+//
+// Memory traffic per element and pass: one global load and one global store issued DIRECTLY in the
+// register layout of the first / last phase (64-byte segments in strided passes, 64-byte runs or 16-byte
+// vectors in the contiguous pass), one shared store + one shared load for the exchange: 4 LSU
+// operations (the first version staged global<->shared and paid 8; ncu showed the LSU pipe 80% busy,
+// profiles/r1_ntt_pass_v2.md).  The next column's tile is prefetched into registers while the current
+// one is transformed, and the shared tile is double buffered, so one barrier per column suffices.
 //
 // Multiplications by twiddles use Shoup's precomputed-quotient form (w, w' = floor(w 2^32 / p)):
 //   q = mulhi(a, w');  r = a*w - q*p  in [0, 2p)   for ANY a < 2^32
 // i.e. IMAD.HI + 2 IMAD and one min-correction, one FMA-pipe slot and one ALU op fewer than a
 // Montgomery product, and the multiplicand may be an unreduced difference a - b + p.
 // Data stay in Montgomery form (twiddles are plain residues, so x~ * w = (x w)~).
-//
-// Shared-memory tile: idx(d, lane) = d*17 + lane  (row stride 17 => conflict-free for the global
-// staging in both orientations and for both phase access patterns).
 #pragma once
 #include "kb31.cuh"
 
 namespace ntt2 {
 
 constexpr int LANES = 16;
-constexpr int ROW = 17;  // padded row stride of the smem tile
+constexpr int ROW = 17;  // padded row stride of the strided-mode tile  [digit][lane]
 constexpr int G2 = 4;    // phase B radix bits
 
 struct Tw {
@@ -127,8 +131,7 @@ struct PassArgs {
     uint64_t col_stride;  // words between columns
     uint32_t ncols;       // total columns
     uint32_t cols_per_cta;
-    uint32_t p;           // low bit of the pass
-    uint32_t strided;     // p != 0
+    uint32_t p;           // low bit of the pass (0 in the contiguous pass)
     const Tw* twA;        // [(2^G1 - 1)][2^(p+4)]  exponent q*m, transform size 2^(p+g)
     const Tw* twB;        // [15][2^p]              exponent q*lo, transform size 2^(p+4); null when p == 0
     // optional fused epilogue of the LAST inverse pass (coset scaling + blow-up): when pw != null the
@@ -140,18 +143,31 @@ struct PassArgs {
     uint32_t log_n;
 };
 
-// G1 in 0..4 (g = G1 + 4).  Threads per CTA = 2^g.
-template <bool INV, int G1>
+// Shared tile index of element (digit d, lane l).
+//   strided pass   : d*17 + l  (phase A warps read 16 lanes x 2 digits, phase B 16 lanes x 2 high digits: both conflict free)
+//   contiguous pass: l*(2^g + 16) + a*16 + swizzled b, where d = a*16 + b and the four 16-byte chunks of a thread's
+//                    64-byte row are XOR-ed with (a >> 1) & 3, so that phase B can move its 16 consecutive words with
+//                    four conflict-free 128-bit accesses while phase A (16 consecutive b, fixed a) stays conflict free.
+template <int g, bool CONTIG>
+__device__ __forceinline__ uint32_t tile_idx(uint32_t d, uint32_t l) {
+    if (!CONTIG) return d * ROW + l;
+    uint32_t a = d >> 4, b = d & 15;
+    return l * ((1u << g) + 16) + a * 16 + ((((b >> 2) ^ (a >> 1)) & 3) << 2) + (b & 3);
+}
+
+// G1 in 0..4 (g = G1 + 4).  Threads per CTA = 2^g.  CONTIG: p == 0 (lanes = 16 consecutive runs of 2^g words).
+template <bool INV, int G1, bool CONTIG>
 __global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
     constexpr int g = G1 + G2, NT = 1 << g;
     constexpr int RA = 1 << G1, NGA = 16 >> G1;  // phase A: radix, groups per thread
-    __shared__ uint32_t sm[2][NT * ROW];
+    constexpr int TILE_WORDS = CONTIG ? 16 * (NT + 16) : NT * ROW;
+    __shared__ __align__(16) uint32_t sm[2][TILE_WORDS];
     const uint32_t t = threadIdx.x;
     const uint32_t p = A.p;
     // tile position
     uint64_t base;
     uint32_t lo_base = 0;
-    if (A.strided) {
+    if (!CONTIG) {
         uint32_t lo_blocks_log = p - 4;
         uint32_t lo_block = blockIdx.x & ((1u << lo_blocks_log) - 1);
         uint64_t hi = blockIdx.x >> lo_blocks_log;
@@ -160,124 +176,168 @@ __global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
     } else {
         base = (uint64_t)blockIdx.x << (g + 4);
     }
+    // ---- per-thread coordinates ------------------------------------------------------------------------
+    // phase A combos j < NGA: (r1, lane); strided: lane fastest across the warp, contiguous: r1 fastest.
+    // phase B: one combo (a, lane); strided: lane fastest; contiguous: lane = t >> G1, a = t & (RA-1).
+    uint32_t laneA[NGA], r1A[NGA];
+#pragma unroll
+    for (int j = 0; j < NGA; j++) {
+        uint32_t cidx = t + j * NT;
+        laneA[j] = CONTIG ? cidx >> 4 : cidx & 15;
+        r1A[j] = CONTIG ? cidx & 15 : cidx >> 4;
+    }
+    const uint32_t laneB = CONTIG ? t >> G1 : t & 15;
+    const uint32_t aB = CONTIG ? t & (RA - 1) : t >> 4;
+    // word offset (inside the tile's address range) of element (d, lane)
+    auto goff = [&](uint32_t d, uint32_t lane) -> uint64_t { return CONTIG ? ((uint64_t)lane << g) + d : ((uint64_t)d << p) + lane; };
+
     // ---- twiddles for this tile position (registers, reused for every column) -------------------
     Tw twa[15], twb[15];
-    // phase A combos: cidx = t + j*NT, cidx = (r1 << 4) | lane ; m = (r1 << p) | lo
     if (G1 > 0) {
 #pragma unroll
         for (int j = 0; j < NGA; j++) {
-            uint32_t cidx = t + j * NT;
-            uint32_t lane = cidx & 15, r1 = cidx >> 4;
-            uint32_t m = A.strided ? ((r1 << p) | (lo_base + lane)) : r1;
-            uint32_t M = A.strided ? (1u << (p + 4)) : 16u;
+            uint32_t m = CONTIG ? r1A[j] : ((r1A[j] << p) | (lo_base + laneA[j]));
+            uint32_t M = CONTIG ? 16u : (1u << (p + 4));
 #pragma unroll
             for (int q = 1; q < RA; q++) twa[j * (RA - 1) + q - 1] = A.twA[(uint64_t)(q - 1) * M + m];
         }
     }
-    const bool has_b = A.strided;
-    if (has_b) {
-        uint32_t lane = t & 15;
+    if (!CONTIG) {
 #pragma unroll
-        for (int q = 1; q < 16; q++) twb[q - 1] = A.twB[(uint64_t)(q - 1) << p | (lo_base + lane)];
+        for (int q = 1; q < 16; q++) twb[q - 1] = A.twB[(uint64_t)(q - 1) << p | (lo_base + laneB)];
     }
     const uint32_t c_begin = blockIdx.y * A.cols_per_cta;
     const uint32_t c_end = min(A.ncols, c_begin + A.cols_per_cta);
-    uint32_t v[16];
-    int buf = 0;
-    // Software pipeline: the tile of column c+1 is loaded into registers (nx) while column c is being
-    // transformed, so HBM latency overlaps the butterflies inside one CTA.  (cp.async 4-byte LDGSTS
-    // was measured slower: 16 LDGSTS per thread per column saturate the LSU issue rate.)
+
+    // ---- global <-> register moves in the phase layouts --------------------------------------------------
     uint32_t nx[16];
-    auto load_tile = [&](uint32_t c) {
-        const uint32_t* col = A.data + (uint64_t)c * A.col_stride + base;
-        if (A.strided) {
+    auto load_A = [&](const uint32_t* col, uint32_t* r) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                uint32_t f = t + i * NT;  // d = f >> 4, lane = f & 15
-                nx[i] = col[((uint64_t)(f >> 4) << p) + (f & 15)];
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) r[j * RA + a] = col[goff(((uint32_t)a << G2) | r1A[j], laneA[j])];
+    };
+    auto load_B = [&](const uint32_t* col, uint32_t* r) {
+        if (CONTIG) {
+            const uint4* q = reinterpret_cast<const uint4*>(col + goff(aB << G2, laneB));
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint4 x = q[k];
+                r[4 * k] = x.x; r[4 * k + 1] = x.y; r[4 * k + 2] = x.z; r[4 * k + 3] = x.w;
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; i++) nx[i] = col[t + i * NT];  // lane = f >> g, d = f & (NT-1)
+            for (int b = 0; b < 16; b++) r[b] = col[goff((aB << G2) | b, laneB)];
         }
     };
-    if (c_begin < c_end) load_tile(c_begin);
+    auto store_B = [&](uint32_t* col, const uint32_t* r) {
+        if (CONTIG) {
+            uint4* q = reinterpret_cast<uint4*>(col + goff(aB << G2, laneB));
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 16; b++) col[goff((aB << G2) | b, laneB)] = r[b];
+        }
+    };
+    // ---- shared exchange -------------------------------------------------------------------------------------
+    auto sts_A = [&](uint32_t* s, const uint32_t* r) {
+#pragma unroll
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) s[tile_idx<g, CONTIG>(((uint32_t)a << G2) | r1A[j], laneA[j])] = r[j * RA + a];
+    };
+    auto lds_A = [&](const uint32_t* s, uint32_t* r) {
+#pragma unroll
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) r[j * RA + a] = s[tile_idx<g, CONTIG>(((uint32_t)a << G2) | r1A[j], laneA[j])];
+    };
+    auto sts_B = [&](uint32_t* s, const uint32_t* r) {
+        if (CONTIG) {
+            uint32_t rowbase = laneB * (NT + 16) + aB * 16;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                *reinterpret_cast<uint4*>(s + rowbase + (((k ^ (aB >> 1)) & 3) << 2)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 16; b++) s[tile_idx<g, CONTIG>((aB << G2) | b, laneB)] = r[b];
+        }
+    };
+    auto lds_B = [&](const uint32_t* s, uint32_t* r) {
+        if (CONTIG) {
+            uint32_t rowbase = laneB * (NT + 16) + aB * 16;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint4 x = *reinterpret_cast<const uint4*>(s + rowbase + (((k ^ (aB >> 1)) & 3) << 2));
+                r[4 * k] = x.x; r[4 * k + 1] = x.y; r[4 * k + 2] = x.z; r[4 * k + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 16; b++) r[b] = s[tile_idx<g, CONTIG>((aB << G2) | b, laneB)];
+        }
+    };
+
+    auto colptr = [&](uint32_t c) { return A.data + (uint64_t)c * A.col_stride + base; };
+    // first phase of the pass: forward = A (when G1 > 0), inverse = B
+    auto load_first = [&](uint32_t c) {
+        if (!INV && G1 > 0) load_A(colptr(c), nx);
+        else load_B(colptr(c), nx);
+    };
+    if (c_begin < c_end) load_first(c_begin);
+    uint32_t v[16];
+    int buf = 0;
     for (uint32_t c = c_begin; c < c_end; c++, buf ^= 1) {
         uint32_t* s = sm[buf];
-        if (A.strided) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                uint32_t f = t + i * NT;
-                s[(f >> 4) * ROW + (f & 15)] = nx[i];
+        for (int i = 0; i < 16; i++) v[i] = nx[i];
+        if (c + 1 < c_end) load_first(c + 1);  // software pipeline: next column's tile in flight during the butterflies
+        if (!INV) {
+            if (G1 > 0) {
+                phase<false, G1, true>(v, twa);
+                sts_A(s, v);
+                __syncthreads();  // double-buffered tile: one barrier per column
+                lds_B(s, v);
             }
+            if (!CONTIG) phase<false, G2, true>(v, twb);
+            else phase<false, G2, false>(v, twb);
+            store_B(colptr(c), v);
         } else {
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                uint32_t f = t + i * NT;
-                s[(f & (NT - 1)) * ROW + (f >> g)] = nx[i];
+            if (!CONTIG) phase<true, G2, true>(v, twb);
+            else phase<true, G2, false>(v, twb);
+            if (G1 > 0) {
+                sts_B(s, v);
+                __syncthreads();
+                lds_A(s, v);
+                phase<true, G1, true>(v, twa);
             }
-        }
-        if (c + 1 < c_end) load_tile(c + 1);
-        __syncthreads();  // tile c visible (double buffering: iteration c-1 read the other buffer)
-        // forward: phase A (high bits) then B; inverse: B then A
-#pragma unroll
-        for (int ph = 0; ph < 2; ph++) {
-            const bool doA = INV ? (ph == 1) : (ph == 0);
-            if (doA) {
+            // ---- store in the phase-A layout (phase-B layout when G1 == 0) ---------------------------------
+            if (A.pw != nullptr) {
+                const uint64_t n = 1ull << A.log_n;
+                uint32_t* ocol = A.out + (uint64_t)c * (n * A.ncosets);
                 if (G1 > 0) {
 #pragma unroll
-                    for (int j = 0; j < NGA; j++) {
-                        uint32_t cidx = t + j * NT;
-                        uint32_t lane = cidx & 15, r1 = cidx >> 4;
+                    for (int j = 0; j < NGA; j++)
 #pragma unroll
-                        for (int a = 0; a < RA; a++) v[j * RA + a] = s[((a << G2) | r1) * ROW + lane];
-                    }
-                    phase<INV, G1, true>(v, twa);
+                        for (int a = 0; a < RA; a++) {
+                            uint64_t idx = base + goff(((uint32_t)a << G2) | r1A[j], laneA[j]);
+                            for (uint32_t h = 0; h < A.ncosets; h++) ocol[h * n + idx] = kb::mul(v[j * RA + a], __ldg(A.pw + h * n + idx));
+                        }
+                } else {
 #pragma unroll
-                    for (int j = 0; j < NGA; j++) {
-                        uint32_t cidx = t + j * NT;
-                        uint32_t lane = cidx & 15, r1 = cidx >> 4;
-#pragma unroll
-                        for (int a = 0; a < RA; a++) s[((a << G2) | r1) * ROW + lane] = v[j * RA + a];
+                    for (int b = 0; b < 16; b++) {
+                        uint64_t idx = base + goff((aB << G2) | b, laneB);
+                        for (uint32_t h = 0; h < A.ncosets; h++) ocol[h * n + idx] = kb::mul(v[b], __ldg(A.pw + h * n + idx));
                     }
                 }
+            } else if (G1 > 0) {
+                uint32_t* col = colptr(c);
+#pragma unroll
+                for (int j = 0; j < NGA; j++)
+#pragma unroll
+                    for (int a = 0; a < RA; a++) col[goff(((uint32_t)a << G2) | r1A[j], laneA[j])] = v[j * RA + a];
             } else {
-                // phase B combo: (a, lane) = (t >> 4, t & 15)
-                uint32_t lane = t & 15, a = t >> 4;
-#pragma unroll
-                for (int b = 0; b < 16; b++) v[b] = s[((a << G2) | b) * ROW + lane];
-                if (has_b) phase<INV, G2, true>(v, twb);
-                else phase<INV, G2, false>(v, twb);
-#pragma unroll
-                for (int b = 0; b < 16; b++) s[((a << G2) | b) * ROW + lane] = v[b];
-            }
-            if (G1 > 0 || ph == 1 || !INV) __syncthreads();
-        }
-        // ---- stage out ----------------------------------------------------------------------------
-        if (INV && A.pw != nullptr) {
-            const uint64_t n = 1ull << A.log_n;
-            uint32_t* ocol = A.out + (uint64_t)c * (n * A.ncosets);
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                uint32_t f = t + i * NT;
-                uint64_t idx = A.strided ? base + ((uint64_t)(f >> 4) << p) + (f & 15) : base + f;
-                uint32_t x = A.strided ? s[(f >> 4) * ROW + (f & 15)] : s[(f & (NT - 1)) * ROW + (f >> g)];
-                for (uint32_t h = 0; h < A.ncosets; h++) ocol[h * n + idx] = kb::mul(x, __ldg(A.pw + h * n + idx));
-            }
-        } else {
-            uint32_t* col = A.data + (uint64_t)c * A.col_stride + base;
-            if (A.strided) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    uint32_t f = t + i * NT;
-                    col[((uint64_t)(f >> 4) << p) + (f & 15)] = s[(f >> 4) * ROW + (f & 15)];
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    uint32_t f = t + i * NT;
-                    col[f] = s[(f & (NT - 1)) * ROW + (f >> g)];
-                }
+                store_B(colptr(c), v);
             }
         }
     }
