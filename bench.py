@@ -30,8 +30,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 P = 2130706433
-# SASS thread-instructions of one Poseidon2 permutation in k_leaf_hash (cuobjdump count)
-P2_INSTR_PER_PERM = 4096
+# executed thread-instructions per Poseidon2 permutation in k_leaf_hash: ncu smsp__inst_executed.sum * 32 / permutations
+# (profiles/r1_leaf_hash_final.md)
+P2_INSTR_PER_PERM = 4606
+# DRAM bytes of one k_leaf_hash launch at the default workload, from the same ncu --set full capture
+LEAF_TRAFFIC_2P22X256 = 8603574000 + 273566720
 
 
 def log(*a):
@@ -323,7 +326,8 @@ def main():
             "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items() if v[1]},
             "roofline": {"kernel": "hashk::k_leaf_hash (Poseidon2 sponge, 1 thread/leaf)", "bound": "int32",
                          "achieved": leaf_giops, "peak": int32_peak, "unit": "Ginstr/s", "frac": leaf_giops / int32_peak,
-                         "traffic": None,
+                         "traffic": LEAF_TRAFFIC_2P22X256 if (args.log_rows, W) == (22, 256) else None,
+                         "algorithmic_bytes": 8 * R * W + 32 * 2 * R,
                          "note": f"achieved = {leaf_perms} permutations x {P2_INSTR_PER_PERM} SASS integer thread-instructions / {leaf_ms_per:.3f} ms; peak = live register-only IMAD/IADD/LOP3 probe (bfgpu_int32_peak_probe)"},
             "roofline_hbm": {"kernel": "LDE = k_ingest + k_ntt_pass<inv> + k_scale_cosets + k_ntt_pass<fwd>", "bound": "hbm",
                              "achieved": lde_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": lde_gbs / hbm_peak, "traffic": None,
