@@ -262,10 +262,9 @@ def main():
     ctx.profile_enable(False)
     clocks = sampler.stop()
     root_dev = root.copy()
-    if dist is not None:
-        t = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    from importlib import import_module
+    shard = import_module("zkvm-brainfuck_b200.shard")
+    ms_total = shard.max_over_ranks(ms_total, dist, "cuda")
     ms_step = ms_total / args.steps
     value = world * algorithmic_bytes(R, W) / (ms_step * 1e-3) / 1e9
 
@@ -291,10 +290,7 @@ def main():
             commit_host()
         ctx.synchronize()
         dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = shard.max_over_ranks(dt, dist, "cuda")
         e2e = {"value": world * algorithmic_bytes(R, W) / (dt / args.steps) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": 4 * R * W, "d2h_bytes_per_step": 32, "ms_per_step": dt / args.steps * 1e3}
         del host

@@ -1,0 +1,64 @@
+"""CPU test of the N>1 host logic with world_size-2 gloo process groups (the GPU path uses the same code over NCCL)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import zkvm_brainfuck_b200 as bf
+from importlib import import_module
+
+shard = import_module("zkvm-brainfuck_b200.shard")
+
+
+def test_plan_is_balanced_and_deterministic():
+    costs = [65536 * 31, 32768 * 41, 16384 * 7, 8192 * 45, 65536 * 2, 64, 192, 80]
+    a, b = shard.plan_units(costs, 4), shard.plan_units(costs, 4)
+    assert a == b and set(a) <= set(range(4))
+    load = [sum(c for c, o in zip(costs, a) if o == r) for r in range(4)]
+    assert max(load) == costs[0]  # the biggest unit alone bounds the makespan
+    assert shard.plan_units(costs, 1) == [0] * len(costs)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    costs = [10, 7, 5, 3, 1]
+    owner = shard.plan_units(costs, world)
+    mine = [i for i, o in enumerate(owner) if o == rank]
+    roots = np.array([[i * 8 + k for k in range(8)] for i in mine], np.uint32).reshape(-1, 8)
+    gathered = shard.gather_roots(roots, dist)
+    ms = shard.max_over_ranks(10.0 + rank, dist)
+    q.put((rank, owner, [g.tolist() for g in gathered], ms))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_and_max():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, owner0, g0, ms0), (r1, owner1, g1, ms1) = res
+    assert owner0 == owner1 and g0 == g1 and ms0 == ms1 == 11.0
+    # every unit's root arrives exactly once, grouped by owning rank
+    flat = [row[0] // 8 for grp in g0 for row in grp]
+    assert sorted(flat) == [0, 1, 2, 3, 4]
+    for rank, grp in enumerate(g0):
+        assert all(owner0[row[0] // 8] == rank for row in grp)
