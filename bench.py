@@ -98,13 +98,15 @@ def prove_timings(ctx, bf, with_cpu):
     gold = os.path.join(ROOT, "tests", "golden")
     progs = {"fibo_stdin17 (config 1, test_e2e_core)": (open(os.path.join(gold, "fibo.bf")).read(), [17]),
              "hello (config 2)": (open(os.path.join(gold, "hello.bf")).read(), []),
-             "loop 2^20 Cpu rows (config 3)": ("-[>-[>+>+>+<<<-]<-]", [])}
+             "loop 2^20 Cpu rows (config 3)": ("-[>-[>+>+>+<<<-]<-]", []),
+             "loop 2^22 Cpu rows (north-star size)": ("++++++++[>-[>-[>+>+<<-]<-]<-]", [])}
     prover = bf.CudaProver(ctx)
     out = {}
     for name, (code, stdin) in progs.items():
         prog = ex.Program(code)
         rec = ex.execute(prog, stdin)
         traces, preps = tg.generate_traces(rec), tg.preprocessed_traces(prog)
+        traces = {k: ctx.pinned_copy(v) for k, v in traces.items()}  # trace generators write into page-locked memory
         pk = prover.setup(preps)
         times = []
         for _ in range(4):
@@ -131,6 +133,7 @@ def prove_timings(ctx, bf, with_cpu):
                                                      and proof["opening_proof"]["pow_witness"] == ref["opening_proof"]["pow_witness"])
         out[name] = entry
         pk.free()
+        ctx.free_pinned()
     return out
 
 

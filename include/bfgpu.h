@@ -76,6 +76,12 @@ int32_t bfgpu_set_fri_params(bfgpu_ctx* ctx, uint32_t log_blowup, uint32_t num_q
 /* number of this library's kernels launched on the context since creation (bench evidence) */
 uint64_t bfgpu_launch_count(const bfgpu_ctx* ctx);
 
+/* page-locked host memory for caller matrices: cudaMemcpyAsync from pageable memory is staged by the driver at
+ * ~11 GB/s, from pinned memory it runs at PCIe speed (~55 GB/s measured).  Trace generators should write
+ * straight into such buffers. */
+int32_t bfgpu_host_alloc(bfgpu_ctx* ctx, uint64_t bytes, void** out);
+void bfgpu_host_free(void* p);
+
 /* ---- measurement hooks (bench.py): per-phase device time via CUDA events on the context's stream -- */
 enum {
     BFGPU_PHASE_H2D = 0,      /* host -> device copies of caller matrices                     */

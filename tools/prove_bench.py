@@ -37,6 +37,7 @@ def main():
         t0 = time.perf_counter()
         traces, preps = tg.generate_traces(rec), tg.preprocessed_traces(prog)
         t_trace = time.perf_counter() - t0
+        traces = {k: ctx.pinned_copy(v) for k, v in traces.items()}  # trace generators write into page-locked memory
         cells = sum(v.size for v in traces.values())
         pk = prover.setup(preps)
         times = []
@@ -57,6 +58,7 @@ def main():
                    pow_witness=proof["opening_proof"]["pow_witness"])
         print(json.dumps(out), flush=True)
         pk.free()
+        ctx.free_pinned()
     ctx.close()
 
 

@@ -49,6 +49,8 @@ ABI = {
     "bfgpu_synchronize": (C.c_int32, [C.c_void_p]),
     "bfgpu_set_fri_params": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "bfgpu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "bfgpu_host_alloc": (C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "bfgpu_host_free": (None, [C.c_void_p]),
     "bfgpu_profile_enable": (C.c_int32, [C.c_void_p, C.c_int]),
     "bfgpu_profile_read": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), _u64p]),
     "bfgpu_int32_peak_probe": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -157,6 +159,23 @@ class Context:
 
     def synchronize(self):
         self.check(lib().bfgpu_synchronize(self._h))
+
+    def pinned_copy(self, arr):
+        """Copy of `arr` in page-locked host memory (uint32), for full-speed host->device transfers."""
+        a = _u32(arr)
+        p = C.c_void_p()
+        self.check(lib().bfgpu_host_alloc(self._h, a.nbytes, C.byref(p)))
+        buf = (C.c_uint32 * max(a.size, 1)).from_address(p.value)
+        out = np.frombuffer(buf, dtype=np.uint32, count=a.size).reshape(a.shape)
+        out[...] = a
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p.value)
+        return out
+
+    def free_pinned(self):
+        for p in getattr(self, "_pinned", []):
+            lib().bfgpu_host_free(C.c_void_p(p))
+        self._pinned = []
 
     PHASES = ["h2d", "ingest", "intt", "scale", "ntt", "leaf_hash", "compress", "other", "open_eval", "open_reduce", "fri",
               "pow", "query", "perm", "quotient", "reserved"]

@@ -59,6 +59,11 @@ struct bfgpu_ctx {
     // dfree() can be handed out again immediately (stream order protects it).  Identical commits
     // reuse identical blocks; the CUDA async pool fragmented (a 4 GiB request carved out of the 8 GiB
     // block forced a fresh 8 GiB mapping every step).
+    // host->device copies of a multi-matrix commit are issued up front on a second stream so that the copy of
+    // matrix i+1 overlaps the LDE of matrix i (prestage_all / ingest)
+    cudaStream_t copy_stream = nullptr;
+    struct Prestaged { uint32_t* d; cudaEvent_t ready; };
+    std::map<const uint32_t*, Prestaged> prestaged;
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live;
     size_t cached_bytes = 0;
@@ -190,6 +195,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
         return fail(ctx, BFGPU_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback", cudaGetErrorString(e));
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
 
     // Poseidon2 constant bank (kb31_poseidon2.rs:35-50): internal constants = column 0 of table rows
@@ -252,6 +258,7 @@ extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
             if (ps.twB) cudaFree(ps.twB);
         }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 extern "C" const char* bfgpu_last_error(const bfgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -291,6 +298,15 @@ extern "C" int32_t bfgpu_set_fri_params(bfgpu_ctx* ctx, uint32_t log_blowup, uin
     return BFGPU_OK;
 }
 extern "C" uint64_t bfgpu_launch_count(const bfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int32_t bfgpu_host_alloc(bfgpu_ctx* ctx, uint64_t bytes, void** out) {
+    if (!ctx || !out) return BFGPU_ERR_INVALID;
+    CU(cudaHostAlloc(out, bytes ? bytes : 4, cudaHostAllocDefault));
+    return BFGPU_OK;
+}
+extern "C" void bfgpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
 
 // ---- measurement hooks -------------------------------------------------------------------------------
 extern "C" int32_t bfgpu_profile_enable(bfgpu_ctx* ctx, int on) {
@@ -373,6 +389,40 @@ extern "C" int32_t bfgpu_int32_peak_probe(bfgpu_ctx* ctx, double* giops) {
 // ---- staging helpers ----------------------------------------------------------------------------
 // Bring a caller matrix (row-major, host or device, caller representation) into a fresh
 // column-major Montgomery device matrix, optionally gathering rows in bit-reversed order.
+// Issue the host->device copies of all caller matrices on the copy stream (ordered after everything already
+// enqueued on the compute stream, because the staging blocks come from the single-stream block cache).
+static int32_t prestage_all(bfgpu_ctx* ctx, const bfgpu_mat* mats, int32_t n) {
+    if (ctx->input_space != BFGPU_MEM_HOST || n <= 1) return BFGPU_OK;
+    Phase ph(ctx, BFGPU_PHASE_H2D);
+    cudaEvent_t fence;
+    CU(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
+    CU(cudaEventRecord(fence, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, fence, 0));
+    cudaEventDestroy(fence);
+    for (int32_t i = 0; i < n; i++) {
+        size_t bytes = (size_t)mats[i].rows * mats[i].cols * 4;
+        if (!bytes || !mats[i].data || ctx->prestaged.count(mats[i].data)) continue;
+        bfgpu_ctx::Prestaged ps{nullptr, nullptr};
+        TRY(dalloc(ctx, (void**)&ps.d, bytes));
+        CU(cudaMemcpyAsync(ps.d, mats[i].data, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventCreateWithFlags(&ps.ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(ps.ready, ctx->copy_stream));
+        ctx->prestaged[mats[i].data] = ps;
+    }
+    return BFGPU_OK;
+}
+
+// drop copies that were issued but never consumed (error paths)
+static void prestage_clear(bfgpu_ctx* ctx) {
+    if (ctx->prestaged.empty()) return;
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (auto& kv : ctx->prestaged) {
+        cudaEventDestroy(kv.second.ready);
+        dfree(ctx, kv.second.d);
+    }
+    ctx->prestaged.clear();
+}
+
 static int32_t ingest(bfgpu_ctx* ctx, const bfgpu_mat& m, bool bitrev, DMat* out) {
     out->rows = m.rows;
     out->cols = (uint32_t)m.cols;
@@ -382,9 +432,17 @@ static int32_t ingest(bfgpu_ctx* ctx, const bfgpu_mat& m, bool bitrev, DMat* out
     const uint32_t* src = m.data;
     uint32_t* staged = nullptr;
     if (ctx->input_space == BFGPU_MEM_HOST) {
-        Phase ph(ctx, BFGPU_PHASE_H2D);
-        TRY(dalloc(ctx, (void**)&staged, bytes));
-        CU(cudaMemcpyAsync(staged, m.data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        auto it = ctx->prestaged.find(m.data);
+        if (it != ctx->prestaged.end()) {
+            staged = it->second.d;
+            CU(cudaStreamWaitEvent(ctx->stream, it->second.ready, 0));
+            cudaEventDestroy(it->second.ready);
+            ctx->prestaged.erase(it);
+        } else {
+            Phase ph(ctx, BFGPU_PHASE_H2D);
+            TRY(dalloc(ctx, (void**)&staged, bytes));
+            CU(cudaMemcpyAsync(staged, m.data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
         src = staged;
     }
     Phase ph(ctx, BFGPU_PHASE_INGEST);
@@ -766,6 +824,9 @@ static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfg
         dfree(ctx, (void*)colptr);
     }
     Phase ph(ctx, BFGPU_PHASE_COMPRESS);
+    std::vector<void*> colptrs_to_free;
+    hashk::TopArgs top;
+    memset(&top, 0, sizeof top);
     for (unsigned l = 1; l <= t->log_max; l++) {
         uint64_t len = max_h >> l;
         auto g = take_group(len);
@@ -776,11 +837,32 @@ static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfg
         TRY(dalloc(ctx, (void**)&layer, len * 32));
         t->layers.push_back(layer);
         t->layer_len.push_back(len);
+        uint32_t rs = g.empty() ? 1u : g[0]->rs;
+        if (2 * len <= hashk::TOP_MAX) {
+            // the rest of the tree is computed by one single-CTA launch
+            if (top.nlevels == 0) {
+                top.in = t->layers[l - 1];
+                top.len0 = (uint32_t)(2 * len);
+            }
+            top.out[top.nlevels] = layer;
+            top.colptr[top.nlevels] = colptr;
+            top.ncols[top.nlevels] = ncols;
+            top.row_stride[top.nlevels] = rs;
+            top.nlevels++;
+            colptrs_to_free.push_back((void*)colptr);
+            continue;
+        }
         hashk::k_compress_layer<<<(unsigned)((len + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(
-            t->layers[l - 1], layer, len, colptr, ncols, g.empty() ? 1u : g[0]->rs);
+            t->layers[l - 1], layer, len, colptr, ncols, rs);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
         dfree(ctx, (void*)colptr);
+    }
+    if (top.nlevels) {
+        hashk::k_compress_top<<<1, hashk::TOP_THREADS, 0, ctx->stream>>>(top);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        for (void* p : colptrs_to_free) dfree(ctx, p);
     }
     if (pos != n) return fail(ctx, BFGPU_ERR_INVALID, "matrix heights are not powers of two below the tallest");
     return BFGPU_OK;
@@ -875,7 +957,7 @@ extern "C" int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, cons
     bfgpu_pcs_data* pd = new bfgpu_pcs_data();
     pd->ctx = ctx;
     pd->ldes.resize(n);
-    int32_t rc = BFGPU_OK;
+    int32_t rc = prestage_all(ctx, evals, n);
     uint32_t gen = kb::to_mont(kb::GEN);
     for (int i = 0; i < n && rc == BFGPU_OK; i++) {
         // shift = GENERATOR / domain.shift  (TwoAdicFriPcs::commit)
@@ -887,6 +969,7 @@ extern "C" int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, cons
         }
         if (rc == BFGPU_OK) rc = lde_device(ctx, evals[i], ctx->log_blowup, shift, &pd->ldes[i]);
     }
+    prestage_clear(ctx);
     if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree);
     if (rc == BFGPU_OK) rc = read_digest(ctx, pd->tree->layers.back(), root);
     if (rc != BFGPU_OK) {
@@ -1066,50 +1149,67 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             *w = it->second;
             return BFGPU_OK;
         };
+        // launch every dot product first (results land in one buffer), then a single copy + synchronisation
+        struct Job {
+            MatPts* mp;
+            size_t t0;
+            uint32_t np;
+            size_t off;  // word offset of this job's sums (cols x np x 4) in sums_all
+        };
+        std::vector<Job> jobs;
+        size_t total_words = 0;
         for (auto& rv : R)
-            for (auto& mp : rv) {
-                const DMat& m = *mp.m;
-                uint32_t h = (uint32_t)(m.rows >> log_blowup);
-                unsigned log_h = ilog2(h);
-                uint32_t nchunks = (h + openk::BARY_ROWS - 1) / openk::BARY_ROWS;
-                mp.ys.resize(mp.pts.size());
+            for (auto& mp : rv)
                 for (size_t t0 = 0; t0 < mp.pts.size(); t0 += 2) {
                     uint32_t np = (uint32_t)std::min<size_t>(2, mp.pts.size() - t0);
-                    uint32_t *w0 = nullptr, *w1 = nullptr;
-                    TRY(weights(log_h, mp.pts[t0], &w0));
-                    if (np == 2) TRY(weights(log_h, mp.pts[t0 + 1], &w1));
-                    uint32_t *partial = nullptr, *sums = nullptr;
-                    size_t nsum = (size_t)m.cols * np * 4;
-                    TRY(dalloc(ctx, (void**)&partial, nsum * nchunks * 4));
-                    TRY(dalloc(ctx, (void**)&sums, nsum * 4));
-                    dim3 grid(nchunks, (m.cols + openk::BARY_COLS - 1) / openk::BARY_COLS);
-                    if (np == 1) openk::k_bary_dot<1><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(m.d, m.rows, m.cols, h, w0, w1, partial, nchunks);
-                    else openk::k_bary_dot<2><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(m.d, m.rows, m.cols, h, w0, w1, partial, nchunks);
-                    LAUNCHED(ctx);
-                    openk::k_bary_finish<<<(unsigned)((nsum + 127) / 128), 128, 0, ctx->stream>>>(partial, sums, m.cols, nchunks, np);
-                    LAUNCHED(ctx);
-                    CU(cudaGetLastError());
-                    std::vector<uint32_t> hs(nsum);
-                    CU(cudaMemcpyAsync(hs.data(), sums, nsum * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                    CU(cudaStreamSynchronize(ctx->stream));
-                    dfree(ctx, partial);
-                    dfree(ctx, sums);
-                    for (uint32_t t = 0; t < np; t++) {
-                        // p(z) = (z^h - s^h) / (h s^(h-1)) * sum
-                        const kb::Ext& z = mp.pts[t0 + t];
-                        kb::Ext zer = ext_pow(z, h);
-                        zer.c[0] = kb::sub(zer.c[0], kb::pow(gen, h));
-                        uint32_t den = kb::mul(kb::pow(gen, h - 1), kb::to_mont(h % kb::P));
-                        kb::Ext scale = kb::ext_scale(zer, kb::inv(den));
-                        auto& ys = mp.ys[t0 + t];
-                        ys.resize(m.cols);
-                        for (uint32_t c = 0; c < m.cols; c++) {
-                            const uint32_t* sp = &hs[((size_t)c * np + t) * 4];
-                            ys[c] = kb::ext_mul(scale, kb::Ext{{sp[0], sp[1], sp[2], sp[3]}});
-                        }
-                    }
+                    jobs.push_back({&mp, t0, np, total_words});
+                    total_words += (size_t)mp.m->cols * np * 4;
+                }
+        uint32_t* sums_all = nullptr;
+        TRY(dalloc(ctx, (void**)&sums_all, total_words * 4));
+        for (Job& jb : jobs) {
+            const DMat& m = *jb.mp->m;
+            uint32_t h = (uint32_t)(m.rows >> log_blowup);
+            unsigned log_h = ilog2(h);
+            uint32_t nchunks = (h + openk::BARY_ROWS - 1) / openk::BARY_ROWS;
+            uint32_t *w0 = nullptr, *w1 = nullptr;
+            TRY(weights(log_h, jb.mp->pts[jb.t0], &w0));
+            if (jb.np == 2) TRY(weights(log_h, jb.mp->pts[jb.t0 + 1], &w1));
+            uint32_t* partial = nullptr;
+            size_t nsum = (size_t)m.cols * jb.np * 4;
+            TRY(dalloc(ctx, (void**)&partial, nsum * nchunks * 4));
+            dim3 grid(nchunks, (m.cols + openk::BARY_COLS - 1) / openk::BARY_COLS);
+            if (jb.np == 1) openk::k_bary_dot<1><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(m.d, m.rows, m.cols, h, w0, w1, partial, nchunks);
+            else openk::k_bary_dot<2><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(m.d, m.rows, m.cols, h, w0, w1, partial, nchunks);
+            LAUNCHED(ctx);
+            openk::k_bary_finish<<<(unsigned)((nsum + 127) / 128), 128, 0, ctx->stream>>>(partial, sums_all + jb.off, m.cols, nchunks, jb.np);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            dfree(ctx, partial);
+        }
+        std::vector<uint32_t> hs(total_words);
+        CU(cudaMemcpyAsync(hs.data(), sums_all, total_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        dfree(ctx, sums_all);
+        for (Job& jb : jobs) {
+            const DMat& m = *jb.mp->m;
+            uint32_t h = (uint32_t)(m.rows >> log_blowup);
+            jb.mp->ys.resize(jb.mp->pts.size());
+            for (uint32_t t = 0; t < jb.np; t++) {
+                // p(z) = (z^h - s^h) / (h s^(h-1)) * sum
+                const kb::Ext& z = jb.mp->pts[jb.t0 + t];
+                kb::Ext zer = ext_pow(z, h);
+                zer.c[0] = kb::sub(zer.c[0], kb::pow(gen, h));
+                uint32_t den = kb::mul(kb::pow(gen, h - 1), kb::to_mont(h % kb::P));
+                kb::Ext scale = kb::ext_scale(zer, kb::inv(den));
+                auto& ys = jb.mp->ys[jb.t0 + t];
+                ys.resize(m.cols);
+                for (uint32_t c = 0; c < m.cols; c++) {
+                    const uint32_t* sp = &hs[jb.off + ((size_t)c * jb.np + t) * 4];
+                    ys[c] = kb::ext_mul(scale, kb::Ext{{sp[0], sp[1], sp[2], sp[3]}});
                 }
             }
+        }
         for (auto& kv : wcache) dfree(ctx, kv.second);
     }
     // opened values go to the proof and (Plonky3 "write evaluations to challenger") into the transcript
@@ -1411,7 +1511,10 @@ static int32_t machine_commit(bfgpu_ctx* ctx, const char* const* names, const bf
     pd->ctx = ctx;
     pd->ldes.resize(n);
     out_traces->resize(n);
-    int32_t rc = BFGPU_OK;
+    // copies in commit order, so the first LDE can start as soon as its own matrix has arrived
+    std::vector<bfgpu_mat> in_order(n);
+    for (int k = 0; k < n; k++) in_order[k] = mats[order[k]];
+    int32_t rc = prestage_all(ctx, in_order.data(), n);
     const uint32_t gen = kb::to_mont(kb::GEN);
     for (int k = 0; k < n && rc == BFGPU_OK; k++) {
         int i = order[k];
@@ -1419,6 +1522,7 @@ static int32_t machine_commit(bfgpu_ctx* ctx, const char* const* names, const bf
         out_chip->push_back(chip_index(names[i]));
         rc = lde_device(ctx, mats[i], ctx->log_blowup, gen, &pd->ldes[k], &(*out_traces)[k]);
     }
+    prestage_clear(ctx);
     if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree);
     if (rc == BFGPU_OK) {
         CU(cudaMemcpyAsync(root_mont, pd->tree->layers.back(), 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1582,9 +1686,9 @@ extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const 
             LAUNCHED(ctx);
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(csum[i].c, rowsum + 4 * (n - 1), 16, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            dfree(ctx, rowsum);
+            dfree(ctx, rowsum);  // stream-ordered reuse: the copy above is enqueued before any later writer
         }
+        CU(cudaStreamSynchronize(ctx->stream));
     }
     bfgpu_pcs_data* perm_data = nullptr;
     uint32_t perm_root[8];
