@@ -134,6 +134,24 @@ def test_mmcs_rejects_bad_shapes(ctx):
         mmcs.commit([np.zeros((0, 2), np.uint32)])
 
 
+def test_two_adicity_limit(ctx):
+    """KoalaBear has two-adicity 24: with blowup 2 the tallest committable matrix has 2^23 rows."""
+    with pytest.raises(bf.BfGpuError, match="two-adicity"):
+        bf.TwoAdicFriPcs(ctx).commit([np.zeros((1 << 24, 1), np.uint32)])
+    with pytest.raises(bf.BfGpuError, match="two-adicity"):
+        bf.Radix2Dit(ctx).coset_lde_batch(np.zeros((1 << 23, 1), np.uint32), 2, 3)
+
+
+def test_maximum_height_commit(ctx, oracle):
+    """2^23 x 1: the largest matrix the PCS can commit to (LDE 2^24 rows); root equals the oracle's."""
+    rng = np.random.default_rng(99)
+    a = rng.integers(0, P, (1 << 23, 1), dtype=np.uint32)
+    root, data = bf.TwoAdicFriPcs(ctx).commit([a])
+    ref = oracle.PcsData([a])
+    assert (root == ref.root).all()
+    data.free()
+
+
 def test_pcs_commit_matches_oracle(ctx, oracle):
     """Shapes of a small `CpuProver::commit` call: 8 chips, heights sorted tallest first."""
     rng = np.random.default_rng(77)

@@ -642,6 +642,8 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
 // coset LDE of a caller matrix.  keep != null: also return a copy of the ingested trace (column-major,
 // bit-reversed rows), which the LogUp kernel reads later.
 static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bits, uint32_t shift_mont, DMat* out, DMat* keep = nullptr) {
+    if (ilog2(m.rows) + added_bits > kb::TWO_ADICITY)
+        return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity (2^%d)", ilog2(m.rows) + added_bits, kb::TWO_ADICITY);
     DMat coef;
     TRY(ingest(ctx, m, /*bitrev=*/true, &coef));
     if (keep) {
