@@ -546,18 +546,29 @@ class CudaProver:
 
     def open(self, pk, shard, challenger, pow_witness=None):
         """MachineProver::open -> ShardProof as nested dicts (commitment, opened_values per chip, opening_proof, chip_ordering)."""
+        buf = self.open_raw(pk, shard, challenger, pow_witness)
+        return self._parse(buf, pk, shard)
+
+    def open_raw(self, pk, shard, challenger, pow_witness=None):
+        """MachineProver::open returning the serialised proof words (layout: include/bfgpu.h, bfgpu_machine_open)."""
         h = C.c_void_p()
         self.ctx.check(lib().bfgpu_machine_open(self.ctx._h, pk._h, shard._h, challenger._h, -1 if pow_witness is None else int(pow_witness), C.byref(h)))
         size = lib().bfgpu_shard_proof_size(h)
         buf = np.zeros(size, np.uint32)
         self.ctx.check(lib().bfgpu_shard_proof_read(h, _ptr(buf)))
         lib().bfgpu_shard_proof_free(h)
-        return self._parse(buf, pk, shard)
+        return buf
 
-    def prove(self, pk, traces, challenger, pow_witness=None):
-        """MachineProver::prove (prover.rs:560-582) minus trace generation: observe pk, commit, open on a clone."""
+    def prove(self, pk, traces, challenger, pow_witness=None, raw=False):
+        """MachineProver::prove (prover.rs:560-582) minus trace generation: observe pk, commit, open on a clone.
+        raw=True returns (serialised proof words, decoder) so that callers can time the prover without the Python decoding."""
         lib().bfgpu_pk_observe_into(pk._h, challenger._h)
         shard = self.commit(traces)
+        if raw:
+            buf = self.open_raw(pk, shard, challenger.clone(), pow_witness)
+            names, heights = list(shard.names), list(shard.heights)
+            shard.free()
+            return buf, (lambda: self._parse(buf, pk, None))
         proof = self.open(pk, shard, challenger.clone(), pow_witness)
         shard.free()
         return proof

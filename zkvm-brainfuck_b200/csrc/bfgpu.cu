@@ -24,6 +24,7 @@
 #include "kernels_ntt.cuh"
 #include "kernels_ntt2.cuh"
 #include <map>
+#include <tuple>
 #include <unordered_map>
 
 // ------------------------------------------------------------------------------------------------
@@ -55,6 +56,8 @@ struct bfgpu_ctx {
     // cached radix-16 pass plans (twiddle tables) per (log_n, inverse)
     struct NttPass { unsigned p, g; ntt2::Tw* twA; ntt2::Tw* twB; };
     std::map<std::pair<unsigned, bool>, std::vector<NttPass>> plans;
+    // cached coset scale vectors pw[h*n + k] = (shift_h)^k / n, keyed by (log_n, added_bits, shift)
+    std::map<std::tuple<unsigned, unsigned, uint32_t>, uint32_t*> pw_cache;
     // size-exact caching allocator: every buffer is used on ctx->stream only, so a block freed by
     // dfree() can be handed out again immediately (stream order protects it).  Identical commits
     // reuse identical blocks; the CUDA async pool fragmented (a 4 GiB request carved out of the 8 GiB
@@ -252,6 +255,7 @@ extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
     if (ctx->d_tw) cudaFree(ctx->d_tw);
     trim_cache(ctx);
     for (auto& kv : ctx->live) cudaFree(kv.first);
+    for (auto& kv : ctx->pw_cache) cudaFree(kv.second);
     for (auto& kv : ctx->plans)
         for (auto& ps : kv.second) {
             if (ps.twA) cudaFree(ps.twA);
@@ -601,19 +605,26 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     if (log_n + added_bits > kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
     uint64_t n = coef.rows, N = n << added_bits;
     uint32_t ncosets = 1u << added_bits;
-    // per-coset scale vectors: pw[h*n + k] = (shift * w_N^{bitrev(h)})^k / n
+    // per-coset scale vectors: pw[h*n + k] = (shift * w_N^{bitrev(h)})^k / n  (cached: a proof reuses a handful)
     uint32_t* pw = nullptr;
     {
-        Phase ph(ctx, BFGPU_PHASE_SCALE);
-        TRY(dalloc(ctx, (void**)&pw, N * 4));
-        uint32_t ninv = kb::inv(kb::to_mont((uint32_t)(n % kb::P)));
-        uint32_t wN = kb::two_adic_generator(log_n + added_bits);
-        for (uint32_t h = 0; h < ncosets; h++) {
-            uint32_t sh = kb::mul(shift_mont, kb::pow(wN, kb::bitrev(h, added_bits)));
-            nttk::k_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pw + h * n, sh, ninv, n);
-            LAUNCHED(ctx);
+        auto key = std::make_tuple(log_n, added_bits, shift_mont);
+        auto it = ctx->pw_cache.find(key);
+        if (it != ctx->pw_cache.end()) {
+            pw = it->second;
+        } else {
+            Phase ph(ctx, BFGPU_PHASE_SCALE);
+            CU(cudaMalloc(&pw, N * 4));
+            uint32_t ninv = kb::inv(kb::to_mont((uint32_t)(n % kb::P)));
+            uint32_t wN = kb::two_adic_generator(log_n + added_bits);
+            for (uint32_t h = 0; h < ncosets; h++) {
+                uint32_t sh = kb::mul(shift_mont, kb::pow(wN, kb::bitrev(h, added_bits)));
+                nttk::k_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pw + h * n, sh, ninv, n);
+                LAUNCHED(ctx);
+            }
+            CU(cudaGetLastError());
+            ctx->pw_cache[key] = pw;
         }
-        CU(cudaGetLastError());
     }
     out->rows = N;
     out->cols = coef.cols;
@@ -634,7 +645,6 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
         CU(cudaGetLastError());
     }
     dfree(ctx, coef.d);
-    dfree(ctx, pw);
     TRY(run_ntt<false>(ctx, out->d, n, log_n, coef.cols * ncosets));
     return BFGPU_OK;
 }
@@ -1679,7 +1689,12 @@ extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const 
             uint32_t* rowsum = nullptr;
             TRY(dalloc(ctx, (void**)&rowsum, n * 16));
             const uint32_t* prep = pk_idx[i] >= 0 ? pk->traces[pk_idx[i]].d : nullptr;
-            air::k_perm_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(sd->chip[i], main.d, prep, log_n, chal, ci.perm_w, perm[i].d, rowsum);
+#define BF_PERM_CASE(C) \
+    case C: air::k_perm_rows<C><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(C, main.d, prep, log_n, chal, ci.perm_w, perm[i].d, rowsum); break;
+            switch (sd->chip[i]) {
+                BF_PERM_CASE(0) BF_PERM_CASE(1) BF_PERM_CASE(2) BF_PERM_CASE(3) BF_PERM_CASE(4) BF_PERM_CASE(5) BF_PERM_CASE(6) BF_PERM_CASE(7)
+            }
+#undef BF_PERM_CASE
             LAUNCHED(ctx);
             CU(cudaGetLastError());
             TRY(scan_ext(ctx, rowsum, n));
@@ -1743,7 +1758,12 @@ extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const 
             qa.out = q;
             air::Challenges c2 = chal;
             c2.cumulative_sum = csum[i];
-            air::k_quotient<<<(unsigned)((2 * n + 127) / 128), 128, 0, ctx->stream>>>(qa, c2);
+#define BF_QUOT_CASE(C) \
+    case C: air::k_quotient<C><<<(unsigned)((2 * n + 127) / 128), 128, 0, ctx->stream>>>(qa, c2); break;
+            switch (qa.chip) {
+                BF_QUOT_CASE(0) BF_QUOT_CASE(1) BF_QUOT_CASE(2) BF_QUOT_CASE(3) BF_QUOT_CASE(4) BF_QUOT_CASE(5) BF_QUOT_CASE(6) BF_QUOT_CASE(7)
+            }
+#undef BF_QUOT_CASE
             LAUNCHED(ctx);
             CU(cudaGetLastError());
             // split_evals / split_domains (prover.rs:391-402): chunk c lives on the coset 3 w_{2n}^c H, LDE shift = GEN / that

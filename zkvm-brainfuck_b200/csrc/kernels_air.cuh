@@ -60,6 +60,7 @@ struct LdeLoader {
 // Thread t handles stored (bit-reversed) trace row t = natural row br(t).  Writes the batch columns
 // (perm_w - 1 ext columns = 4 base columns each) at stored position t and the row sum at NATURAL position
 // br(t) of `rowsum` (ext, AoS) for the prefix scan.
+template <int CHIP>  // one instantiation per chip: register allocation follows the chip's own program
 __global__ void __launch_bounds__(128) k_perm_rows(int chip, const uint32_t* __restrict__ main, const uint32_t* __restrict__ prep, unsigned log_n,
                                                    Challenges ch, int perm_w, uint32_t* __restrict__ perm_out, uint32_t* __restrict__ rowsum) {
     uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(128) k_perm_rows(int chip, const uint32_t* __r
     if (t >= n) return;
     TraceLoader ld{main, prep, n, t};
     kb::Ext out[MAX_PERM_W];
-    air_perm_row(chip, ld, ch, out);
+    (void)chip;
+    air_perm_row(CHIP, ld, ch, out);
     kb::Ext s = kb::ext_zero();
     for (int j = 0; j < perm_w - 1; j++) {
         s = kb::ext_add(s, out[j]);
@@ -153,6 +155,7 @@ __device__ __forceinline__ uint32_t root_pow_(const uint32_t* __restrict__ tw, u
     uint32_t v = __ldg(tw + ((uint64_t)(j & (half - 1)) << (kb::TWO_ADICITY - log_n)));
     return (j & half) ? kb::neg(v) : v;
 }
+template <int CHIP>
 __global__ void __launch_bounds__(128) k_quotient(QuotientArgs A, Challenges ch) {
     const unsigned L = A.log_n + A.lqd;
     const uint64_t N = 1ull << L, n = 1ull << A.log_n;
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientArgs A, Challenges ch)
     sel.is_last = kb::mul(zh, kb::inv(kb::sub(x, A.g_inv)));
     sel.is_trans = kb::sub(x, A.g_inv);
     kb::Ext acc = kb::ext_zero();
-    air_constraints(A.chip, ld, sel, ch, A.apow, acc);
+    air_constraints(CHIP, ld, sel, ch, A.apow, acc);
     acc = kb::ext_scale(acc, zh_inv);
     // chunk c = i mod 2^lqd holds natural rows i >> lqd; its bit-reversed position is t mod n, and c = t >> log_n
     uint32_t c = (uint32_t)(t >> A.log_n);
