@@ -26,7 +26,8 @@ def build(force=False, verbose=False):
     if not (force or needs_build()):
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(_DIR, "csrc", "bfgpu.cu")]
+    extra = os.environ.get("BFGPU_NVCC_EXTRA", "").split()  # experiment switches, e.g. -DNTT2_MONT_TW=1
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(_DIR, "csrc", "bfgpu.cu")]
     subprocess.check_call(cmd)
     return SO
 

@@ -54,7 +54,7 @@ struct bfgpu_ctx {
     uint64_t phase_launches[BFGPU_NUM_PHASES] = {0};
     int cur_phase = -1;
     // cached radix-16 pass plans (twiddle tables) per (log_n, inverse)
-    struct NttPass { unsigned p, g; ntt2::Tw* twA; ntt2::Tw* twB; };
+    struct NttPass { unsigned p, g; ntt2::TWT* twA; ntt2::TWT* twB; };
     std::map<std::pair<unsigned, bool>, std::vector<NttPass>> plans;
     // cached coset scale vectors pw[h*n + k] = (shift_h)^k / n, keyed by (log_n, added_bits, shift)
     std::map<std::tuple<unsigned, unsigned, uint32_t>, uint32_t*> pw_cache;
@@ -524,14 +524,14 @@ static int32_t get_plan(bfgpu_ctx* ctx, unsigned log_n, bool inverse, const std:
             unsigned G1 = ps.g - 4;
             if (G1 > 0) {
                 uint32_t nq = (1u << G1) - 1, M = 1u << (ps.p + 4);
-                CU(cudaMalloc(&ps.twA, (size_t)nq * M * sizeof(ntt2::Tw)));
+                CU(cudaMalloc(&ps.twA, (size_t)nq * M * sizeof(ntt2::TWT)));
                 uint64_t total = (uint64_t)nq * M;
                 ntt2::k_build_tw<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ps.twA, nq, M, ps.p + ps.g, inverse, wmax);
                 LAUNCHED(ctx);
             }
             if (ps.p > 0) {
                 uint32_t nq = 15, M = 1u << ps.p;
-                CU(cudaMalloc(&ps.twB, (size_t)nq * M * sizeof(ntt2::Tw)));
+                CU(cudaMalloc(&ps.twB, (size_t)nq * M * sizeof(ntt2::TWT)));
                 uint64_t total = (uint64_t)nq * M;
                 ntt2::k_build_tw<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ps.twB, nq, M, ps.p + 4, inverse, wmax);
                 LAUNCHED(ctx);
@@ -629,8 +629,8 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     out->rows = N;
     out->cols = coef.cols;
     TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
-    if (log_n >= NTT2_MIN_LOG) {
-        // scaling and 2^added_bits-fold expansion fused into the last inverse pass
+    if (log_n >= NTT2_MIN_LOG && ncosets == 2) {
+        // scaling and 2-fold expansion fused into the last inverse pass
         CosetEpilogue epi;
         epi.pw = pw;
         epi.out = out->d;

@@ -37,6 +37,21 @@ struct Tw {
     uint32_t w, wp;  // w (canonical residue) and floor(w * 2^32 / p)
 };
 
+// Inter-phase twiddle representation (compile-time switch): Shoup pairs cost two registers
+// per twiddle (60 of the 128 registers of a strided pass), single Montgomery words one register and one extra
+// instruction per multiply.
+#ifndef NTT2_MONT_TW
+#define NTT2_MONT_TW 0
+#endif
+#ifndef NTT2_MINBLOCKS
+#define NTT2_MINBLOCKS 2
+#endif
+#if NTT2_MONT_TW
+using TWT = uint32_t;
+#else
+using TWT = Tw;
+#endif
+
 // 16th roots of unity: c_w16[dir][j] = w16^j (dir 0) or w16^-j (dir 1), j < 8
 __constant__ Tw c_w16[2][8];
 
@@ -47,47 +62,53 @@ __device__ __forceinline__ uint32_t shoup_lazy(uint32_t a, Tw t) {  // -> [0, 2p
 __device__ __forceinline__ uint32_t red(uint32_t x) { return kb::umin_(x, x - kb::P); }  // [0,2p) -> [0,p)
 
 // ---- radix-2^K butterflies on K-digit register arrays (constant twiddles) -----------------------
-// forward DIF: natural in -> outputs at bit-reversed positions; all values canonical on exit unless
-// LAZY_LAST (then the last stage leaves values in [0, 2p) for a following Shoup multiply)
+// Every stage is ONE flat loop with a compile-time trip count, so that nvcc unrolls it completely (the nested
+// gb/k loops of the first version were left partially rolled: ptxas then emulated the register-array indexing
+// with ~150 predicated moves per column).
+// forward DIF stage S (butterfly span 2^S); LAZY: leave the results in [0, 2p) for a following Shoup multiply
+template <int K, int S, bool LAZY>
+__device__ __forceinline__ void dif_stage(uint32_t* v) {
+    constexpr int half = 1 << S;
+#pragma unroll
+    for (int i = 0; i < (1 << (K - 1)); i++) {
+        const int lo = ((i >> S) << (S + 1)) | (i & (half - 1)), hi = lo + half;
+        const int tj = (i & (half - 1)) * (8 >> S);  // exponent of w16
+        uint32_t a = v[lo], b = v[hi];
+        uint32_t x = a + b;
+        uint32_t y = a - b + kb::P;  // (0, 2p)
+        if (tj != 0) y = shoup_lazy(y, c_w16[0][tj]);
+        v[lo] = LAZY ? x : red(x);
+        v[hi] = LAZY ? y : red(y);
+    }
+}
+// forward DIF: natural in -> outputs at bit-reversed positions; canonical on exit unless LAZY_LAST
 template <int K, bool LAZY_LAST>
 __device__ __forceinline__ void radix_dif(uint32_t* v) {
+    if constexpr (K >= 4) dif_stage<K, 3, false>(v);
+    if constexpr (K >= 3) dif_stage<K, 2, false>(v);
+    if constexpr (K >= 2) dif_stage<K, 1, false>(v);
+    if constexpr (K >= 1) dif_stage<K, 0, LAZY_LAST>(v);
+}
+template <int K, int S>
+__device__ __forceinline__ void dit_stage(uint32_t* v) {
+    constexpr int half = 1 << S;
 #pragma unroll
-    for (int s = K - 1; s >= 0; s--) {
-        const int half = 1 << s;
-#pragma unroll
-        for (int gb = 0; gb < (1 << K); gb += 2 * half) {
-#pragma unroll
-            for (int k = 0; k < half; k++) {
-                uint32_t a = v[gb + k], b = v[gb + k + half];
-                const bool lazy = LAZY_LAST && s == 0;
-                uint32_t x = a + b;
-                uint32_t y = a - b + kb::P;  // (0, 2p)
-                const int tj = k * (8 >> s);  // exponent of w16
-                if (tj != 0) y = shoup_lazy(y, c_w16[0][tj]);
-                v[gb + k] = lazy ? x : red(x);
-                v[gb + k + half] = lazy ? y : red(y);
-            }
-        }
+    for (int i = 0; i < (1 << (K - 1)); i++) {
+        const int lo = ((i >> S) << (S + 1)) | (i & (half - 1)), hi = lo + half;
+        const int tj = (i & (half - 1)) * (8 >> S);
+        uint32_t a = v[lo], b = v[hi];
+        if (tj != 0) b = red(shoup_lazy(b, c_w16[1][tj]));
+        v[lo] = red(a + b);
+        v[hi] = red(a - b + kb::P);
     }
 }
 // inverse DIT: inputs at bit-reversed positions -> natural out, canonical
 template <int K>
 __device__ __forceinline__ void radix_dit(uint32_t* v) {
-#pragma unroll
-    for (int s = 0; s < K; s++) {
-        const int half = 1 << s;
-#pragma unroll
-        for (int gb = 0; gb < (1 << K); gb += 2 * half) {
-#pragma unroll
-            for (int k = 0; k < half; k++) {
-                uint32_t a = v[gb + k], b = v[gb + k + half];
-                const int tj = k * (8 >> s);
-                if (tj != 0) b = red(shoup_lazy(b, c_w16[1][tj]));
-                v[gb + k] = red(a + b);
-                v[gb + k + half] = red(a - b + kb::P);
-            }
-        }
-    }
+    if constexpr (K >= 1) dit_stage<K, 0>(v);
+    if constexpr (K >= 2) dit_stage<K, 1>(v);
+    if constexpr (K >= 3) dit_stage<K, 2>(v);
+    if constexpr (K >= 4) dit_stage<K, 3>(v);
 }
 
 __device__ __forceinline__ constexpr int brev(int x, int bits) {
@@ -96,10 +117,15 @@ __device__ __forceinline__ constexpr int brev(int x, int bits) {
     return r;
 }
 
+// inter-phase twiddle multiply: Shoup pair (any a < 2^32 -> canonical) or a single Montgomery word (twiddle stored
+// as w * 2^32 mod p; one register instead of two, one instruction more)
+__device__ __forceinline__ uint32_t twmul(uint32_t a, Tw t) { return red(shoup_lazy(a, t)); }
+__device__ __forceinline__ uint32_t twmul(uint32_t a, uint32_t t) { return kb::mul(a, t); }
+
 // One phase over a K-bit digit held as v[j*2^K + digit] for NG = 16 >> K independent groups.
 // tw[j*(2^K-1) + q-1] multiplies output/input q of group j.
-template <bool INV, int K, bool HAS_TW>
-__device__ __forceinline__ void phase(uint32_t* v, const Tw* tw) {
+template <bool INV, int K, bool HAS_TW, class TWF>
+__device__ __forceinline__ void phase(uint32_t* v, TWF tw) {
     constexpr int R = 1 << K, NG = 16 >> K;
 #pragma unroll
     for (int j = 0; j < NG; j++) {
@@ -110,7 +136,7 @@ __device__ __forceinline__ void phase(uint32_t* v, const Tw* tw) {
 #pragma unroll
                 for (int i = 0; i < R; i++) {
                     const int q = brev(i, K);  // position i holds output q
-                    x[i] = q ? red(shoup_lazy(x[i], tw[j * (R - 1) + q - 1])) : red(x[i]);
+                    x[i] = q ? twmul(x[i], tw(j * (R - 1) + q - 1)) : red(x[i]);
                 }
             }
         } else {
@@ -118,7 +144,7 @@ __device__ __forceinline__ void phase(uint32_t* v, const Tw* tw) {
 #pragma unroll
                 for (int i = 1; i < R; i++) {
                     const int q = brev(i, K);
-                    x[i] = red(shoup_lazy(x[i], tw[j * (R - 1) + q - 1]));
+                    x[i] = twmul(x[i], tw(j * (R - 1) + q - 1));
                 }
             }
             radix_dit<K>(x);
@@ -132,8 +158,8 @@ struct PassArgs {
     uint32_t ncols;       // total columns
     uint32_t cols_per_cta;
     uint32_t p;           // low bit of the pass (0 in the contiguous pass)
-    const Tw* twA;        // [(2^G1 - 1)][2^(p+4)]  exponent q*m, transform size 2^(p+g)
-    const Tw* twB;        // [15][2^p]              exponent q*lo, transform size 2^(p+4); null when p == 0
+    const TWT* twA;       // [(2^G1 - 1)][2^(p+4)]  exponent q*m, transform size 2^(p+g)
+    const TWT* twB;       // [15][2^p]              exponent q*lo, transform size 2^(p+4); null when p == 0
     // optional fused epilogue of the LAST inverse pass (coset scaling + blow-up): when pw != null the
     // result is not written back in place but as out[c][h*n + k] = x[k] * pw[h*n + k] for h < ncosets
     // (pw = (shift_h)^k / n in Montgomery form), out columns being ncosets*n words long.
@@ -157,7 +183,7 @@ __device__ __forceinline__ uint32_t tile_idx(uint32_t d, uint32_t l) {
 
 // G1 in 0..4 (g = G1 + 4).  Threads per CTA = 2^g.  CONTIG: p == 0 (lanes = 16 consecutive runs of 2^g words).
 template <bool INV, int G1, bool CONTIG>
-__global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
+__global__ void __launch_bounds__(256, NTT2_MINBLOCKS) k_pass(PassArgs A) {
     constexpr int g = G1 + G2, NT = 1 << g;
     constexpr int RA = 1 << G1, NGA = 16 >> G1;  // phase A: radix, groups per thread
     constexpr int TILE_WORDS = CONTIG ? 16 * (NT + 16) : NT * ROW;
@@ -188,11 +214,15 @@ __global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
     }
     const uint32_t laneB = CONTIG ? t >> G1 : t & 15;
     const uint32_t aB = CONTIG ? t & (RA - 1) : t >> 4;
-    // word offset (inside the tile's address range) of element (d, lane)
-    auto goff = [&](uint32_t d, uint32_t lane) -> uint64_t { return CONTIG ? ((uint64_t)lane << g) + d : ((uint64_t)d << p) + lane; };
+    // word offset (inside the tile's address range, < 2^32) of element (d, lane): 32-bit arithmetic on purpose, the
+    // 64-bit column base is CTA-uniform (64-bit per-element address math was 5 instructions per access)
+    auto goff = [&](uint32_t d, uint32_t lane) -> uint32_t { return CONTIG ? (lane << g) + d : (d << p) + lane; };
 
     // ---- twiddles for this tile position (registers, reused for every column) -------------------
-    Tw twa[15], twb[15];
+    // phase A twiddles (per thread) live in registers; phase B twiddles depend on the lane only and are read from
+    // shared memory (15 broadcast LDS.64 per column instead of 30 more registers, which spilled)
+    TWT twa[15];
+    __shared__ TWT s_twb[15][LANES];
     if (G1 > 0) {
 #pragma unroll
         for (int j = 0; j < NGA; j++) {
@@ -203,9 +233,11 @@ __global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
         }
     }
     if (!CONTIG) {
-#pragma unroll
-        for (int q = 1; q < 16; q++) twb[q - 1] = A.twB[(uint64_t)(q - 1) << p | (lo_base + laneB)];
+        for (uint32_t i = t; i < 15 * LANES; i += NT) s_twb[i / LANES][i % LANES] = A.twB[(uint64_t)(i / LANES) << p | (lo_base + i % LANES)];
+        __syncthreads();
     }
+    auto twA = [&](int i) { return twa[i]; };
+    auto twB = [&](int i) { return s_twb[i][laneB]; };
     const uint32_t c_begin = blockIdx.y * A.cols_per_cta;
     const uint32_t c_end = min(A.ncols, c_begin + A.cols_per_cta);
 
@@ -294,40 +326,48 @@ __global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
         if (c + 1 < c_end) load_first(c + 1);  // software pipeline: next column's tile in flight during the butterflies
         if (!INV) {
             if (G1 > 0) {
-                phase<false, G1, true>(v, twa);
+                phase<false, G1, true>(v, twA);
                 sts_A(s, v);
                 __syncthreads();  // double-buffered tile: one barrier per column
                 lds_B(s, v);
             }
-            if (!CONTIG) phase<false, G2, true>(v, twb);
-            else phase<false, G2, false>(v, twb);
+            if (!CONTIG) phase<false, G2, true>(v, twB);
+            else phase<false, G2, false>(v, twB);
             store_B(colptr(c), v);
         } else {
-            if (!CONTIG) phase<true, G2, true>(v, twb);
-            else phase<true, G2, false>(v, twb);
+            if (!CONTIG) phase<true, G2, true>(v, twB);
+            else phase<true, G2, false>(v, twB);
             if (G1 > 0) {
                 sts_B(s, v);
                 __syncthreads();
                 lds_A(s, v);
-                phase<true, G1, true>(v, twa);
+                phase<true, G1, true>(v, twA);
             }
             // ---- store in the phase-A layout (phase-B layout when G1 == 0) ---------------------------------
             if (A.pw != nullptr) {
+                // fused coset epilogue for blow-up 2 (the host only requests it when ncosets == 2): CTA-uniform 64-bit
+                // bases, 32-bit per-element offsets
                 const uint64_t n = 1ull << A.log_n;
-                uint32_t* ocol = A.out + (uint64_t)c * (n * A.ncosets);
+                const uint32_t* pw0 = A.pw + base;
+                const uint32_t* pw1 = pw0 + n;
+                uint32_t* o0 = A.out + (uint64_t)c * (2 * n) + base;
+                uint32_t* o1 = o0 + n;
                 if (G1 > 0) {
 #pragma unroll
                     for (int j = 0; j < NGA; j++)
 #pragma unroll
                         for (int a = 0; a < RA; a++) {
-                            uint64_t idx = base + goff(((uint32_t)a << G2) | r1A[j], laneA[j]);
-                            for (uint32_t h = 0; h < A.ncosets; h++) ocol[h * n + idx] = kb::mul(v[j * RA + a], __ldg(A.pw + h * n + idx));
+                            uint32_t off = goff(((uint32_t)a << G2) | r1A[j], laneA[j]);
+                            uint32_t x = v[j * RA + a];
+                            o0[off] = kb::mul(x, __ldg(pw0 + off));
+                            o1[off] = kb::mul(x, __ldg(pw1 + off));
                         }
                 } else {
 #pragma unroll
                     for (int b = 0; b < 16; b++) {
-                        uint64_t idx = base + goff((aB << G2) | b, laneB);
-                        for (uint32_t h = 0; h < A.ncosets; h++) ocol[h * n + idx] = kb::mul(v[b], __ldg(A.pw + h * n + idx));
+                        uint32_t off = goff((aB << G2) | b, laneB);
+                        o0[off] = kb::mul(v[b], __ldg(pw0 + off));
+                        o1[off] = kb::mul(v[b], __ldg(pw1 + off));
                     }
                 }
             } else if (G1 > 0) {
@@ -344,17 +384,21 @@ __global__ void __launch_bounds__(256, 2) k_pass(PassArgs A) {
 }
 
 // table entry i of a phase table: exponent e = q * m of a root of order 2^order_log (inverse: -e)
-__global__ void k_build_tw(Tw* out, uint32_t nq, uint32_t M, uint32_t order_log, int inverse, uint32_t w_max /* Montgomery, order 2^24 */) {
+__global__ void k_build_tw(TWT* out, uint32_t nq, uint32_t M, uint32_t order_log, int inverse, uint32_t w_max /* Montgomery, order 2^24 */) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= (uint64_t)nq * M) return;
     uint32_t q = (uint32_t)(i / M) + 1, m = (uint32_t)(i % M);
     uint64_t e = ((uint64_t)q * m) << (kb::TWO_ADICITY - order_log);  // exponent of the order-2^24 root
     if (inverse) e = ((1ull << kb::TWO_ADICITY) - e) & ((1ull << kb::TWO_ADICITY) - 1);
+#if NTT2_MONT_TW
+    out[i] = kb::pow(w_max, e);
+#else
     uint32_t w = kb::from_mont(kb::pow(w_max, e));
     Tw tw;
     tw.w = w;
     tw.wp = (uint32_t)(((uint64_t)w << 32) / kb::P);
     out[i] = tw;
+#endif
 }
 
 }  // namespace ntt2
