@@ -547,8 +547,13 @@ static int32_t get_plan(bfgpu_ctx* ctx, unsigned log_n, bool inverse, const std:
 
 template <bool INVERSE, int G1>
 static void launch_pass(bfgpu_ctx* ctx, const ntt2::PassArgs& a, dim3 grid) {
-    if (a.p == 0) ntt2::k_pass<INVERSE, G1, true><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
-    else ntt2::k_pass<INVERSE, G1, false><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
+    if (INVERSE && a.pw != nullptr) {  // last inverse pass with the fused coset epilogue (always a strided pass: log_n >= 12)
+        ntt2::k_pass<INVERSE, G1, false, INVERSE><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
+    } else if (a.p == 0) {
+        ntt2::k_pass<INVERSE, G1, true><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
+    } else {
+        ntt2::k_pass<INVERSE, G1, false><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
+    }
 }
 
 // Run all stages of a size-2^log_n transform on `ncols` column vectors (stride col_stride words).

@@ -182,8 +182,9 @@ __device__ __forceinline__ uint32_t tile_idx(uint32_t d, uint32_t l) {
 }
 
 // G1 in 0..4 (g = G1 + 4).  Threads per CTA = 2^g.  CONTIG: p == 0 (lanes = 16 consecutive runs of 2^g words).
-template <bool INV, int G1, bool CONTIG>
-__global__ void __launch_bounds__(256, NTT2_MINBLOCKS) k_pass(PassArgs A) {
+// EPI: the fused coset epilogue (separate instantiation: keeps its registers out of the plain passes)
+template <bool INV, int G1, bool CONTIG, bool EPI = false>
+__global__ void __launch_bounds__(256, EPI ? 1 : NTT2_MINBLOCKS) k_pass(PassArgs A) {
     constexpr int g = G1 + G2, NT = 1 << g;
     constexpr int RA = 1 << G1, NGA = 16 >> G1;  // phase A: radix, groups per thread
     constexpr int TILE_WORDS = CONTIG ? 16 * (NT + 16) : NT * ROW;
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(256, NTT2_MINBLOCKS) k_pass(PassArgs A) {
                 phase<true, G1, true>(v, twA);
             }
             // ---- store in the phase-A layout (phase-B layout when G1 == 0) ---------------------------------
-            if (A.pw != nullptr) {
+            if (EPI) {
                 // fused coset epilogue for blow-up 2 (the host only requests it when ncosets == 2): CTA-uniform 64-bit
                 // bases, 32-bit per-element offsets
                 const uint64_t n = 1ull << A.log_n;
