@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cols", type=int, default=256)
     ap.add_argument("--cpu-log-rows", type=int, default=16, help="bounded CPU sample height (log2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dist-commit", action="store_true", help="N>1: skip the one-commitment-over-all-ranks measurements")
     ap.add_argument("--no-prove", action="store_true", help="skip the end-to-end shard-prove timings (BASELINE configs 1-3)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -299,6 +300,53 @@ def main():
                "h2d_bytes_per_step": 4 * R * W, "d2h_bytes_per_step": 32, "ms_per_step": dt / args.steps * 1e3}
         del host
 
+    # ---- N > 1: ONE commitment over all ranks (columns -> LDE -> P2P row exchange -> subtrees -> caps) -------
+    one_commitment = None
+    if dist is not None and not args.no_dist_commit:
+        ctx.set_input_space(bf.MEM_DEVICE)
+        del trace
+        torch.cuda.empty_cache()
+
+        def dist_case(total_cols, exchange):
+            c0, nloc = shard.col_range(total_cols, world, rank)
+            gg = torch.Generator(device="cuda")
+            gg.manual_seed(0xD157 + rank)
+            cols = torch.randint(0, P, (R, nloc), dtype=torch.int32, device="cuda", generator=gg)
+            torch.cuda.synchronize()
+            roots = []
+
+            def step():
+                dc = shard.DistributedCommit(ctx, dist, [R], [total_cols], exchange=exchange)
+                roots.append(dc.commit([(cols.data_ptr(), R, nloc)]).copy())
+                dc.free()
+
+            for _ in range(2):
+                step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ctx.launch_count
+            e0.record(stream)
+            for _ in range(args.steps):
+                step()
+            e1.record(stream)
+            barrier()
+            ms = shard.max_over_ranks(e0.elapsed_time(e1), dist, "cuda") / args.steps
+            assert all((r == roots[0]).all() for r in roots)
+            del cols
+            torch.cuda.empty_cache()
+            return {"workload": workload_name(args.log_rows, total_cols), "exchange": exchange, "ms_per_step": ms,
+                    "value": algorithmic_bytes(R, total_cols) / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                    "launches_per_step_per_rank": (ctx.launch_count - l0) // args.steps, "root": [int(x) for x in roots[0]]}
+
+        one_commitment = {
+            "note": "one Pcs::commit sharded over the ranks: column shards -> LDE -> row shards stored into peer HBM by "
+                    "k_scatter_rows (CUDA IPC over NVLink, overlapped with the next LDE block) -> per-rank subtree -> all-gather of caps; "
+                    "'staged' = same with a local pack + NCCL all_to_all_single instead (comparison baseline)",
+            "strong_p2p": dist_case(W, "p2p"),
+            "weak_p2p": dist_case(W * world, "p2p"),
+            "weak_staged_nccl": dist_case(W * world, "staged"),
+        }
+
     if rank == 0:
         peaks = {}
         try:
@@ -337,6 +385,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if one_commitment:
+            line["one_commitment"] = one_commitment
         if world == 1 and not args.no_prove:
             line["prove"] = prove_timings(ctx, bf, not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:

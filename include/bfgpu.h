@@ -99,6 +99,7 @@ enum {
     BFGPU_PHASE_QUERY = 12,      /* query gathers                                                   */
     BFGPU_PHASE_PERM = 13,       /* LogUp permutation trace                                         */
     BFGPU_PHASE_QUOTIENT = 14,   /* quotient values                                                 */
+    BFGPU_PHASE_EXCHANGE = 15,   /* multi-GPU commit: launches of the column->row exchange (they run on the copy stream) */
     BFGPU_NUM_PHASES = 16
 };
 /* start (on != 0, clears the accumulators) or stop collecting per-phase timings */
@@ -156,6 +157,37 @@ int32_t bfgpu_pcs_lde_dims(const bfgpu_pcs_data* data, int32_t idx, uint64_t* ro
 int32_t bfgpu_pcs_get_evaluations(bfgpu_pcs_data* data, int32_t idx, int bit_reversed_rows, uint32_t* out);
 bfgpu_tree* bfgpu_pcs_tree(bfgpu_pcs_data* data); /* borrowed; freed with the pcs data */
 void bfgpu_pcs_data_free(bfgpu_pcs_data* data);
+
+/* ---- one Pcs::commit over several GPUs (one process / context per GPU) -------------------------------- */
+/* Shards `TwoAdicFriPcs::commit` (prover.rs:227,334,411) as SURVEY.md §8e lays out: rank r LDEs columns
+ * [W*r/G, W*(r+1)/G) of every matrix, the LDE blocks are stored straight into the peers' row-shard matrices
+ * over NVLink (CUDA IPC mappings; no library collective on the data path), rank r hashes LDE rows
+ * [r*h/G, (r+1)*h/G) and builds subtree r of the Merkle tree, and the G subtree caps (32 B each) plus the
+ * top log2(G) levels give the same root as the single-GPU commit.  The caller's plumbing
+ * (torch.distributed in the Python mirror, any byte all-gather + barrier in a Rust shim) moves only the
+ * 64-byte buffer handles and the caps.  Call order on every rank:
+ *   begin -> recv_handle -> [all-gather handles] -> set_peers -> lde -> bfgpu_synchronize -> [barrier]
+ *         -> finish -> [all-gather caps] -> root          (open_batch any time after root)
+ * Staged mode (baseline for comparison): set_staging instead of set_peers, then the caller runs an
+ * all-to-all of block_words()-sized blocks between lde and unpack. */
+typedef struct bfgpu_dist_commit bfgpu_dist_commit;
+int32_t bfgpu_dist_commit_begin(bfgpu_ctx* ctx, uint32_t rank, uint32_t world, const uint64_t* rows, const uint32_t* total_cols,
+                                int32_t n, bfgpu_dist_commit** out);
+/* number of columns of matrix i this rank owns (and the first one's global index) */
+uint32_t bfgpu_dist_commit_local_cols(const bfgpu_dist_commit* dc, int32_t i, uint32_t* col0);
+int32_t bfgpu_dist_commit_recv_handle(bfgpu_dist_commit* dc, uint8_t handle[64]);
+int32_t bfgpu_dist_commit_set_peers(bfgpu_dist_commit* dc, const uint8_t* handles /* world x 64 */);
+uint64_t bfgpu_dist_commit_block_words(const bfgpu_dist_commit* dc, uint32_t src_rank);
+int32_t bfgpu_dist_commit_set_staging(bfgpu_dist_commit* dc, uint32_t* dev_send /* world x block_words(rank) words */);
+/* local[i]: rows[i] x local_cols(i) row-major slice in the context's input space; domain_shifts as bfgpu_pcs_commit */
+int32_t bfgpu_dist_commit_lde(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts);
+int32_t bfgpu_dist_commit_unpack(bfgpu_dist_commit* dc, const uint32_t* dev_recv /* sum_src block_words(src) words */);
+int32_t bfgpu_dist_commit_finish(bfgpu_dist_commit* dc, uint32_t cap[8]);
+int32_t bfgpu_dist_commit_root(bfgpu_dist_commit* dc, const uint32_t* caps /* world x 8 */, uint32_t root[8]);
+/* Mmcs::open_batch for a global leaf index owned by this rank (index / rows_per_rank == rank) */
+int32_t bfgpu_dist_commit_open_batch(bfgpu_dist_commit* dc, uint64_t index, uint32_t* opened_rows, uint32_t* siblings);
+uint64_t bfgpu_dist_commit_rows_per_rank(const bfgpu_dist_commit* dc);
+void bfgpu_dist_commit_free(bfgpu_dist_commit* dc);
 
 /* ---- Challenger = DuplexChallenger<Val, Perm, 16, 8> (kb31_poseidon2.rs:31,126-128) ------------ */
 /* Host-side sponge (the transcript is sequential and tiny); the library advances it exactly as the

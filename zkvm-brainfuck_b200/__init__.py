@@ -72,6 +72,19 @@ ABI = {
     "bfgpu_pcs_get_evaluations": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]),
     "bfgpu_pcs_tree": (C.c_void_p, [C.c_void_p]),
     "bfgpu_pcs_data_free": (None, [C.c_void_p]),
+    "bfgpu_dist_commit_begin": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u32p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "bfgpu_dist_commit_local_cols": (C.c_uint32, [C.c_void_p, C.c_int32, _u32p]),
+    "bfgpu_dist_commit_recv_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_dist_commit_set_peers": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_dist_commit_block_words": (C.c_uint64, [C.c_void_p, C.c_uint32]),
+    "bfgpu_dist_commit_set_staging": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_dist_commit_lde": (C.c_int32, [C.c_void_p, C.POINTER(Mat), _u32p]),
+    "bfgpu_dist_commit_unpack": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_dist_commit_finish": (C.c_int32, [C.c_void_p, _u32p]),
+    "bfgpu_dist_commit_root": (C.c_int32, [C.c_void_p, _u32p, _u32p]),
+    "bfgpu_dist_commit_open_batch": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "bfgpu_dist_commit_rows_per_rank": (C.c_uint64, [C.c_void_p]),
+    "bfgpu_dist_commit_free": (None, [C.c_void_p]),
     "bfgpu_challenger_create": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bfgpu_challenger_clone": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bfgpu_challenger_free": (None, [C.c_void_p]),
@@ -178,7 +191,7 @@ class Context:
         self._pinned = []
 
     PHASES = ["h2d", "ingest", "intt", "scale", "ntt", "leaf_hash", "compress", "other", "open_eval", "open_reduce", "fri",
-              "pow", "query", "perm", "quotient", "reserved"]
+              "pow", "query", "perm", "quotient", "exchange"]
 
     def profile_enable(self, on=True):
         self.check(lib().bfgpu_profile_enable(self._h, 1 if on else 0))

@@ -3,7 +3,7 @@ import os
 import subprocess
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(_DIR, "libbfgpu.so")
+SO = os.environ.get("BFGPU_SO") or os.path.join(_DIR, "libbfgpu.so")  # BFGPU_SO: experiment builds (tools/)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

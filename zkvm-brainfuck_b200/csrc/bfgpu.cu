@@ -23,6 +23,7 @@
 #include "kernels_hash.cuh"
 #include "kernels_ntt.cuh"
 #include "kernels_ntt2.cuh"
+#include <array>
 #include <map>
 #include <tuple>
 #include <unordered_map>
@@ -70,6 +71,8 @@ struct bfgpu_ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live;
     size_t cached_bytes = 0;
+    // peer receive buffers mapped through CUDA IPC (dist_commit.cuh), keyed by the 64-byte handle
+    std::map<std::array<uint8_t, 64>, void*> ipc_open;
 };
 
 struct bfgpu_tree {
@@ -253,6 +256,7 @@ extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
     if (!ctx) return;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
+    for (auto& kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
     trim_cache(ctx);
     for (auto& kv : ctx->live) cudaFree(kv.first);
     for (auto& kv : ctx->pw_cache) cudaFree(kv.second);
@@ -605,7 +609,7 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
 // shift_mont: Montgomery form of the coset shift.
 // coset LDE of a column-major device matrix whose rows are already in bit-reversed order (consumed) ->
 // column-major device matrix with bit-reversed rows.  shift_mont: Montgomery form of the coset shift.
-static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, uint32_t shift_mont, DMat* out) {
+static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, uint32_t shift_mont, DMat* out, bool consume = true) {
     unsigned log_n = ilog2(coef.rows);
     if (log_n + added_bits > kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
     uint64_t n = coef.rows, N = n << added_bits;
@@ -649,7 +653,7 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
         LAUNCHED(ctx);
         CU(cudaGetLastError());
     }
-    dfree(ctx, coef.d);
+    if (consume) dfree(ctx, coef.d);
     TRY(run_ntt<false>(ctx, out->d, n, log_n, coef.cols * ncosets));
     return BFGPU_OK;
 }
@@ -1862,3 +1866,8 @@ extern "C" int32_t bfgpu_machine_chip_info(int32_t i, const char** name, int32_t
     if (local_only) *local_only = air::CHIPS[i].local_only;
     return BFGPU_OK;
 }
+
+// =====================================================================================================
+// one commitment over several GPUs
+// =====================================================================================================
+#include "dist_commit.cuh"

@@ -51,6 +51,15 @@ KB_HD uint32_t mont_reduce(uint64_t t) {
     uint32_t r = (uint32_t)(t >> 32) - u;
     return umin_(r, r + P);
 }
+// Lazy multiply-accumulate for long dot products: acc (< 2^32 p) += a * b with a, b in [0, p), kept below 2^32 p by
+// a conditional subtraction of 2^32 p on the high word (one IMAD.WIDE + one add/min instead of a full Montgomery
+// product and a modular add).  mont_reduce(acc) at the end is the Montgomery-form sum of the products.
+KB_HD void mac(uint64_t& acc, uint32_t a, uint32_t b) {
+    acc += (uint64_t)a * b;  // < 2^32 p + p^2 < 2^64
+    uint32_t hi = (uint32_t)(acc >> 32);
+    hi = umin_(hi, hi - P);
+    acc = ((uint64_t)hi << 32) | (uint32_t)acc;
+}
 // Montgomery product.  Exact for a in [0, 2^32), b in [0, p): result in [0, p).
 KB_HD uint32_t mul(uint32_t a, uint32_t b) { return mont_reduce((uint64_t)a * b); }
 KB_HD uint32_t sqr(uint32_t a) { return mul(a, a); }

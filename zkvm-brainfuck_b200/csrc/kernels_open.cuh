@@ -41,30 +41,44 @@ __global__ void k_bary_weights(uint32_t* __restrict__ w, unsigned log_h, uint32_
 }
 
 // partial[(c * nchunks + chunk) * NP + t] = sum over the chunk's rows of col_c[r] * w_t[r]
-constexpr int BARY_THREADS = 256, BARY_ROWS = 4096, BARY_COLS = 4;
+// Products are accumulated unreduced in 64 bits (kb::mac) and reduced once per thread.
+#ifndef BFGPU_BARY_COLS
+#define BFGPU_BARY_COLS 4
+#endif
+#ifndef BFGPU_BARY_UNROLL
+#define BFGPU_BARY_UNROLL 2
+#endif
+constexpr int BARY_THREADS = 256, BARY_ROWS = 4096, BARY_COLS = BFGPU_BARY_COLS, BARY_UNROLL = BFGPU_BARY_UNROLL;  // BARY_COLS columns share each pair of 16-byte weights
 template <int NP>
 __global__ void __launch_bounds__(BARY_THREADS) k_bary_dot(const uint32_t* __restrict__ mat, uint64_t col_stride, uint32_t ncols, uint32_t h,
                                                            const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
                                                            uint32_t* __restrict__ partial, uint32_t nchunks) {
     const uint32_t chunk = blockIdx.x, c0 = blockIdx.y * BARY_COLS;
-    Ext acc[BARY_COLS][NP];
+    uint64_t acc[BARY_COLS][NP][4];
 #pragma unroll
     for (int c = 0; c < BARY_COLS; c++)
 #pragma unroll
-        for (int t = 0; t < NP; t++) acc[c][t] = kb::ext_zero();
+        for (int t = 0; t < NP; t++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[c][t][k] = 0;
     uint32_t r_end = min(h, (chunk + 1) * BARY_ROWS);
+    const uint32_t* colp[BARY_COLS];
+#pragma unroll
+    for (int c = 0; c < BARY_COLS; c++) colp[c] = mat + (uint64_t)min(c0 + c, ncols - 1) * col_stride;  // tail columns recompute the last one
+#pragma unroll BARY_UNROLL  // several rows of loads in flight: the kernel was latency bound (ncu: long_scoreboard ~10 cycles / issue)
     for (uint32_t r = chunk * BARY_ROWS + threadIdx.x; r < r_end; r += BARY_THREADS) {
         Ext w[NP];
         w[0] = ld_ext(w0 + 4 * (uint64_t)r);
         if (NP > 1) w[NP - 1] = ld_ext(w1 + 4 * (uint64_t)r);
+        uint32_t v[BARY_COLS];
 #pragma unroll
-        for (int c = 0; c < BARY_COLS; c++) {
-            if (c0 + c < ncols) {
-                uint32_t v = mat[(uint64_t)(c0 + c) * col_stride + r];
+        for (int c = 0; c < BARY_COLS; c++) v[c] = colp[c][r];
 #pragma unroll
-                for (int t = 0; t < NP; t++) acc[c][t] = kb::ext_add(acc[c][t], kb::ext_scale(w[t], v));
-            }
-        }
+        for (int c = 0; c < BARY_COLS; c++)
+#pragma unroll
+            for (int t = 0; t < NP; t++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) kb::mac(acc[c][t][k], w[t].c[k], v[c]);
     }
     __shared__ uint32_t red[BARY_THREADS / 32][BARY_COLS * NP * 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -74,7 +88,7 @@ __global__ void __launch_bounds__(BARY_THREADS) k_bary_dot(const uint32_t* __res
         for (int t = 0; t < NP; t++)
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                uint32_t v = acc[c][t].c[k];
+                uint32_t v = kb::mont_reduce(acc[c][t][k]);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v = kb::add(v, __shfl_xor_sync(0xffffffffu, v, o));
                 if (lane == 0) red[warp][(c * NP + t) * 4 + k] = v;
@@ -123,12 +137,18 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
     Ext acc = kb::ext_zero();
     for (uint32_t m = 0; m < nmats; m++) {
         const RoMat& M = mats[m];
-        Ext rr = kb::ext_zero();
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // unreduced sum_k alpha^k M[r][k]
         const uint32_t* col = M.d + r;
+#pragma unroll 4
         for (uint32_t k = 0; k < M.width; k++) {
             uint32_t v = col[(uint64_t)k << log_h];
-            rr = kb::ext_add(rr, kb::ext_scale(ld_ext(apow + 4 * k), v));
+            Ext a = ld_ext(apow + 4 * k);
+            kb::mac(a0, a.c[0], v);
+            kb::mac(a1, a.c[1], v);
+            kb::mac(a2, a.c[2], v);
+            kb::mac(a3, a.c[3], v);
         }
+        Ext rr = Ext{{kb::mont_reduce(a0), kb::mont_reduce(a1), kb::mont_reduce(a2), kb::mont_reduce(a3)}};
         for (uint32_t t = 0; t < M.npoints; t++) {
             Ext y = Ext{{M.yred[t][0], M.yred[t][1], M.yred[t][2], M.yred[t][3]}};
             Ext a = Ext{{M.aoff[t][0], M.aoff[t][1], M.aoff[t][2], M.aoff[t][3]}};

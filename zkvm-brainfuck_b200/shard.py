@@ -45,3 +45,139 @@ def max_over_ranks(value, dist=None, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- one commitment over several GPUs -----------------------------------------------------------------------------
+def col_range(total_cols, world_size, rank):
+    """Columns [c0, c0 + n) of a `total_cols`-wide matrix that `rank` extends (same rule as dist_commit.cuh)."""
+    a, b = total_cols * rank // world_size, total_cols * (rank + 1) // world_size
+    return a, b - a
+
+
+def cap_tree(caps, compress):
+    """Top of the Merkle tree over the ranks' subtree caps: [caps, ..., root] with root = layers[-1][0].
+    `compress(left, right)` maps (n, 8) digest arrays to (n, 8) (TruncatedPermutation, kb31_poseidon2.rs:26)."""
+    layers = [np.asarray(caps, np.uint32).reshape(-1, 8)]
+    while layers[-1].shape[0] > 1:
+        prev = layers[-1]
+        layers.append(np.asarray(compress(prev[0::2], prev[1::2]), np.uint32).reshape(-1, 8))
+    return layers
+
+
+def _all_gather_bytes(payload, dist, group=None):
+    """All-gather equally sized byte strings through torch.distributed (CUDA tensors under NCCL, CPU under gloo)."""
+    import torch
+    dev = "cuda" if "nccl" in str(dist.get_backend(group)) else "cpu"
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, mine, group=group)
+    return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+
+class DistributedCommit:
+    """`Pcs::commit` (prover.rs:227) of matrices whose COLUMNS are spread over the ranks of a process group: every
+    rank extends its columns, the LDE blocks are stored into the peers' row shards over NVLink (exchange="p2p",
+    CUDA IPC, no library collective on the data path) or moved by `all_to_all_single` (exchange="staged", the
+    comparison baseline), every rank hashes its rows into one subtree, and the caps are all-gathered.
+    `root` is identical to the single-GPU commitment of the full matrices."""
+
+    def __init__(self, ctx, dist, rows, total_cols, group=None, exchange="p2p"):
+        from . import lib, BfGpuError, _u32p, _u64p  # noqa: F401
+        import ctypes as C
+        self._lib, self._C = lib(), C
+        self.ctx, self.dist, self.group = ctx, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if exchange not in ("p2p", "staged"):
+            raise ValueError("exchange must be 'p2p' or 'staged'")
+        self.exchange = exchange
+        self.rows = np.ascontiguousarray(rows, np.uint64)
+        self.total_cols = np.ascontiguousarray(total_cols, np.uint32)
+        self.n = len(self.rows)
+        self._h = C.c_void_p()
+        ctx.check(self._lib.bfgpu_dist_commit_begin(ctx._h, self.rank, self.world, self.rows.ctypes.data_as(_u64p),
+                                                    self.total_cols.ctypes.data_as(_u32p), self.n, C.byref(self._h)))
+        self.root = None
+        self._send = self._recv = None
+
+    def local_cols(self, i):
+        return col_range(int(self.total_cols[i]), self.world, self.rank)
+
+    def commit(self, local_mats, domain_shifts=None):
+        """local_mats[i]: this rank's rows[i] x local_cols(i) slice — numpy array (host input space) or a
+        (device_pointer, rows, cols) tuple (device input space).  Returns the 8-word root."""
+        from . import Mat, _u32, _u32p
+        C, L, ctx = self._C, self._lib, self.ctx
+        arr, keep = (Mat * self.n)(), []
+        for i, m in enumerate(local_mats):
+            if isinstance(m, tuple):
+                arr[i] = Mat(m[0], m[1], m[2])
+            else:
+                a = _u32(m)
+                keep.append(a)
+                arr[i] = Mat(a.ctypes.data if a.size else None, a.shape[0], a.shape[1])
+        sh = None
+        if domain_shifts is not None:
+            sh = _u32(domain_shifts)
+        if self.exchange == "p2p":
+            handle = (C.c_uint8 * 64)()
+            ctx.check(L.bfgpu_dist_commit_recv_handle(self._h, handle))
+            handles = b"".join(_all_gather_bytes(bytes(handle), self.dist, self.group))
+            ctx.check(L.bfgpu_dist_commit_set_peers(self._h, handles))
+        else:
+            import torch
+            bw = [int(L.bfgpu_dist_commit_block_words(self._h, r)) for r in range(self.world)]
+            self._send = torch.empty(max(bw[self.rank] * self.world, 1), dtype=torch.int32, device="cuda")
+            self._recv = torch.empty(max(sum(bw), 1), dtype=torch.int32, device="cuda")
+            ctx.check(L.bfgpu_dist_commit_set_staging(self._h, C.c_void_p(self._send.data_ptr())))
+        ctx.check(L.bfgpu_dist_commit_lde(self._h, arr, sh.ctypes.data_as(_u32p) if sh is not None else None))
+        ctx.synchronize()  # this rank's stores into the peers (or the staging buffer) have landed
+        if self.exchange == "p2p":
+            self.dist.barrier(group=self.group)  # ... and so have everybody else's into this rank
+        else:
+            import torch
+            send, recv = self._send[:bw[self.rank] * self.world], self._recv[:sum(bw)]
+            on_gpu = "nccl" in str(self.dist.get_backend(self.group))
+            if not on_gpu:  # gloo has no CUDA all-to-all: bounce through the host (tests on a single GPU only)
+                send, recv_dev, recv = send.cpu(), recv, torch.empty(sum(bw), dtype=torch.int32)
+            self.dist.all_to_all_single(recv, send, output_split_sizes=bw, input_split_sizes=[bw[self.rank]] * self.world, group=self.group)
+            if not on_gpu:
+                recv_dev.copy_(recv)
+            torch.cuda.synchronize()
+            ctx.check(L.bfgpu_dist_commit_unpack(self._h, C.c_void_p(self._recv.data_ptr())))
+        cap = np.zeros(8, np.uint32)
+        ctx.check(L.bfgpu_dist_commit_finish(self._h, cap.ctypes.data_as(_u32p)))
+        caps = np.frombuffer(b"".join(_all_gather_bytes(cap.tobytes(), self.dist, self.group)), np.uint32).copy()
+        root = np.zeros(8, np.uint32)
+        ctx.check(L.bfgpu_dist_commit_root(self._h, caps.ctypes.data_as(_u32p), root.ctypes.data_as(_u32p)))
+        self.caps, self.root = caps.reshape(-1, 8), root
+        self._send = self._recv = None
+        return root
+
+    @property
+    def rows_per_rank(self):
+        return int(self._lib.bfgpu_dist_commit_rows_per_rank(self._h))
+
+    def owner(self, index):
+        return int(index) // self.rows_per_rank
+
+    def open_batch(self, index):
+        """Mmcs::open_batch(index) on the rank that owns the leaf: ([row of every matrix], siblings (log2 h, 8))."""
+        nl = (int(self.rows.max()) << 1).bit_length() - 1  # log_blowup = 1 (kb31_poseidon2.rs:57)
+        total = int(self.total_cols.sum())
+        rows = np.zeros(total, np.uint32)
+        sib = np.zeros((nl, 8), np.uint32)
+        self.ctx.check(self._lib.bfgpu_dist_commit_open_batch(self._h, int(index), rows.ctypes.data_as(self._C.c_void_p),
+                                                              sib.ctypes.data_as(self._C.c_void_p)))
+        out, o = [], 0
+        for c in self.total_cols:
+            out.append(rows[o:o + int(c)].copy())
+            o += int(c)
+        return out, sib
+
+    def free(self):
+        if getattr(self, "_h", None):
+            self._lib.bfgpu_dist_commit_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.free()
