@@ -59,6 +59,8 @@ int main() {
     p2::Consts h; memset(&h, 0, sizeof h);
     for (int r = 0; r < 4; r++) for (int i = 0; i < 16; i++) { h.ext[r][i] = kb::to_mont(BFGPU_RC_16_30[r][i]); h.ext[4 + r][i] = kb::to_mont(BFGPU_RC_16_30[17 + r][i]); }
     for (int r = 0; r < 13; r++) h.internal[r] = kb::to_mont(BFGPU_RC_16_30[4 + r][0]);
+    for (int r = 0; r < 8; r++) for (int i = 0; i < 16; i++) h.ext_s[r][i] = h.ext[r][i] - kb::P;
+    for (int r = 0; r < 13; r++) h.internal_s[r] = h.internal[r] - kb::P;
     auto frac = [](int sign, unsigned k) { uint32_t v = kb::ONE; for (unsigned i = 0; i < k; i++) v = kb::halve(v); return sign < 0 ? kb::neg(v) : v; };
     auto small = [](int v) { return v >= 0 ? kb::to_mont((uint32_t)v) : kb::neg(kb::to_mont((uint32_t)(-v))); };
     uint32_t dg[16] = {small(-2), small(1), small(2), frac(1, 1), small(3), small(4), frac(-1, 1), small(-3), small(-4), frac(1, 8), frac(1, 3), frac(1, 24), frac(-1, 8), frac(-1, 3), frac(-1, 4), frac(-1, 24)};

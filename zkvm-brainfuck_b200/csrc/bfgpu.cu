@@ -71,6 +71,9 @@ struct bfgpu_ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live;
     size_t cached_bytes = 0;
+    // pipelined host commit (commit_host_pipelined): columns per block, multiple of 8; 0 disables.
+    // $BFGPU_PIPE_COLS overrides (experiments)
+    uint32_t pipe_cols = 64;  // 256-byte row segments per strided copy: 32 was 3 % slower end to end, 128 19 % (fewer stages)
     // peer receive buffers mapped through CUDA IPC (dist_commit.cuh), keyed by the 64-byte handle
     std::map<std::array<uint8_t, 64>, void*> ipc_open;
 };
@@ -202,6 +205,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("BFGPU_PIPE_COLS")) ctx->pipe_cols = (uint32_t)atoi(e) / 8 * 8;
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
 
     // Poseidon2 constant bank (kb31_poseidon2.rs:35-50): internal constants = column 0 of table rows
@@ -214,6 +218,9 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
             h.ext[4 + r][i] = kb::to_mont(BFGPU_RC_16_30[17 + r][i]);
         }
     for (int r = 0; r < 13; r++) h.internal[r] = kb::to_mont(BFGPU_RC_16_30[4 + r][0]);
+    for (int r = 0; r < 8; r++)
+        for (int i = 0; i < 16; i++) h.ext_s[r][i] = h.ext[r][i] - kb::P;
+    for (int r = 0; r < 13; r++) h.internal_s[r] = h.internal[r] - kb::P;
     {  // V = [-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 1/2^8, 1/8, 1/2^24, -1/2^8, -1/8, -1/16, -1/2^24]
         auto frac = [](int sign, unsigned k) {
             uint32_t v = kb::ONE;
@@ -431,6 +438,16 @@ static void prestage_clear(bfgpu_ctx* ctx) {
     ctx->prestaged.clear();
 }
 
+// row-major device words in the caller's representation -> column-major Montgomery words at dst
+static int32_t ingest_device(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows, uint32_t cols, bool bitrev, uint32_t* dst) {
+    Phase ph(ctx, BFGPU_PHASE_INGEST);
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
+    nttk::k_ingest<<<grid, block, 0, ctx->stream>>>(src, dst, rows, cols, ilog2(rows), bitrev ? 1 : 0, ctx->repr == BFGPU_REPR_CANONICAL);
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    return BFGPU_OK;
+}
+
 static int32_t ingest(bfgpu_ctx* ctx, const bfgpu_mat& m, bool bitrev, DMat* out) {
     out->rows = m.rows;
     out->cols = (uint32_t)m.cols;
@@ -453,14 +470,9 @@ static int32_t ingest(bfgpu_ctx* ctx, const bfgpu_mat& m, bool bitrev, DMat* out
         }
         src = staged;
     }
-    Phase ph(ctx, BFGPU_PHASE_INGEST);
-    dim3 grid((unsigned)((m.rows + 31) / 32), (unsigned)((m.cols + 31) / 32)), block(32, 8);
-    nttk::k_ingest<<<grid, block, 0, ctx->stream>>>(src, out->d, m.rows, (uint32_t)m.cols, ilog2(m.rows), bitrev ? 1 : 0,
-                                                     ctx->repr == BFGPU_REPR_CANONICAL);
-    LAUNCHED(ctx);
-    CU(cudaGetLastError());
+    int32_t rc = ingest_device(ctx, src, m.rows, (uint32_t)m.cols, bitrev, out->d);
     dfree(ctx, staged);
-    return BFGPU_OK;
+    return rc;
 }
 
 // column-major Montgomery device matrix -> caller's row-major host buffer
@@ -609,7 +621,8 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
 // shift_mont: Montgomery form of the coset shift.
 // coset LDE of a column-major device matrix whose rows are already in bit-reversed order (consumed) ->
 // column-major device matrix with bit-reversed rows.  shift_mont: Montgomery form of the coset shift.
-static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, uint32_t shift_mont, DMat* out, bool consume = true) {
+static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, uint32_t shift_mont, DMat* out, bool consume = true,
+                               uint32_t* out_buf = nullptr) {
     unsigned log_n = ilog2(coef.rows);
     if (log_n + added_bits > kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
     uint64_t n = coef.rows, N = n << added_bits;
@@ -637,7 +650,8 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     }
     out->rows = N;
     out->cols = coef.cols;
-    TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
+    if (out_buf) out->d = out_buf;  // caller-provided destination (a column block of a larger matrix)
+    else TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
     if (log_n >= NTT2_MIN_LOG && ncosets == 2) {
         // scaling and 2-fold expansion fused into the last inverse pass
         CosetEpilogue epi;
@@ -811,7 +825,8 @@ static void tree_release(bfgpu_tree* t) {
 }
 
 // Build the tree over device matrices (input order preserved in t->mats).
-static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfgpu_tree** out) {
+// first_layer != null: the leaf digests of the tallest group were already produced (pipelined commit) and are adopted.
+static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfgpu_tree** out, uint32_t* first_layer = nullptr) {
     bfgpu_tree* t = new bfgpu_tree();
     t->ctx = ctx;
     t->mats = std::move(mats);
@@ -829,7 +844,11 @@ static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfg
         while (pos < n && t->mats[order[pos]].rows == h) g.push_back(&t->mats[order[pos++]]);
         return g;
     };
-    {
+    if (first_layer) {
+        take_group(max_h);
+        t->layers.push_back(first_layer);
+        t->layer_len.push_back(max_h);
+    } else {
         Phase ph(ctx, BFGPU_PHASE_LEAF);
         auto g = take_group(max_h);
         const uint32_t** colptr = nullptr;
@@ -970,6 +989,95 @@ extern "C" int32_t bfgpu_tree_get_layer(bfgpu_tree* t, int32_t l, uint32_t* dige
 extern "C" void bfgpu_tree_free(bfgpu_tree* t) { tree_release(t); }
 
 // ---- TwoAdicFriPcs::commit ------------------------------------------------------------------------------
+// Commit of ONE tall host matrix as a three-stage pipeline over blocks of `pipe_cols` columns:
+//   copy stream   : strided host->device copy of block b+1 (cudaMemcpy2DAsync out of the row-major host matrix)
+//   compute stream: ingest + coset LDE of block b into its slice of the column-major LDE, then the leaf sponge
+//                   absorbs the block's columns (k_leaf_absorb; 16-word states parked in HBM between blocks).
+// PCIe (~55 GB/s) and the GPU work (~LDE + hash) take about the same time at 2^22 x 256, so the commit from host
+// memory costs about max(copy, compute) instead of their sum.  Same LDE, same digests as the one-shot path.
+static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bits, uint32_t shift_mont, DMat* lde, uint32_t** first_layer) {
+    const uint64_t R = m.rows, N = R << added_bits;
+    const uint32_t W = (uint32_t)m.cols, CB = ctx->pipe_cols;
+    // block boundaries (multiples of 8 columns).  The copy is the longer stage, so the commit ends one block of compute
+    // after the last byte arrives: the final block is split in two to shorten that tail (narrower strided copies are
+    // slower per byte, so only the tail is split).
+    std::vector<uint32_t> start;
+    for (uint32_t c = 0; c < W; c += CB) start.push_back(c);
+    {
+        uint32_t last = start.back(), len = W - last, half = (len / 2 + 7) / 8 * 8;
+        if (len >= 32 && half < len) start.push_back(last + half);
+    }
+    start.push_back(W);
+    const uint32_t nb = (uint32_t)start.size() - 1;
+    if (ilog2(R) + added_bits > kb::TWO_ADICITY)
+        return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity (2^%d)", ilog2(R) + added_bits, kb::TWO_ADICITY);
+    lde->rows = N;
+    lde->cols = W;
+    lde->rs = 1;
+    uint32_t *staged[2] = {nullptr, nullptr}, *state = nullptr, *layer = nullptr;
+    TRY(dalloc(ctx, (void**)&lde->d, N * W * 4));
+    TRY(dalloc(ctx, (void**)&staged[0], R * CB * 4));
+    TRY(dalloc(ctx, (void**)&staged[1], R * CB * 4));
+    TRY(dalloc(ctx, (void**)&state, N * 16 * 4));
+    TRY(dalloc(ctx, (void**)&layer, N * 32));
+    cudaEvent_t ready[2], consumed[2], fence;
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&consumed[k], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
+    CU(cudaEventRecord(fence, ctx->stream));  // the staging blocks come from the single-stream block cache
+    CU(cudaStreamWaitEvent(ctx->copy_stream, fence, 0));
+    cudaEventDestroy(fence);
+    int32_t rc = BFGPU_OK;
+    auto copy_block = [&](uint32_t b) -> int32_t {
+        const int slot = b & 1;
+        const uint32_t cb = start[b + 1] - start[b];
+        if (b >= 2) CU(cudaStreamWaitEvent(ctx->copy_stream, consumed[slot], 0));
+        CU(cudaMemcpy2DAsync(staged[slot], (size_t)cb * 4, m.data + start[b], (size_t)W * 4, (size_t)cb * 4, R, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(ready[slot], ctx->copy_stream));
+        return BFGPU_OK;
+    };
+    rc = copy_block(0);
+    for (uint32_t b = 0; b < nb && rc == BFGPU_OK; b++) {
+        const int slot = b & 1;
+        const uint32_t cb = start[b + 1] - start[b];
+        DMat coef, blk;
+        coef.rows = R;
+        coef.cols = cb;
+        if ((rc = dalloc(ctx, (void**)&coef.d, R * cb * 4)) != BFGPU_OK) break;
+        CU(cudaStreamWaitEvent(ctx->stream, ready[slot], 0));
+        if ((rc = ingest_device(ctx, staged[slot], R, cb, /*bitrev=*/true, coef.d)) != BFGPU_OK) break;
+        CU(cudaEventRecord(consumed[slot], ctx->stream));
+        // enqueue the copy after next only now: its wait on consumed[slot] must see this record
+        if (b + 1 < nb && b == 0) rc = copy_block(1);
+        if (rc == BFGPU_OK && b + 2 < nb) rc = copy_block(b + 2);
+        if (rc != BFGPU_OK) break;
+        if ((rc = lde_from_bitrev(ctx, coef, added_bits, shift_mont, &blk, /*consume=*/true, lde->d + (uint64_t)start[b] * N)) != BFGPU_OK) break;
+        Phase ph(ctx, BFGPU_PHASE_LEAF);
+        hashk::k_leaf_absorb<<<(unsigned)((N + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(
+            blk.d, N, cb, N, state, b == 0, b + 1 == nb, layer);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+    }
+    for (int k = 0; k < 2; k++) {
+        cudaEventDestroy(ready[k]);
+        cudaEventDestroy(consumed[k]);
+    }
+    if (rc != BFGPU_OK) cudaStreamSynchronize(ctx->copy_stream);
+    dfree(ctx, staged[0]);
+    dfree(ctx, staged[1]);
+    dfree(ctx, state);
+    if (rc != BFGPU_OK) {
+        dfree(ctx, layer);
+        dfree(ctx, lde->d);
+        lde->d = nullptr;
+        return rc;
+    }
+    *first_layer = layer;
+    return BFGPU_OK;
+}
+
 extern "C" int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, const uint32_t* domain_shifts, int32_t n, uint32_t root[8],
                                     bfgpu_pcs_data** out) {
     if (!ctx || !evals || n <= 0 || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
@@ -980,6 +1088,9 @@ extern "C" int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, cons
     pd->ldes.resize(n);
     int32_t rc = prestage_all(ctx, evals, n);
     uint32_t gen = kb::to_mont(kb::GEN);
+    uint32_t* first_layer = nullptr;
+    const bool pipelined = ctx->input_space == BFGPU_MEM_HOST && n == 1 && ctx->pipe_cols >= 8 && evals[0].cols >= 2 * (uint64_t)ctx->pipe_cols &&
+                           evals[0].rows * evals[0].cols >= (1ull << 20);
     for (int i = 0; i < n && rc == BFGPU_OK; i++) {
         // shift = GENERATOR / domain.shift  (TwoAdicFriPcs::commit)
         uint32_t shift = gen;
@@ -988,10 +1099,11 @@ extern "C" int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, cons
             if (ds == 0) rc = fail(ctx, BFGPU_ERR_INVALID, "zero domain shift");
             else shift = kb::mul(gen, kb::inv(ds));
         }
-        if (rc == BFGPU_OK) rc = lde_device(ctx, evals[i], ctx->log_blowup, shift, &pd->ldes[i]);
+        if (rc == BFGPU_OK && pipelined) rc = commit_host_pipelined(ctx, evals[i], ctx->log_blowup, shift, &pd->ldes[i], &first_layer);
+        else if (rc == BFGPU_OK) rc = lde_device(ctx, evals[i], ctx->log_blowup, shift, &pd->ldes[i]);
     }
     prestage_clear(ctx);
-    if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree);
+    if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree, first_layer);
     if (rc == BFGPU_OK) rc = read_digest(ctx, pd->tree->layers.back(), root);
     if (rc != BFGPU_OK) {
         bfgpu_pcs_data_free(pd);

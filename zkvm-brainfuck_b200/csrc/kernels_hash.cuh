@@ -56,6 +56,37 @@ __global__ void __launch_bounds__(HASH_THREADS) k_leaf_hash(const uint32_t* cons
     store_digest(digests + 8 * r, s);
 }
 
+// Incremental form of k_leaf_hash for the pipelined commit: absorbs `ncols` more columns (a multiple of 8 unless
+// `last`) of a column-major block into the per-row sponge states.  state: 16 word-planes of `rows` words (plane k
+// holds word k of every row, so thread r's accesses are coalesced); first: start from the zero state; last: write
+// the digest instead of the state.
+__global__ void __launch_bounds__(HASH_THREADS) k_leaf_absorb(const uint32_t* __restrict__ cols, uint64_t col_stride, uint32_t ncols, uint64_t rows,
+                                                              uint32_t* __restrict__ state, int first, int last, uint32_t* __restrict__ digests) {
+    uint64_t r = blockIdx.x * (uint64_t)HASH_THREADS + threadIdx.x;
+    if (r >= rows) return;
+    uint32_t s[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) s[k] = first ? 0u : state[(uint64_t)k * rows + r];
+    const uint32_t* p = cols + r;
+#pragma unroll 1
+    for (uint32_t c0 = 0; c0 < ncols; c0 += 8, p += 8 * col_stride) {
+        if (c0 + 8 <= ncols) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = __ldg(p + k * col_stride);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (c0 + k < ncols) s[k] = __ldg(p + k * col_stride);
+        }
+        p2::permute(s);
+    }
+    if (last) store_digest(digests + 8 * r, s);
+    else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) state[(uint64_t)k * rows + r] = s[k];
+    }
+}
+
 // next layer: out[i] = compress(prev[2i], prev[2i+1]); if ncols > 0 additionally
 // out[i] = compress(out[i], sponge(row i of the injected columns))
 __global__ void __launch_bounds__(HASH_THREADS) k_compress_layer(const uint32_t* __restrict__ prev, uint32_t* __restrict__ out, uint64_t len,

@@ -18,6 +18,8 @@ struct Consts {
     uint32_t diag[16];      // internal diagonal V (Montgomery form), kept for reference/tests
     uint32_t diag_w[16];    // V as plain residues and
     uint32_t diag_wp[16];   // their Shoup quotients floor(V * 2^32 / p): x~ * V = (x V)~ without a Montgomery reduction
+    uint32_t ext_s[8][16];  // ext - p and
+    uint32_t internal_s[16];  // internal - p as wrapped 32-bit words: state + constant lands in [-p, p) with one plain add
 };
 
 #if defined(__CUDACC__)
@@ -41,6 +43,32 @@ KB_D uint32_t sbox(uint32_t x) {
     int32_t u2 = __mulhi(m2, (int32_t)kb::P);
     uint32_t r = (uint32_t)((int32_t)(t2 >> 32) - u2);
     return kb::umin_(r, r + kb::P);
+}
+// Same for a SIGNED input in [-p, p) (a state word plus a round constant stored as c - p): saves the
+// conditional subtraction of the modular add in front of every S-box.
+#ifndef P2_SIGNED_RC
+#define P2_SIGNED_RC 1
+#endif
+KB_D uint32_t sbox_signed(uint32_t xs) {
+    int32_t x = (int32_t)xs;
+    int64_t t = (int64_t)x * x;  // in [0, p^2]
+    uint32_t m = (uint32_t)t * kb::PINV;
+    uint32_t u = __umulhi(m, kb::P);
+    int32_t x2 = (int32_t)((uint32_t)(t >> 32) - u);
+    int64_t t2 = (int64_t)x2 * x;
+    int32_t m2 = (int32_t)((uint32_t)t2 * kb::PINV);
+    int32_t u2 = __mulhi(m2, (int32_t)kb::P);
+    uint32_t r = (uint32_t)((int32_t)(t2 >> 32) - u2);
+    return kb::umin_(r, r + kb::P);
+}
+KB_D uint32_t sbox_rc(uint32_t x, uint32_t rc, uint32_t rc_minus_p) {
+#if P2_SIGNED_RC
+    (void)rc;
+    return sbox_signed(x + rc_minus_p);
+#else
+    (void)rc_minus_p;
+    return sbox(add(x, rc));
+#endif
 }
 // x * V[i] via Shoup's precomputed quotient (IMAD.HI + 2 IMAD + one min)
 KB_D uint32_t mul_diag(uint32_t x, int i) {
@@ -106,16 +134,17 @@ KB_D void permute(uint32_t (&s)[16]) {
 #pragma unroll 1
         for (int r = 0; r < 4; r++) {
             const uint32_t* rc = c_p2.ext[half * 4 + r];
+            const uint32_t* rcs = c_p2.ext_s[half * 4 + r];
             if (BARRIER) __syncthreads();
 #pragma unroll
-            for (int i = 0; i < 16; i++) s[i] = sbox(add(s[i], rc[i]));
+            for (int i = 0; i < 16; i++) s[i] = sbox_rc(s[i], rc[i], rcs[i]);
             external_linear(s);
         }
         if (half == 0) {
 #pragma unroll 1
             for (int r = 0; r < 13; r++) {
                 if (BARRIER) __syncthreads();
-                s[0] = sbox(add(s[0], c_p2.internal[r]));
+                s[0] = sbox_rc(s[0], c_p2.internal[r], c_p2.internal_s[r]);
                 internal_linear(s);
             }
         }
