@@ -81,13 +81,16 @@ def _affine_expr(em, aff, tag):
 
 def _emit_rlc(em, lk, tag):
     """rlc = alpha + beta^0 * kind + sum_k beta^(k+1) * value_k   (ext)."""
+    # the beta-power products are accumulated unreduced (kb::ext_mac), one Montgomery reduction per coefficient
     em.emit(f"kb::Ext rlc_{tag} = ch.alpha;")
     em.emit(f"rlc_{tag}.c[0] = kb::add(rlc_{tag}.c[0], 0x{mont(lk.kind):08x}u);")
+    em.emit(f"kb::ExtAcc rl_{tag} = kb::ext_acc_from(rlc_{tag});")
     for k, v in enumerate(lk.values):
         val, is_const = _affine_expr(em, v, f"{tag}_{k}")
         if is_const and val == "0x00000000u":
             continue
-        em.emit(f"rlc_{tag} = kb::ext_add(rlc_{tag}, kb::ext_scale(ch.beta_pow[{k + 1}], {val}));")
+        em.emit(f"kb::ext_mac(rl_{tag}, ch.beta_pow[{k + 1}], {val});")
+    em.emit(f"rlc_{tag} = kb::ext_acc_reduce(rl_{tag});")
     m, _ = _affine_expr(em, lk.multiplicity, f"{tag}_m")
     return f"rlc_{tag}", m
 
@@ -106,8 +109,10 @@ def gen_chip(chip, index):
     for n in topo_order(list(chip.constraints)):
         if n.op == "var" and n.args[1] == 0:
             em.loaded.add(f"{n.args[0][0]}0_{n.args[2]}")
+    em.emit("kb::ExtAcc lacc = kb::ext_acc_zero();  // base constraints: alpha-power products accumulated unreduced")
     for k, c in enumerate(chip.constraints):
-        em.emit(f"acc = kb::ext_add(acc, kb::ext_scale(apow[{total - 1 - k}], {names[c._id]}));")
+        em.emit(f"kb::ext_mac(lacc, apow[{total - 1 - k}], {names[c._id]});")
+    em.emit("acc = kb::ext_add(acc, kb::ext_acc_reduce(lacc));")
     # permutation constraints: one per batch, then first / transition / last
     lookups = chip.lookups
     for j in range(chip.perm_width - 1):
@@ -159,10 +164,18 @@ def gen_chip(chip, index):
             r, m = _emit_rlc(em, lk, f"{j}_{i}")
             terms.append((r, m, is_send))
         em.emit("{")
-        em.emit("    kb::Ext s = kb::ext_zero();")
-        for r, m, is_send in terms:
-            em.emit(f"    s = kb::ext_{'add' if is_send else 'sub'}(s, kb::ext_scale(kb::ext_inv({r}), {m}));")
-        em.emit(f"    out[{j}] = s;")
+        if len(terms) == 2:
+            # +-m0/r0 +- m1/r1 = (+-m0 r1 +- m1 r0) / (r0 r1): one extension inversion per batch instead of two
+            (r0, m0, s0), (r1, m1, s1) = terms
+            em.emit("    kb::ExtAcc num = kb::ext_acc_zero();")
+            em.emit(f"    kb::ext_mac(num, {r1}, {m0 if s0 else f'kb::neg({m0})'});")
+            em.emit(f"    kb::ext_mac(num, {r0}, {m1 if s1 else f'kb::neg({m1})'});")
+            em.emit(f"    out[{j}] = kb::ext_mul(kb::ext_acc_reduce(num), kb::ext_inv(kb::ext_mul({r0}, {r1})));")
+        else:
+            em.emit("    kb::Ext s = kb::ext_zero();")
+            for r, m, is_send in terms:
+                em.emit(f"    s = kb::ext_{'add' if is_send else 'sub'}(s, kb::ext_scale(kb::ext_inv({r}), {m}));")
+            em.emit(f"    out[{j}] = s;")
         em.emit("}")
     out.append(f"template <class L>\n__device__ __forceinline__ void air_perm_row_{name}(const L& ld, const Challenges& ch, kb::Ext* out) {{")
     out += em.lines

@@ -106,6 +106,20 @@ KB_HD Ext ext_add(Ext a, Ext b) { return Ext{{add(a.c[0], b.c[0]), add(a.c[1], b
 KB_HD Ext ext_sub(Ext a, Ext b) { return Ext{{sub(a.c[0], b.c[0]), sub(a.c[1], b.c[1]), sub(a.c[2], b.c[2]), sub(a.c[3], b.c[3])}}; }
 KB_HD Ext ext_neg(Ext a) { return Ext{{neg(a.c[0]), neg(a.c[1]), neg(a.c[2]), neg(a.c[3])}}; }
 KB_HD Ext ext_scale(Ext a, uint32_t s) { return Ext{{mul(a.c[0], s), mul(a.c[1], s), mul(a.c[2], s), mul(a.c[3], s)}}; }
+// unreduced accumulator of ext * base products (see mac): sum_k e_k * s_k with one reduction per coefficient at the end
+struct ExtAcc {
+    uint64_t c[4];
+};
+KB_HD ExtAcc ext_acc_zero() { return ExtAcc{{0, 0, 0, 0}}; }
+// accumulator holding the reduced element e (mont_reduce(e * 2^32) = e)
+KB_HD ExtAcc ext_acc_from(Ext e) { return ExtAcc{{(uint64_t)e.c[0] << 32, (uint64_t)e.c[1] << 32, (uint64_t)e.c[2] << 32, (uint64_t)e.c[3] << 32}}; }
+KB_HD void ext_mac(ExtAcc& a, Ext e, uint32_t s) {
+    mac(a.c[0], e.c[0], s);
+    mac(a.c[1], e.c[1], s);
+    mac(a.c[2], e.c[2], s);
+    mac(a.c[3], e.c[3], s);
+}
+KB_HD Ext ext_acc_reduce(ExtAcc a) { return Ext{{mont_reduce(a.c[0]), mont_reduce(a.c[1]), mont_reduce(a.c[2]), mont_reduce(a.c[3])}}; }
 KB_HD uint32_t mul3(uint32_t a) { return add(dbl(a), a); }
 KB_HD Ext ext_mul(Ext a, Ext b) {
     // schoolbook with X^4 = 3; sums of Montgomery products stay in the field via add()
