@@ -104,9 +104,11 @@ def prove_timings(ctx, bf, with_cpu):
     prover = bf.CudaProver(ctx)
     out = {}
     for name, (code, stdin) in progs.items():
+        t_host = time.perf_counter()
         prog = ex.Program(code)
         rec = ex.execute(prog, stdin)
         traces, preps = tg.generate_traces(rec), tg.preprocessed_traces(prog)
+        t_host = time.perf_counter() - t_host
         traces = {k: ctx.pinned_copy(v) for k, v in traces.items()}  # trace generators write into page-locked memory
         pk = prover.setup(preps)
         times = []
@@ -120,6 +122,26 @@ def prove_timings(ctx, bf, with_cpu):
         entry = {"cycles": rec.cycles, "cpu_rows": int(traces["Cpu"].shape[0]), "committed_main_cells": int(sum(v.size for v in traces.values())),
                  "prove_ms": best, "trace_rows_per_s": float(traces["Cpu"].shape[0]) / (best * 1e-3), "khz": rec.cycles / best,
                  "main_root": [int(x) for x in proof["commitment"]["main"]]}
+        # ProverClient::prove end to end on this backend: native executor -> 16 B/cycle records -> device-side trace
+        # generation -> commit -> open (setup excluded, as in the reference where the pk is an input of prove)
+        ptimes, etimes = [], []
+        for _ in range(4):
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            nrec = prover.execute(code, stdin)
+            t1 = time.perf_counter()
+            ch = bf.Challenger(ctx)
+            bf.lib().bfgpu_pk_observe_into(pk._h, ch._h)
+            shard = prover.commit_record(nrec)
+            buf2 = prover.open_raw(pk, shard, ch.clone())
+            t2 = time.perf_counter()
+            shard.free()
+            nrec.free()
+            etimes.append((t1 - t0) * 1e3)
+            ptimes.append((t2 - t0) * 1e3)
+        entry.update({"program_to_proof_ms": min(ptimes[1:]), "native_executor_ms": min(etimes[1:]), "python_executor_tracegen_s": round(t_host, 2),
+                      "program_proof_equals_trace_proof": bool(buf2.shape == buf.shape and (buf2 == buf).all()),
+                      "program_to_proof_khz": rec.cycles / min(ptimes[1:])})
         if with_cpu and name.startswith("hello"):
             # CPU oracle of the same proof (numpy + C, single process): parity check + a rough CPU figure
             from oracle import prover as PR, stark as S

@@ -100,7 +100,8 @@ enum {
     BFGPU_PHASE_PERM = 13,       /* LogUp permutation trace                                         */
     BFGPU_PHASE_QUOTIENT = 14,   /* quotient values                                                 */
     BFGPU_PHASE_EXCHANGE = 15,   /* multi-GPU commit: launches of the column->row exchange (they run on the copy stream) */
-    BFGPU_NUM_PHASES = 16
+    BFGPU_PHASE_TRACEGEN = 16,   /* device-side trace generation from the execution record                          */
+    BFGPU_NUM_PHASES = 20
 };
 /* start (on != 0, clears the accumulators) or stop collecting per-phase timings */
 int32_t bfgpu_profile_enable(bfgpu_ctx* ctx, int on);
@@ -263,6 +264,34 @@ int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const bfgpu_shard
 uint64_t bfgpu_shard_proof_size(const bfgpu_shard_proof* p);
 int32_t bfgpu_shard_proof_read(const bfgpu_shard_proof* p, uint32_t* out);
 void bfgpu_shard_proof_free(bfgpu_shard_proof* p);
+
+/* ---- executor + device-side trace generation -------------------------------------- */
+/* `Program::from` + `Executor::run` (crates/core/executor/src/program.rs:22-44, executor.rs:71-79,106-325) as one
+ * native pass that emits a 16-byte record per cycle; the eight `MachineAir::generate_trace` implementations and
+ * `generate_dependencies` (machine.rs:228-248) run on the GPU from those records (csrc/tracegen.cuh), so only
+ * 16 B/cycle cross PCIe.  ctx may be NULL for bfgpu_execute (plain host memory, no device needed).
+ * max_cycles 0 = the shard limit 2^23 (clk = 2*cycle must fit the 24-bit range checks). */
+typedef struct bfgpu_record bfgpu_record; /* ExecutionRecord */
+int32_t bfgpu_execute(bfgpu_ctx* ctx, const char* code, const uint8_t* stdin_bytes, uint64_t n_stdin, uint64_t max_cycles,
+                      bfgpu_record** out); /* *out is set even on failure: bfgpu_record_error(), then bfgpu_record_free() */
+const char* bfgpu_record_error(const bfgpu_record* rec);
+/* counts: cycles, instructions, alu / jump / memory-instruction / io events, touched cells, output bytes */
+int32_t bfgpu_record_info(const bfgpu_record* rec, uint64_t counts[8]);
+int32_t bfgpu_record_output(const bfgpu_record* rec, uint8_t* out);
+/* raw views (tests): (cycles+1) x {pc, mp, prev_ts, mv | prev_value << 8}; cells x {addr, initial ts, initial value,
+ * final ts, final value}; program opcodes / jump targets */
+const uint32_t* bfgpu_record_cycles(const bfgpu_record* rec);
+const uint32_t* bfgpu_record_mem_events(const bfgpu_record* rec);
+int32_t bfgpu_record_program(const bfgpu_record* rec, uint32_t* ops, uint32_t* args);
+void bfgpu_record_free(bfgpu_record* rec);
+/* StarkMachine::setup for the record's program (preprocessed Program + Byte traces) */
+int32_t bfgpu_machine_setup_record(bfgpu_ctx* ctx, const bfgpu_record* rec, uint32_t commit[8], bfgpu_pk** out);
+/* generate every included chip's main trace on the device and commit (MachineProver::commit, prover.rs:209-236) */
+int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_record* rec, uint32_t root[8], bfgpu_shard** out);
+/* traces held by a shard, in commit order; get_trace copies one out row-major, natural row order, caller representation */
+int32_t bfgpu_shard_num_traces(const bfgpu_shard* shard);
+int32_t bfgpu_shard_trace_info(const bfgpu_shard* shard, int32_t i, const char** name, uint64_t* rows, uint64_t* cols);
+int32_t bfgpu_shard_get_trace(const bfgpu_shard* shard, int32_t i, uint32_t* out);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,19 @@ ABI = {
     "bfgpu_pcs_get_evaluations": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]),
     "bfgpu_pcs_tree": (C.c_void_p, [C.c_void_p]),
     "bfgpu_pcs_data_free": (None, [C.c_void_p]),
+    "bfgpu_execute": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "bfgpu_record_error": (C.c_char_p, [C.c_void_p]),
+    "bfgpu_record_info": (C.c_int32, [C.c_void_p, _u64p]),
+    "bfgpu_record_output": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bfgpu_record_cycles": (C.c_void_p, [C.c_void_p]),
+    "bfgpu_record_mem_events": (C.c_void_p, [C.c_void_p]),
+    "bfgpu_record_program": (C.c_int32, [C.c_void_p, _u32p, _u32p]),
+    "bfgpu_record_free": (None, [C.c_void_p]),
+    "bfgpu_machine_setup_record": (C.c_int32, [C.c_void_p, C.c_void_p, _u32p, C.POINTER(C.c_void_p)]),
+    "bfgpu_machine_commit_record": (C.c_int32, [C.c_void_p, C.c_void_p, _u32p, C.POINTER(C.c_void_p)]),
+    "bfgpu_shard_num_traces": (C.c_int32, [C.c_void_p]),
+    "bfgpu_shard_trace_info": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), _u64p, _u64p]),
+    "bfgpu_shard_get_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "bfgpu_dist_commit_begin": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u32p, C.c_int32, C.POINTER(C.c_void_p)]),
     "bfgpu_dist_commit_local_cols": (C.c_uint32, [C.c_void_p, C.c_int32, _u32p]),
     "bfgpu_dist_commit_recv_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),
@@ -191,15 +204,15 @@ class Context:
         self._pinned = []
 
     PHASES = ["h2d", "ingest", "intt", "scale", "ntt", "leaf_hash", "compress", "other", "open_eval", "open_reduce", "fri",
-              "pow", "query", "perm", "quotient", "exchange"]
+              "pow", "query", "perm", "quotient", "exchange", "tracegen", "reserved17", "reserved18", "reserved19"]
 
     def profile_enable(self, on=True):
         self.check(lib().bfgpu_profile_enable(self._h, 1 if on else 0))
 
     def profile_read(self):
         """-> {phase: (milliseconds, launches)} accumulated since profile_enable(True)."""
-        ms = (C.c_float * 16)()
-        ln = (C.c_uint64 * 16)()
+        ms = (C.c_float * 20)()
+        ln = (C.c_uint64 * 20)()
         self.check(lib().bfgpu_profile_read(self._h, ms, ln))
         return {n: (float(ms[i]), int(ln[i])) for i, n in enumerate(self.PHASES)}
 
@@ -521,6 +534,53 @@ def _named_mats(named):
     return cn, arr, keep
 
 
+class Record:
+    """ExecutionRecord of the native executor (`Program::from` + `Executor::run`, crates/core/executor/src/
+    program.rs:22-44, executor.rs:71-79,106-325): one 16-byte record per cycle, kept in page-locked memory when a
+    context is given.  ctx=None runs without a device (host logic tests)."""
+
+    def __init__(self, code, stdin=(), ctx=None, max_cycles=0):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        inp = np.ascontiguousarray(np.asarray(list(stdin), np.uint8))
+        rc = lib().bfgpu_execute(ctx._h if ctx is not None else None, code.encode(), _ptr(inp) if inp.size else None, inp.size, max_cycles,
+                                 C.byref(self._h))
+        if rc != 0:
+            msg = lib().bfgpu_record_error(self._h).decode() if self._h else "allocation failed"
+            self.free()
+            raise BfGpuError(f"bfgpu_execute failed ({rc}): {msg}")
+        c = (C.c_uint64 * 8)()
+        lib().bfgpu_record_info(self._h, c)
+        (self.cycles, self.n_instr, self.n_alu, self.n_jump, self.n_mem_instr, self.n_io, self.n_cells, n_out) = [int(x) for x in c]
+        out = np.zeros(max(n_out, 1), np.uint8)
+        lib().bfgpu_record_output(self._h, _ptr(out))
+        self.output = out[:n_out].tolist()
+
+    def cycle_records(self):
+        """(cycles + 1, 4) uint32: pc, mp, previous timestamp of the cell, mv | previous value << 8 (last row = sentinel)."""
+        p = lib().bfgpu_record_cycles(self._h)
+        return np.ctypeslib.as_array(C.cast(p, _u32p), shape=(self.cycles + 1, 4)).copy()
+
+    def memory_events(self):
+        if not self.n_cells:
+            return np.zeros((0, 5), np.uint32)
+        p = lib().bfgpu_record_mem_events(self._h)
+        return np.ctypeslib.as_array(C.cast(p, _u32p), shape=(self.n_cells, 5)).copy()
+
+    def program(self):
+        ops, args = np.zeros(self.n_instr, np.uint32), np.zeros(self.n_instr, np.uint32)
+        lib().bfgpu_record_program(self._h, ops.ctypes.data_as(_u32p), args.ctypes.data_as(_u32p))
+        return ops, args
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib().bfgpu_record_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.free()
+
+
 class CudaProver:
     """`MachineProver<KoalaBearPoseidon2, BfAir>` on the GPU (reference trait: crates/stark/src/prover.rs:27-150;
     CPU implementation it replaces: `CpuProver`, prover.rs:162-582)."""
@@ -556,6 +616,63 @@ class CudaProver:
         sd = _Named(self.ctx, h, lib().bfgpu_shard_free, [k for k, _ in srt], [v.shape[0] for _, v in srt])
         sd.commit = root
         return sd
+
+    def execute(self, code, stdin=()):
+        """`Executor::run`: native interpreter writing the cycle records into page-locked memory."""
+        return Record(code, stdin, self.ctx)
+
+    def setup_record(self, rec):
+        """StarkMachine::setup for the record's program (preprocessed traces are built inside the library)."""
+        commit = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        self.ctx.check(lib().bfgpu_machine_setup_record(self.ctx._h, rec._h, commit.ctypes.data_as(_u32p), C.byref(h)))
+        prows = max(16, 1 << max(rec.n_instr - 1, 0).bit_length())
+        srt = sorted([("Program", prows, 6), ("Byte", 65536, 2)], key=lambda t: (-t[1], t[0]))
+        pk = _Named(self.ctx, h, lib().bfgpu_pk_free, [t[0] for t in srt], [t[1] for t in srt])
+        pk.commit = commit
+        pk.widths = [t[2] for t in srt]
+        return pk
+
+    def commit_record(self, rec):
+        """MachineProver::commit with the main traces generated on the device from the execution record."""
+        root = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        self.ctx.check(lib().bfgpu_machine_commit_record(self.ctx._h, rec._h, root.ctypes.data_as(_u32p), C.byref(h)))
+        names, heights = [], []
+        for i in range(lib().bfgpu_shard_num_traces(h)):
+            nm, r, c = C.c_char_p(), C.c_uint64(), C.c_uint64()
+            lib().bfgpu_shard_trace_info(h, i, C.byref(nm), C.byref(r), C.byref(c))
+            names.append(nm.value.decode())
+            heights.append(r.value)
+        sd = _Named(self.ctx, h, lib().bfgpu_shard_free, names, heights)
+        sd.commit = root
+        return sd
+
+    def shard_traces(self, shard):
+        """{chip: main trace (rows, width)} held by a shard, natural row order (test hook)."""
+        out = {}
+        for i in range(lib().bfgpu_shard_num_traces(shard._h)):
+            nm, r, c = C.c_char_p(), C.c_uint64(), C.c_uint64()
+            lib().bfgpu_shard_trace_info(shard._h, i, C.byref(nm), C.byref(r), C.byref(c))
+            a = np.zeros((r.value, c.value), np.uint32)
+            self.ctx.check(lib().bfgpu_shard_get_trace(shard._h, i, _ptr(a)))
+            out[nm.value.decode()] = a
+        return out
+
+    def prove_program(self, code, stdin=(), pk=None, pow_witness=None, raw=False):
+        """`ProverClient::prove` (sdk/lib.rs, prover/lib.rs:70-90) end to end on the GPU backend: execute, generate the
+        traces on the device, commit, open.  Returns (proof | (words, decoder), record)."""
+        rec = self.execute(code, stdin)
+        own_pk = pk is None
+        if own_pk:
+            pk = self.setup_record(rec)
+        ch = Challenger(self.ctx)
+        lib().bfgpu_pk_observe_into(pk._h, ch._h)
+        shard = self.commit_record(rec)
+        buf = self.open_raw(pk, shard, ch.clone(), pow_witness)
+        shard.free()
+        res = (buf, (lambda: self._parse(buf, pk, None))) if raw else self._parse(buf, pk, None)
+        return res, rec
 
     def open(self, pk, shard, challenger, pow_witness=None):
         """MachineProver::open -> ShardProof as nested dicts (commitment, opened_values per chip, opening_proof, chip_ordering)."""

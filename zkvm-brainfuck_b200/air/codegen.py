@@ -220,7 +220,30 @@ def generate():
     return "\n".join(hdr) + "\n\n" + body + "\n\n" + "\n".join(disp) + "\n}  // namespace air\n"
 
 
+def generate_layout():
+    """csrc/gen_layout.cuh: column indices of every chip's main trace (first index for multi-column fields) for the
+    device-side trace generators (csrc/tracegen.cuh)."""
+    L = ["// GENERATED by zkvm-brainfuck_b200/air/codegen.py from the layouts in air/chips.py — do not edit.", "#pragma once", "namespace lay {"]
+    for ns, lay, width in (("cpu", C.CPU_LAYOUT, C.CPU_WIDTH), ("program", C.PROGRAM_LAYOUT, C.PROGRAM_WIDTH),
+                           ("addsub", C.ADDSUB_LAYOUT, C.ADDSUB_WIDTH), ("jump", C.JUMP_LAYOUT, C.JUMP_WIDTH),
+                           ("memory", C.MEMORY_LAYOUT, C.MEMORY_WIDTH), ("byte", C.BYTE_LAYOUT, C.BYTE_WIDTH),
+                           ("meminstr", C.MEMINSTR_LAYOUT, C.MEMINSTR_WIDTH), ("io", C.IO_LAYOUT, C.IO_WIDTH),
+                           ("program_prep", C.PROGRAM_PREP_LAYOUT, C.PROGRAM_PREP_WIDTH), ("byte_prep", C.BYTE_PREP_LAYOUT, C.BYTE_PREP_WIDTH)):
+        L.append(f"namespace {ns} {{")
+        L.append(f"constexpr int WIDTH = {width};")
+        for name, idx in lay.items():
+            L.append(f"constexpr int {name} = {idx if isinstance(idx, int) else idx[0]};")
+        L.append("}")
+    L.append(f"constexpr int OP_LOOP_START = {C.LOOP_START}, OP_LOOP_END = {C.LOOP_END}, OP_ADD = {C.ADD}, OP_SUB = {C.SUB}, OP_MEM_FWD = {C.MEM_FWD}, "
+             f"OP_MEM_BWD = {C.MEM_BWD}, OP_INPUT = {C.INPUT}, OP_OUTPUT = {C.OUTPUT};")
+    L.append(f"constexpr int U8_RANGE = {C.U8_RANGE}, U16_RANGE = {C.U16_RANGE};")
+    L.append("}  // namespace lay")
+    return "\n".join(L) + "\n"
+
+
 def main():
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "gen_layout.cuh"), "w") as f:
+        f.write(generate_layout())
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "gen_air.cuh")
     src = generate()
     with open(out, "w") as f:

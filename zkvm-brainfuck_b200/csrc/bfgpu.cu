@@ -25,6 +25,8 @@
 #include "kernels_ntt2.cuh"
 #include <array>
 #include <map>
+#include <mutex>
+#include <set>
 #include <tuple>
 #include <unordered_map>
 
@@ -74,6 +76,9 @@ struct bfgpu_ctx {
     // pipelined host commit (commit_host_pipelined): columns per block, multiple of 8; 0 disables.
     // $BFGPU_PIPE_COLS overrides (experiments)
     uint32_t pipe_cols = 64;  // 256-byte row segments per strided copy: 32 was 3 % slower end to end, 128 19 % (fewer stages)
+    void* pinned_cycles = nullptr;  // page-locked cycle-record buffer parked between executions (tracegen.cuh)
+    uint64_t pinned_cycles_cap = 0;
+    uint32_t* d_inv256 = nullptr;  // Montgomery inverses of 0..255 (tracegen.cuh, Jump chip)
     // peer receive buffers mapped through CUDA IPC (dist_commit.cuh), keyed by the 64-byte handle
     std::map<std::array<uint8_t, 64>, void*> ipc_open;
 };
@@ -92,6 +97,9 @@ struct bfgpu_pcs_data {
     std::vector<DMat> ldes;  // bit-reversed rows
     bfgpu_tree* tree = nullptr;
 };
+
+static std::mutex g_ctx_mutex;
+static std::set<bfgpu_ctx*> g_live_ctx;  // contexts that may still receive parked buffers
 
 static int32_t fail(bfgpu_ctx* ctx, int32_t code, const char* fmt, ...) {
     char buf[512];
@@ -256,6 +264,10 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     CU(cudaFuncSetAttribute(nttk::k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << (nttk::GMAX + nttk::LANES_LOG)));
     CU(cudaFuncSetAttribute(nttk::k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << (nttk::GMAX + nttk::LANES_LOG)));
     CU(cudaStreamSynchronize(ctx->stream));
+    {
+        std::lock_guard<std::mutex> g(g_ctx_mutex);
+        g_live_ctx.insert(ctx);
+    }
     return BFGPU_OK;
 }
 
@@ -263,6 +275,13 @@ extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
     if (!ctx) return;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
+    if (ctx->d_inv256) cudaFree(ctx->d_inv256);
+    {
+        std::lock_guard<std::mutex> g(g_ctx_mutex);
+        g_live_ctx.erase(ctx);
+        if (ctx->pinned_cycles) cudaFreeHost(ctx->pinned_cycles);
+        ctx->pinned_cycles = nullptr;
+    }
     for (auto& kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
     trim_cache(ctx);
     for (auto& kv : ctx->live) cudaFree(kv.first);
@@ -1983,3 +2002,8 @@ extern "C" int32_t bfgpu_machine_chip_info(int32_t i, const char** name, int32_t
 // one commitment over several GPUs
 // =====================================================================================================
 #include "dist_commit.cuh"
+
+// =====================================================================================================
+// native executor + device-side trace generation
+// =====================================================================================================
+#include "tracegen.cuh"
