@@ -322,6 +322,38 @@ def main():
                "h2d_bytes_per_step": 4 * R * W, "d2h_bytes_per_step": 32, "ms_per_step": dt / args.steps * 1e3}
         del host
 
+    # ---- N > 1: one independent program -> proof per GPU (replica throughput of the whole prover) -----------
+    replica_prove = None
+    if dist is not None and not args.no_prove:
+        code = "++++++++[>-[>-[>+>+<<-]<-]<-]"  # 4 173 897 cycles, Cpu trace 2^22 rows (north-star size)
+        prover = bf.CudaProver(ctx)
+        rec0 = prover.execute(code)
+        pk = prover.setup_record(rec0)
+        cycles = rec0.cycles
+        rec0.free()
+
+        def prove_once():
+            nrec = prover.execute(code)
+            ch = bf.Challenger(ctx)
+            lib.bfgpu_pk_observe_into(pk._h, ch._h)
+            sh = prover.commit_record(nrec)
+            buf = prover.open_raw(pk, sh, ch.clone())
+            sh.free()
+            nrec.free()
+            return buf
+
+        first = prove_once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            prove_once()
+        ctx.synchronize()
+        dt = shard.max_over_ranks(time.perf_counter() - t0, dist, "cuda") / args.steps
+        replica_prove = {"workload": "program -> proof, 4 173 897 cycles (Cpu trace 2^22 rows), one independent proof per GPU",
+                         "ms_per_proof": dt * 1e3, "proofs_per_s": world / dt, "trace_rows_per_s": world * (1 << 22) / dt,
+                         "cycles_per_s": world * cycles / dt, "proof_words": int(first.size)}
+        pk.free()
+
     # ---- N > 1: ONE commitment over all ranks (columns -> LDE -> P2P row exchange -> subtrees -> caps) -------
     one_commitment = None
     if dist is not None and not args.no_dist_commit:
@@ -409,6 +441,8 @@ def main():
             line["e2e"] = e2e
         if one_commitment:
             line["one_commitment"] = one_commitment
+        if replica_prove:
+            line["replica_prove"] = replica_prove
         if world == 1 and not args.no_prove:
             line["prove"] = prove_timings(ctx, bf, not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:

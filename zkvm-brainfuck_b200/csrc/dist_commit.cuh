@@ -245,8 +245,10 @@ extern "C" int32_t bfgpu_dist_commit_lde(bfgpu_dist_commit* dc, const bfgpu_mat*
         }
         DMat coef;
         if ((rc = ingest(ctx, local[i], /*bitrev=*/true, &coef)) != BFGPU_OK) break;
-        for (uint32_t c = 0; c < m.ncols && rc == BFGPU_OK; c += DIST_CHUNK_COLS) {
-            uint32_t nc = std::min(DIST_CHUNK_COLS, m.ncols - c);
+        // at least ~4 blocks per matrix so that only the last quarter of the exchange is exposed (16..64 columns each)
+        const uint32_t chunk = std::min(DIST_CHUNK_COLS, std::max(16u, ((m.ncols + 3) / 4 + 7) / 8 * 8));
+        for (uint32_t c = 0; c < m.ncols && rc == BFGPU_OK; c += chunk) {
+            uint32_t nc = std::min(chunk, m.ncols - c);
             if ((rc = retire(1)) != BFGPU_OK) break;  // at most two LDE blocks alive: one in the NTT, one being scattered
             DMat slice = coef, lde;
             slice.d = coef.d + (uint64_t)c * coef.rows;
