@@ -116,3 +116,31 @@ def test_distributed_commit_shifted_domains(oracle):
     ref = oracle.PcsData(evals, domain_shifts=shifts)
     for rank, _, reps in _run(2, "narrow", "p2p", shifts):
         assert reps[0][0] == ref.root.tolist()
+
+
+def test_distributed_commit_argument_errors():
+    """C-ABI validation of the sharded commit (no second process needed)."""
+    import ctypes as C
+    import zkvm_brainfuck_b200 as bf
+    ctx = bf.Context()
+    L = bf.lib()
+    rows = (C.c_uint64 * 1)(256)
+    cols = (C.c_uint32 * 1)(8)
+    h = C.c_void_p()
+
+    def begin(rank, world, r=rows):
+        return L.bfgpu_dist_commit_begin(ctx._h, rank, world, r, cols, 1, C.byref(h))
+
+    assert begin(0, 3) == -1 and b"power of two" in L.bfgpu_last_error(ctx._h)
+    assert begin(2, 2) == -1
+    assert begin(0, 32) == -1
+    assert begin(0, 2, (C.c_uint64 * 1)(100)) == -1 and b"power of two" in L.bfgpu_last_error(ctx._h)
+    tiny = (C.c_uint64 * 1)(2)  # LDE height 4 < 8 ranks
+    assert begin(0, 8, tiny) == -1 and b"below the world size" in L.bfgpu_last_error(ctx._h)
+    assert begin(0, 2) == 0
+    mat = bf.Mat(None, 256, 4)
+    assert L.bfgpu_dist_commit_lde(h, C.byref(mat), None) == -4  # neither peers nor staging set
+    cap = (C.c_uint32 * 8)()
+    assert L.bfgpu_dist_commit_finish(h, cap) == -4              # no LDE yet
+    L.bfgpu_dist_commit_free(h)
+    ctx.close()
