@@ -139,6 +139,38 @@ def prove_timings(ctx, bf, with_cpu):
             nrec.free()
             etimes.append((t1 - t0) * 1e3)
             ptimes.append((t2 - t0) * 1e3)
+        # one more run with the library's per-phase CUDA-event timers: HBM rooflines of the prover-side kernels from their
+        # ALGORITHMIC bytes: quotient reads prep+main+perm LDE rows once and writes 16 B per coset point; the
+        # reduced openings read every committed LDE once; the barycentric evaluation reads the low coset (half) of every LDE
+        ctx.profile_enable(True)
+        nrec = prover.execute(code, stdin)
+        ch = bf.Challenger(ctx)
+        bf.lib().bfgpu_pk_observe_into(pk._h, ch._h)
+        shard = prover.commit_record(nrec)
+        prover.open_raw(pk, shard, ch.clone())
+        ph = {k: v[0] for k, v in ctx.profile_read().items() if v[0] or v[1]}
+        ctx.profile_enable(False)
+        info = {c[0]: c for c in prover.chips}
+        lde_cells = quot_bytes = 0
+        for nm, h in zip(shard.names, shard.heights):
+            _, mw, pw, ew, _lo = info[nm]
+            lde_cells += 2 * h * (pw + mw + 4 * ew + 8)             # prep + main + perm + two 4-column quotient chunks (each 2h x 4)
+            quot_bytes += 4 * 2 * h * (pw + mw + 4 * ew) + 16 * 2 * h
+        shard.free()
+        nrec.free()
+        hbm = 6451.5
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", hbm)
+        except OSError:
+            pass
+
+        def roof(bytes_, ms):
+            return {"algorithmic_bytes": int(bytes_), "ms": ms, "GB/s": bytes_ / (ms * 1e-3) / 1e9, "frac_hbm": bytes_ / (ms * 1e-3) / 1e9 / hbm}
+
+        entry["phases_ms"] = ph
+        entry["hbm_rooflines"] = {"quotient": roof(quot_bytes, ph["quotient"]), "open_reduce": roof(4 * lde_cells, ph["open_reduce"]),
+                                  "open_eval": roof(2 * lde_cells, ph["open_eval"]),
+                                  "note": "all three are arithmetic-bound on F_p^4 products (profiles/r1_prover_kernels.md), not HBM-bound"}
         entry.update({"program_to_proof_ms": min(ptimes[1:]), "native_executor_ms": min(etimes[1:]), "python_executor_tracegen_s": round(t_host, 2),
                       "program_proof_equals_trace_proof": bool(buf2.shape == buf.shape and (buf2 == buf).all()),
                       "program_to_proof_khz": rec.cycles / min(ptimes[1:])})

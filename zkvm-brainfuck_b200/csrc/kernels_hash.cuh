@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(HASH_THREADS) k_compress_layer(const uint32_t*
 // Top of the tree in ONE launch: starting from a layer of `len0` <= TOP_MAX digests, computes every remaining layer
 // down to the root inside a single CTA (the layer being consumed sits in shared memory), writing each layer to its
 // global array.  Removes ~10 launches per tree, which dominate small proofs and the FRI commit phase.
-constexpr int TOP_MAX = 1024, TOP_THREADS = 512, TOP_LEVELS = 10;
+constexpr int TOP_MAX = 1024, TOP_THREADS = 1024, TOP_LEVELS = 10;
 struct TopArgs {
     const uint32_t* in;                  // len0 digests
     uint32_t* out[TOP_LEVELS];            // out[k]: len0 >> (k+1) digests
@@ -126,16 +126,65 @@ struct TopArgs {
     uint32_t len0;
     uint32_t nlevels;
 };
+// Levels with at most TOP_THREADS / 4 nodes run the four-lane permutation (p2::permute_x4): a level costs one
+// permutation LATENCY whatever its width, and the four-lane form has a third of the dependent chain.
 __global__ void __launch_bounds__(TOP_THREADS) k_compress_top(TopArgs A) {
     __shared__ __align__(16) uint32_t cur[TOP_MAX * 8];
-    for (uint32_t i = threadIdx.x; i < A.len0 * 2; i += TOP_THREADS)
-        reinterpret_cast<uint4*>(cur)[i] = reinterpret_cast<const uint4*>(A.in)[i];
+    __shared__ uint32_t s_ext[8 * 16], s_int[16];
+    const uint32_t t = threadIdx.x;
+    for (uint32_t i = t; i < A.len0 * 2; i += TOP_THREADS) reinterpret_cast<uint4*>(cur)[i] = reinterpret_cast<const uint4*>(A.in)[i];
+    if (t < 128) s_ext[t] = p2::c_p2.ext_s[t >> 4][t & 15];
+    if (t < 16) s_int[t] = p2::c_p2.internal_s[t];
     __syncthreads();
+    const int q = t & 3;
+    const p2::X4 xc = p2::x4_setup(s_ext, s_int, q);
     uint32_t len = A.len0;
     for (uint32_t k = 0; k < A.nlevels; k++) {
         len >>= 1;
+        if (4 * len <= TOP_THREADS) {
+            // ---- four lanes per node ----
+            const uint32_t i = t >> 2;
+            const bool warp_on = ((t & ~31u) >> 2) < len, on = i < len;  // whole warps without a node skip the level
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (on) {
+                uint4 x = *reinterpret_cast<const uint4*>(cur + 16 * i + 4 * q);
+                w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+            }
+            __syncthreads();  // everyone has read its pair before the layer is overwritten
+            if (warp_on) {
+                p2::permute_x4(w, xc, q);
+                if (A.ncols[k]) {
+                    // digest of the injected row i: overwrite-mode sponge, rate 8 = the words of lanes q = 0, 1
+                    uint32_t h[4] = {0, 0, 0, 0};
+                    const uint32_t nc = A.ncols[k];
+                    for (uint32_t c0 = 0; c0 < nc; c0 += 8) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            uint32_t c = c0 + 4 * q + j;
+                            if (on && q < 2 && c < nc) h[j] = __ldg(A.colptr[k][c] + (uint64_t)i * A.row_stride[k]);
+                        }
+                        p2::permute_x4(h, xc, q);
+                    }
+                    // state = (compressed children, row digest): lanes 2, 3 take the digest words of lanes 0, 1
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t from_low = __shfl_xor_sync(0xffffffffu, h[j], 2);
+                        if (q >= 2) w[j] = from_low;
+                    }
+                    p2::permute_x4(w, xc, q);
+                }
+                if (on && q < 2) {
+                    uint4 o = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(A.out[k] + 8 * i + 4 * q) = o;
+                    *reinterpret_cast<uint4*>(cur + 8 * i + 4 * q) = o;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- one thread per node (first level of a full-size top: 512 nodes) ----
         uint32_t s[16];
-        const uint32_t i = threadIdx.x;  // len <= TOP_MAX / 2 = TOP_THREADS
+        const uint32_t i = t;
         if (i < len) {
 #pragma unroll
             for (int w = 0; w < 16; w++) s[w] = cur[16 * i + w];

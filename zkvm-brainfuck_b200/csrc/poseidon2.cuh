@@ -151,6 +151,65 @@ KB_D void permute(uint32_t (&s)[16]) {
     }
 }
 
+// ---- one permutation spread over FOUR lanes (latency variant) ---------------------------------------------------
+// Lane q = lane & 3 of an aligned 4-lane group holds state words 4q .. 4q+3.  M4 is local to a lane, the column sums
+// of the external layer and the 16-word sum of the internal layer are two xor-shuffles, the internal diagonal is the
+// generic Shoup product on every word (uniform code, per-lane constants).  ~1/3 of the dependent instruction chain
+// of the one-thread permutation: used where a tree level has fewer nodes than the machine has lanes
+// (hashk::k_compress_top), where latency, not throughput, is what is paid.  All 32 lanes of the warp must call it.
+struct X4 {
+    const uint32_t* ext_s;  // [8][16] round constants minus p (shared or global memory)
+    const uint32_t* int_s;  // [13]
+    uint32_t dw[4], dwp[4];  // this lane's four diagonal entries (plain residue, Shoup quotient)
+};
+KB_D X4 x4_setup(const uint32_t* ext_s, const uint32_t* int_s, int q) {
+    X4 c;
+    c.ext_s = ext_s;
+    c.int_s = int_s;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        c.dw[j] = c_p2.diag_w[4 * q + j];
+        c.dwp[j] = c_p2.diag_wp[4 * q + j];
+    }
+    return c;
+}
+KB_D uint32_t quad_sum(uint32_t v) {
+    v = add(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return add(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+KB_D void external_linear_x4(uint32_t (&w)[4]) {
+    mat4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[j] = add(w[j], quad_sum(w[j]));
+}
+KB_D void permute_x4(uint32_t (&w)[4], const X4& c, int q) {
+    external_linear_x4(w);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            const uint32_t* rcs = c.ext_s + (half * 4 + r) * 16 + 4 * q;
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[j] = sbox_signed(w[j] + rcs[j]);
+            external_linear_x4(w);
+        }
+        if (half == 0) {
+#pragma unroll 1
+            for (int r = 0; r < 13; r++) {
+                uint32_t x = sbox_signed(w[0] + c.int_s[r]);
+                w[0] = q == 0 ? x : w[0];
+                uint32_t sum = quad_sum(add(add(w[0], w[1]), add(w[2], w[3])));
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t qq = __umulhi(w[j], c.dwp[j]);
+                    uint32_t rr = w[j] * c.dw[j] - qq * kb::P;
+                    w[j] = add(kb::umin_(rr, rr - kb::P), sum);
+                }
+            }
+        }
+    }
+}
+
 // fully unrolled variant (kept for the instruction-cache experiment in tools/p2_bench.cu)
 KB_D void permute_unrolled(uint32_t (&s)[16]) {
     external_linear(s);
