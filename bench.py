@@ -32,6 +32,11 @@ sys.path.insert(0, ROOT)
 P = 2130706433
 # executed thread-instructions per Poseidon2 permutation in k_leaf_hash: ncu smsp__inst_executed.sum * 32 / permutations
 # (profiles/r1_leaf_hash_final.md)
+# SASS thread-instructions per element of the NTT passes of a 2^22-point column (pass plan g = 8, 7, 7): column-loop bodies of
+# k_pass<0,3,0,0> x2 + k_pass<0,4,1,0> (584 + 584 + 472) / 16 forward, k_pass<1,4,1,0> + k_pass<1,3,0,0> + k_pass<1,3,0,1> (517 + 641 + 857) / 16
+# inverse incl. the fused coset epilogue (cuobjdump -sass, profiles/r1_ntt_instr_counts.txt)
+NTT_INSTR_FWD_2P22 = 102.5
+NTT_INSTR_INV_2P22 = 125.9
 P2_INSTR_PER_PERM = 4606
 # DRAM bytes of one k_leaf_hash launch at the default workload, from the same ncu --set full capture
 LEAF_TRAFFIC_2P22X256 = 8603574000 + 273566720
@@ -466,6 +471,13 @@ def main():
             "roofline_hbm": {"kernel": "LDE = k_ingest + k_ntt_pass<inv> + k_scale_cosets + k_ntt_pass<fwd>", "bound": "hbm",
                              "achieved": lde_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": lde_gbs / hbm_peak, "traffic": None,
                              "peak_source": hbm_src, "note": f"12*R*W algorithmic bytes / {lde_ms:.3f} ms for the whole LDE"},
+            "roofline_ntt_int32": None if args.log_rows != 22 else {
+                "kernel": "ntt2::k_pass (3 inverse + 3 forward passes per column at 2^22)", "bound": "int32",
+                "achieved": (NTT_INSTR_FWD_2P22 * 2 * R * W + NTT_INSTR_INV_2P22 * R * W) / ((phases["intt"][0] + phases["ntt"][0]) / args.steps * 1e-3) / 1e9,
+                "peak": int32_peak, "unit": "Ginstr/s",
+                "frac": (NTT_INSTR_FWD_2P22 * 2 * R * W + NTT_INSTR_INV_2P22 * R * W) / ((phases["intt"][0] + phases["ntt"][0]) / args.steps * 1e-3) / 1e9 / int32_peak,
+                "note": "the transforms are issue-bound, not HBM-bound: SASS thread-instructions per element (column-loop bodies, cuobjdump) "
+                        f"forward {NTT_INSTR_FWD_2P22} per LDE element, inverse {NTT_INSTR_INV_2P22} per trace element; >85 % of them are butterfly arithmetic"},
             "clocks": clocks,
             "root": [int(x) for x in root_dev],
         }
