@@ -176,6 +176,13 @@ def prove_timings(ctx, bf, with_cpu):
         entry["hbm_rooflines"] = {"quotient": roof(quot_bytes, ph["quotient"]), "open_reduce": roof(4 * lde_cells, ph["open_reduce"]),
                                   "open_eval": roof(2 * lde_cells, ph["open_eval"]),
                                   "note": "all three are arithmetic-bound on F_p^4 products (profiles/r1_prover_kernels.md), not HBM-bound"}
+        if "2^22" in name:
+            # throughput of a stream of proofs: the interpreter of proof k+1 runs on a host thread while the GPU proves proof k
+            njobs, stamps = 5, []
+            for _buf, _rec in prover.prove_many([(code, stdin)] * njobs, pk_for=lambda _c: pk):
+                stamps.append(time.perf_counter())
+            entry["pipelined_ms_per_proof"] = (stamps[-1] - stamps[0]) / (njobs - 1) * 1e3
+            entry["pipelined_trace_rows_per_s"] = float(traces["Cpu"].shape[0]) / ((stamps[-1] - stamps[0]) / (njobs - 1))
         entry.update({"program_to_proof_ms": min(ptimes[1:]), "native_executor_ms": min(etimes[1:]), "python_executor_tracegen_s": round(t_host, 2),
                       "program_proof_equals_trace_proof": bool(buf2.shape == buf.shape and (buf2 == buf).all()),
                       "program_to_proof_khz": rec.cycles / min(ptimes[1:])})

@@ -81,3 +81,20 @@ def test_prove_program_equals_proof_from_host_traces(ctx, oracle, code, stdin):
         pk.free()
     finally:
         ctx.set_fri_params(1, 84, 16)
+
+
+def test_prove_many_pipelines_executor_and_gpu(ctx):
+    """A stream of jobs through `prove_many` (interpreter of job k+1 overlapped with the GPU proof of job k) gives the
+    same proofs as one-at-a-time `prove_program`."""
+    ctx.set_fri_params(1, 12, 6)
+    try:
+        prover = bf.CudaProver(ctx)
+        jobs = [(_code("hello.bf"), []), (",.", [9]), (_code("fibo.bf"), [17]), (_code("hello.bf"), [])]
+        got = [(buf.copy(), rec.output) for buf, rec in prover.prove_many(jobs)]
+        assert len(got) == len(jobs)
+        for (code, stdin), (buf, output) in zip(jobs, got):
+            (ref, _), rec = prover.prove_program(code, stdin, raw=True)
+            assert output == rec.output and buf.shape == ref.shape and (buf == ref).all()
+        assert (got[0][0] == got[3][0]).all()
+    finally:
+        ctx.set_fri_params(1, 84, 16)

@@ -674,6 +674,52 @@ class CudaProver:
         res = (buf, (lambda: self._parse(buf, pk, None))) if raw else self._parse(buf, pk, None)
         return res, rec
 
+    def prove_many(self, jobs, pk_for=None, prefetch=1):
+        """Proofs of a stream of (code, stdin) jobs with the host interpreter of job k+1 running while the GPU proves
+        job k (the executor is sequential host code, ~4 ns/cycle; the C call releases the GIL).  Yields
+        (serialised proof words, Record) in job order.  pk_for(code) -> proving key (default: one setup per distinct
+        program, cached)."""
+        import queue
+        import threading
+        pks = {}
+
+        def get_pk(code, rec):
+            if pk_for is not None:
+                return pk_for(code)
+            if code not in pks:
+                pks[code] = self.setup_record(rec)
+            return pks[code]
+
+        q = queue.Queue(maxsize=max(1, prefetch))
+
+        def producer():
+            try:
+                for code, stdin in jobs:
+                    q.put((code, self.execute(code, stdin)))
+                q.put(None)
+            except BaseException as e:  # surface executor errors in the consumer
+                q.put(e)
+
+        th = threading.Thread(target=producer, daemon=True)
+        th.start()
+        while True:
+            item = q.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            code, rec = item
+            pk = get_pk(code, rec)
+            ch = Challenger(self.ctx)
+            lib().bfgpu_pk_observe_into(pk._h, ch._h)
+            shard = self.commit_record(rec)
+            buf = self.open_raw(pk, shard, ch.clone())
+            shard.free()
+            yield buf, rec
+        th.join()
+        for pk in pks.values():
+            pk.free()
+
     def open(self, pk, shard, challenger, pow_witness=None):
         """MachineProver::open -> ShardProof as nested dicts (commitment, opened_values per chip, opening_proof, chip_ordering)."""
         buf = self.open_raw(pk, shard, challenger, pow_witness)

@@ -93,6 +93,7 @@ extern "C" int32_t bfgpu_execute(bfgpu_ctx* ctx, const char* code, const uint8_t
     r->pinned = ctx != nullptr;
     r->owner = ctx;
     if (ctx) {
+        cudaSetDevice(ctx->device);  // may run on a helper thread (CudaProver.prove_many): page-lock against the right device
         std::lock_guard<std::mutex> g(g_ctx_mutex);
         if (ctx->pinned_cycles) {
             r->cycles = (uint4*)ctx->pinned_cycles;
