@@ -495,6 +495,7 @@ def main():
         if replica_prove:
             line["replica_prove"] = replica_prove
         if world == 1 and not args.no_prove:
+            ctx.set_input_space(bf.MEM_HOST)  # traces come from (pinned) host memory
             line["prove"] = prove_timings(ctx, bf, not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             gbs, sec, threads = cpu_commit_sample(args.cpu_log_rows, W, 1, 1)
