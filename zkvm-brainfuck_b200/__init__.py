@@ -715,7 +715,9 @@ class CudaProver:
             shard = self.commit_record(rec)
             buf = self.open_raw(pk, shard, ch.clone())
             shard.free()
+            item = None
             yield buf, rec
+            del buf, rec  # the record's page-locked buffer goes back to the context's pool for the next execution
         th.join()
         for pk in pks.values():
             pk.free()

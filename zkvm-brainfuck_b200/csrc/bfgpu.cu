@@ -76,8 +76,7 @@ struct bfgpu_ctx {
     // pipelined host commit (commit_host_pipelined): columns per block, multiple of 8; 0 disables.
     // $BFGPU_PIPE_COLS overrides (experiments)
     uint32_t pipe_cols = 64;  // 256-byte row segments per strided copy: 32 was 3 % slower end to end, 128 19 % (fewer stages)
-    void* pinned_cycles = nullptr;  // page-locked cycle-record buffer parked between executions (tracegen.cuh)
-    uint64_t pinned_cycles_cap = 0;
+    std::vector<std::pair<void*, uint64_t>> pinned_pool;  // page-locked cycle-record buffers parked between executions (tracegen.cuh)
     uint32_t* d_inv256 = nullptr;  // Montgomery inverses of 0..255 (tracegen.cuh, Jump chip)
     // peer receive buffers mapped through CUDA IPC (dist_commit.cuh), keyed by the 64-byte handle
     std::map<std::array<uint8_t, 64>, void*> ipc_open;
@@ -279,8 +278,8 @@ extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
     {
         std::lock_guard<std::mutex> g(g_ctx_mutex);
         g_live_ctx.erase(ctx);
-        if (ctx->pinned_cycles) cudaFreeHost(ctx->pinned_cycles);
-        ctx->pinned_cycles = nullptr;
+        for (auto& b : ctx->pinned_pool) cudaFreeHost(b.first);
+        ctx->pinned_pool.clear();
     }
     for (auto& kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
     trim_cache(ctx);

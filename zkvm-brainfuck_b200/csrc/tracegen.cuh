@@ -41,6 +41,9 @@ static bool record_grow(bfgpu_record* r, uint64_t want, uint64_t used) {
     if (want <= r->cap) return true;
     uint64_t cap = std::max<uint64_t>(r->cap * 2, 1u << 16);
     while (cap < want) cap *= 2;
+    // page-locked buffers are allocated once at the shard limit (2^23 cycles + sentinel, 128 MB) and recycled through the
+    // context: cudaHostAlloc / cudaFreeHost cost tens of milliseconds and serialise against the GPU work of other threads
+    if (r->pinned) cap = std::max<uint64_t>(cap, (1ull << 23) + 2);
     uint4* p = nullptr;
     if (r->pinned) {
         if (cudaHostAlloc((void**)&p, cap * sizeof(uint4), cudaHostAllocDefault) != cudaSuccess) {
@@ -71,12 +74,8 @@ extern "C" void bfgpu_record_free(bfgpu_record* r) {
         else {
             // page-locking 128 MB costs tens of milliseconds: hand the buffer to the owning context for the next execution
             std::lock_guard<std::mutex> g(g_ctx_mutex);
-            if (g_live_ctx.count(r->owner) && !r->owner->pinned_cycles) {
-                r->owner->pinned_cycles = r->cycles;
-                r->owner->pinned_cycles_cap = r->cap;
-            } else {
-                cudaFreeHost(r->cycles);
-            }
+            if (g_live_ctx.count(r->owner) && r->owner->pinned_pool.size() < 4) r->owner->pinned_pool.emplace_back(r->cycles, r->cap);
+            else cudaFreeHost(r->cycles);
         }
     }
     delete r;
@@ -95,10 +94,10 @@ extern "C" int32_t bfgpu_execute(bfgpu_ctx* ctx, const char* code, const uint8_t
     if (ctx) {
         cudaSetDevice(ctx->device);  // may run on a helper thread (CudaProver.prove_many): page-lock against the right device
         std::lock_guard<std::mutex> g(g_ctx_mutex);
-        if (ctx->pinned_cycles) {
-            r->cycles = (uint4*)ctx->pinned_cycles;
-            r->cap = ctx->pinned_cycles_cap;
-            ctx->pinned_cycles = nullptr;
+        if (!ctx->pinned_pool.empty()) {
+            r->cycles = (uint4*)ctx->pinned_pool.back().first;
+            r->cap = ctx->pinned_pool.back().second;
+            ctx->pinned_pool.pop_back();
         }
     }
     using namespace lay;
