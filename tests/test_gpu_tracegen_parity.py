@@ -98,3 +98,37 @@ def test_prove_many_pipelines_executor_and_gpu(ctx):
         assert (got[0][0] == got[3][0]).all()
     finally:
         ctx.set_fri_params(1, 84, 16)
+
+
+@pytest.mark.parametrize("code,cycles,cpu_rows", [("-[>-[>+>+>+<<<-]<-]", 716807, 1 << 20), ("++++++++[>-[>-[>+>+<<-]<-]<-]", 4173897, 1 << 22)])
+def test_fullsize_program_proof_is_accepted_by_the_restated_verifier(ctx, oracle, code, cycles, cpu_rows):
+    """BASELINE config 3 and the north-star size, program -> proof entirely on the backend (native executor, device
+    traces, 84 queries, 16 PoW bits); too big for a word-for-word comparison with the numpy prover, so the check is the
+    reference's own acceptance test: `Verifier::verify_shard` (restated, oracle/prover.py) must accept, which includes
+    C(zeta) = q(zeta) Z_H(zeta) for every chip, the FRI low-degree test, all Merkle openings and the zero total of the
+    LogUp cumulative sums."""
+    from oracle import prover as PR, stark as S
+    prover = bf.CudaProver(ctx)
+    rec = prover.execute(code)
+    assert rec.cycles == cycles
+    pk = prover.setup_record(rec)
+    ch = bf.Challenger(ctx)
+    bf.lib().bfgpu_pk_observe_into(pk._h, ch._h)
+    shard = prover.commit_record(rec)
+    assert shard.names[0] == "Cpu" and shard.heights[0] == cpu_rows
+    proof = prover.open(pk, shard, ch.clone())
+    shard.free()
+    chips = importlib.import_module("zkvm-brainfuck_b200.air.chips").machine_chips()
+    local_only = dict((c[0], c[4]) for c in prover.chips)
+    vk = dict(commit=pk.commit, chip_information=[(n, h.bit_length() - 1, local_only[n]) for n, h in zip(pk.names, pk.heights)])
+    och = S.Challenger()
+    och.observe_digest(pk.commit)
+    for _ in range(7):
+        och.observe(0)
+    assert PR.verify_shard(chips, vk, proof, och, S.FriConfig()) is None
+    total = S.E_ZERO
+    for c in proof["opened_values"]:
+        total = S.e_add(total, c["cumulative_sum"])
+    assert S.e_eq(total, S.E_ZERO)
+    pk.free()
+    rec.free()
