@@ -75,6 +75,10 @@ struct bfgpu_ctx {
     size_t cached_bytes = 0;
     // pipelined host commit (commit_host_pipelined): columns per block, multiple of 8; 0 disables.
     // $BFGPU_PIPE_COLS overrides (experiments)
+    // device-resident single-matrix commits: leaf sponge of block b concurrent with the NTT of block b+1 ($BFGPU_OVERLAP=1).
+    // Measured at 2^22 x 256: 75.3 ms against 71.4 ms for the plain sequence (both kernels want the same two integer pipes;
+    // the blocked LDE and the parked sponge states cost more than co-scheduling recovers) => off.
+    bool overlap_device = false;
     uint32_t pipe_cols = 64;  // 256-byte row segments per strided copy: 32 was 3 % slower end to end, 128 19 % (fewer stages)
     std::vector<std::pair<void*, uint64_t>> pinned_pool;  // page-locked cycle-record buffers parked between executions (tracegen.cuh)
     uint32_t* d_inv256 = nullptr;  // Montgomery inverses of 0..255 (tracegen.cuh, Jump chip)
@@ -213,6 +217,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (const char* e = getenv("BFGPU_PIPE_COLS")) ctx->pipe_cols = (uint32_t)atoi(e) / 8 * 8;
+    if (const char* e = getenv("BFGPU_OVERLAP")) ctx->overlap_device = atoi(e) != 0;
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
 
     // Poseidon2 constant bank (kb31_poseidon2.rs:35-50): internal constants = column 0 of table rows
@@ -457,10 +462,11 @@ static void prestage_clear(bfgpu_ctx* ctx) {
 }
 
 // row-major device words in the caller's representation -> column-major Montgomery words at dst
-static int32_t ingest_device(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows, uint32_t cols, bool bitrev, uint32_t* dst) {
+static int32_t ingest_device(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows, uint32_t cols, bool bitrev, uint32_t* dst, uint64_t src_pitch = 0) {
     Phase ph(ctx, BFGPU_PHASE_INGEST);
     dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
-    nttk::k_ingest<<<grid, block, 0, ctx->stream>>>(src, dst, rows, cols, ilog2(rows), bitrev ? 1 : 0, ctx->repr == BFGPU_REPR_CANONICAL);
+    nttk::k_ingest<<<grid, block, 0, ctx->stream>>>(src, dst, rows, cols, ilog2(rows), bitrev ? 1 : 0, ctx->repr == BFGPU_REPR_CANONICAL,
+                                                     src_pitch ? src_pitch : cols);
     LAUNCHED(ctx);
     CU(cudaGetLastError());
     return BFGPU_OK;
@@ -1013,7 +1019,10 @@ extern "C" void bfgpu_tree_free(bfgpu_tree* t) { tree_release(t); }
 //                   absorbs the block's columns (k_leaf_absorb; 16-word states parked in HBM between blocks).
 // PCIe (~55 GB/s) and the GPU work (~LDE + hash) take about the same time at 2^22 x 256, so the commit from host
 // memory costs about max(copy, compute) instead of their sum.  Same LDE, same digests as the one-shot path.
+// Experiment switch (ctx->overlap_device, off): device-resident input through the same block structure with the leaf
+// sponge of block b on the second stream, concurrent with the NTT of block b+1.  It lost 5 % (see bfgpu_ctx).
 static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bits, uint32_t shift_mont, DMat* lde, uint32_t** first_layer) {
+    const bool from_device = ctx->input_space == BFGPU_MEM_DEVICE;
     const uint64_t R = m.rows, N = R << added_bits;
     const uint32_t W = (uint32_t)m.cols, CB = ctx->pipe_cols;
     // block boundaries (multiples of 8 columns).  The copy is the longer stage, so the commit ends one block of compute
@@ -1034,8 +1043,10 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
     lde->rs = 1;
     uint32_t *staged[2] = {nullptr, nullptr}, *state = nullptr, *layer = nullptr;
     TRY(dalloc(ctx, (void**)&lde->d, N * W * 4));
-    TRY(dalloc(ctx, (void**)&staged[0], R * CB * 4));
-    TRY(dalloc(ctx, (void**)&staged[1], R * CB * 4));
+    if (!from_device) {
+        TRY(dalloc(ctx, (void**)&staged[0], R * CB * 4));
+        TRY(dalloc(ctx, (void**)&staged[1], R * CB * 4));
+    }
     TRY(dalloc(ctx, (void**)&state, N * 16 * 4));
     TRY(dalloc(ctx, (void**)&layer, N * 32));
     cudaEvent_t ready[2], consumed[2], fence;
@@ -1056,7 +1067,7 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
         CU(cudaEventRecord(ready[slot], ctx->copy_stream));
         return BFGPU_OK;
     };
-    rc = copy_block(0);
+    if (!from_device) rc = copy_block(0);
     for (uint32_t b = 0; b < nb && rc == BFGPU_OK; b++) {
         const int slot = b & 1;
         const uint32_t cb = start[b + 1] - start[b];
@@ -1064,19 +1075,33 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
         coef.rows = R;
         coef.cols = cb;
         if ((rc = dalloc(ctx, (void**)&coef.d, R * cb * 4)) != BFGPU_OK) break;
-        CU(cudaStreamWaitEvent(ctx->stream, ready[slot], 0));
-        if ((rc = ingest_device(ctx, staged[slot], R, cb, /*bitrev=*/true, coef.d)) != BFGPU_OK) break;
-        CU(cudaEventRecord(consumed[slot], ctx->stream));
-        // enqueue the copy after next only now: its wait on consumed[slot] must see this record
-        if (b + 1 < nb && b == 0) rc = copy_block(1);
-        if (rc == BFGPU_OK && b + 2 < nb) rc = copy_block(b + 2);
-        if (rc != BFGPU_OK) break;
+        if (from_device) {
+            if ((rc = ingest_device(ctx, m.data + start[b], R, cb, /*bitrev=*/true, coef.d, W)) != BFGPU_OK) break;
+        } else {
+            CU(cudaStreamWaitEvent(ctx->stream, ready[slot], 0));
+            if ((rc = ingest_device(ctx, staged[slot], R, cb, /*bitrev=*/true, coef.d)) != BFGPU_OK) break;
+            CU(cudaEventRecord(consumed[slot], ctx->stream));
+            // enqueue the copy after next only now: its wait on consumed[slot] must see this record
+            if (b + 1 < nb && b == 0) rc = copy_block(1);
+            if (rc == BFGPU_OK && b + 2 < nb) rc = copy_block(b + 2);
+            if (rc != BFGPU_OK) break;
+        }
         if ((rc = lde_from_bitrev(ctx, coef, added_bits, shift_mont, &blk, /*consume=*/true, lde->d + (uint64_t)start[b] * N)) != BFGPU_OK) break;
         Phase ph(ctx, BFGPU_PHASE_LEAF);
-        hashk::k_leaf_absorb<<<(unsigned)((N + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(
+        cudaStream_t hs = ctx->stream;
+        if (from_device) {  // sponge on the second stream, behind this block's LDE
+            CU(cudaEventRecord(ready[slot], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ready[slot], 0));
+            hs = ctx->copy_stream;
+        }
+        hashk::k_leaf_absorb<<<(unsigned)((N + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, hs>>>(
             blk.d, N, cb, N, state, b == 0, b + 1 == nb, layer);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
+    }
+    if (from_device && rc == BFGPU_OK) {  // the tree is built on the compute stream: join
+        CU(cudaEventRecord(consumed[0], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, consumed[0], 0));
     }
     for (int k = 0; k < 2; k++) {
         cudaEventDestroy(ready[k]);
@@ -1107,8 +1132,8 @@ extern "C" int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, cons
     int32_t rc = prestage_all(ctx, evals, n);
     uint32_t gen = kb::to_mont(kb::GEN);
     uint32_t* first_layer = nullptr;
-    const bool pipelined = ctx->input_space == BFGPU_MEM_HOST && n == 1 && ctx->pipe_cols >= 8 && evals[0].cols >= 2 * (uint64_t)ctx->pipe_cols &&
-                           evals[0].rows * evals[0].cols >= (1ull << 20);
+    const bool pipelined = (ctx->input_space == BFGPU_MEM_HOST || ctx->overlap_device) && n == 1 && ctx->pipe_cols >= 8 &&
+                           evals[0].cols >= 2 * (uint64_t)ctx->pipe_cols && evals[0].rows * evals[0].cols >= (1ull << 20);
     for (int i = 0; i < n && rc == BFGPU_OK; i++) {
         // shift = GENERATOR / domain.shift  (TwoAdicFriPcs::commit)
         uint32_t shift = gen;

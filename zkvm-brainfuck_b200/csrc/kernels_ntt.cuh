@@ -48,8 +48,9 @@ __global__ void k_powers(uint32_t* __restrict__ out, uint32_t base, uint32_t sca
 
 // ---- ingest / egress: row-major host layout <-> column-major Montgomery ---------------------
 // dst[c][j] = conv(src[perm(j)][c]),  perm = bit reversal on log_rows bits when bitrev != 0
+// (src_pitch = words between consecutive source rows: cols for a whole matrix, more for a column block of a wider one)
 __global__ void k_ingest(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t rows, uint32_t cols, unsigned log_rows,
-                         int bitrev, int to_mont) {
+                         int bitrev, int to_mont, uint64_t src_pitch) {
     __shared__ uint32_t tile[32][33];
     uint64_t r0 = (uint64_t)blockIdx.x * 32;
     uint32_t c0 = blockIdx.y * 32;
@@ -58,7 +59,7 @@ __global__ void k_ingest(const uint32_t* __restrict__ src, uint32_t* __restrict_
         uint32_t c = c0 + threadIdx.x;
         if (j < rows && c < cols) {
             uint64_t sr = bitrev ? kb::bitrev((uint32_t)j, log_rows) : j;
-            uint32_t v = src[sr * cols + c];
+            uint32_t v = src[sr * src_pitch + c];
             tile[i][threadIdx.x] = to_mont ? kb::to_mont(v) : v;
         }
     }
