@@ -30,16 +30,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 P = 2130706433
-# executed thread-instructions per Poseidon2 permutation in k_leaf_hash: ncu smsp__inst_executed.sum * 32 / permutations
-# (profiles/r1_leaf_hash_final.md)
 # SASS thread-instructions per element of the NTT passes of a 2^22-point column (pass plan g = 8, 7, 7): column-loop bodies of
 # k_pass<0,3,0,0> x2 + k_pass<0,4,1,0> (584 + 584 + 472) / 16 forward, k_pass<1,4,1,0> + k_pass<1,3,0,0> + k_pass<1,3,0,1> (517 + 641 + 857) / 16
 # inverse incl. the fused coset epilogue (cuobjdump -sass, profiles/r1_ntt_instr_counts.txt)
 NTT_INSTR_FWD_2P22 = 102.5
 NTT_INSTR_INV_2P22 = 125.9
-P2_INSTR_PER_PERM = 4606
+# executed thread-instructions per Poseidon2 permutation in k_leaf_hash: ncu smsp__inst_executed.sum * 32 / permutations
+# = 38.01e9 * 32 / 268 435 456 (profiles/r1_leaf_hash_final.md)
+P2_INSTR_PER_PERM = 4531
 # DRAM bytes of one k_leaf_hash launch at the default workload, from the same ncu --set full capture
-LEAF_TRAFFIC_2P22X256 = 8603574000 + 273566720
+LEAF_TRAFFIC_2P22X256 = 8600113000 + 269837312
 
 
 def log(*a):

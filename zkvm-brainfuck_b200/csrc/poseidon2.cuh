@@ -31,15 +31,33 @@ using kb::dbl;
 using kb::mul;
 using kb::sub;
 
+// x * p^{-1} mod 2^32.  p^{-1} = 2^31 + 2^24 + 1, so the product is also x + (x << 24) + (x << 31): two funnel shifts
+// and adds on the ALU pipe instead of one IMAD on the FMA-heavy pipe, which is the busy one here (ncu: fma pipe cycles
+// 45 % of heavy+lite = ~90 % of the IMAD-capable half, ALU 62 %).  Tried (P2_SHIFT_PINV=1) and measured SLOWER, 49.3 vs
+// 46.75 ms per 2^23 x 32 permutations: ptxas answers by moving 60 more plain additions onto the FMA pipe as IMAD.IADD
+// (222 instead of 162 in the round bodies), so the heavy pipe ends up busier, not idler.  Left as a switch.
+#ifndef P2_SHIFT_PINV
+#define P2_SHIFT_PINV 0
+#endif
+KB_D uint32_t mul_pinv(uint32_t x) {
+#if P2_SHIFT_PINV
+    uint32_t m;
+    asm("{\n\t.reg .u32 a, b;\n\tshf.l.wrap.b32 a, 0, %1, 24;\n\tshf.l.wrap.b32 b, 0, %1, 31;\n\tadd.u32 a, a, %1;\n\tadd.u32 %0, a, b;\n\t}" : "=r"(m) : "r"(x));
+    return m;
+#else
+    return x * kb::PINV;
+#endif
+}
+
 // x^3 with one correction instead of two: the square is left in (-p, p) and the second product is a
 // signed Montgomery product (|x2 * x| < p^2 < 2^31 p keeps the result in (-p, p)).
 KB_D uint32_t sbox(uint32_t x) {
     uint64_t t = (uint64_t)x * x;
-    uint32_t m = (uint32_t)t * kb::PINV;
+    uint32_t m = mul_pinv((uint32_t)t);
     uint32_t u = __umulhi(m, kb::P);
     int32_t x2 = (int32_t)((uint32_t)(t >> 32) - u);
     int64_t t2 = (int64_t)x2 * (int32_t)x;
-    int32_t m2 = (int32_t)((uint32_t)t2 * kb::PINV);
+    int32_t m2 = (int32_t)mul_pinv((uint32_t)t2);
     int32_t u2 = __mulhi(m2, (int32_t)kb::P);
     uint32_t r = (uint32_t)((int32_t)(t2 >> 32) - u2);
     return kb::umin_(r, r + kb::P);
@@ -52,11 +70,11 @@ KB_D uint32_t sbox(uint32_t x) {
 KB_D uint32_t sbox_signed(uint32_t xs) {
     int32_t x = (int32_t)xs;
     int64_t t = (int64_t)x * x;  // in [0, p^2]
-    uint32_t m = (uint32_t)t * kb::PINV;
+    uint32_t m = mul_pinv((uint32_t)t);
     uint32_t u = __umulhi(m, kb::P);
     int32_t x2 = (int32_t)((uint32_t)(t >> 32) - u);
     int64_t t2 = (int64_t)x2 * x;
-    int32_t m2 = (int32_t)((uint32_t)t2 * kb::PINV);
+    int32_t m2 = (int32_t)mul_pinv((uint32_t)t2);
     int32_t u2 = __mulhi(m2, (int32_t)kb::P);
     uint32_t r = (uint32_t)((int32_t)(t2 >> 32) - u2);
     return kb::umin_(r, r + kb::P);
