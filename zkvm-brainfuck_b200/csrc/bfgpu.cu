@@ -79,6 +79,7 @@ struct bfgpu_ctx {
     // Measured at 2^22 x 256: 75.3 ms against 71.4 ms for the plain sequence (both kernels want the same two integer pipes;
     // the blocked LDE and the parked sponge states cost more than co-scheduling recovers) => off.
     bool overlap_device = false;
+    int pipe_tail_splits = 1;  // $BFGPU_PIPE_SPLITS
     uint32_t pipe_cols = 64;  // 256-byte row segments per strided copy: 32 was 3 % slower end to end, 128 19 % (fewer stages)
     std::vector<std::pair<void*, uint64_t>> pinned_pool;  // page-locked cycle-record buffers parked between executions (tracegen.cuh)
     uint32_t* d_inv256 = nullptr;  // Montgomery inverses of 0..255 (tracegen.cuh, Jump chip)
@@ -218,6 +219,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (const char* e = getenv("BFGPU_PIPE_COLS")) ctx->pipe_cols = (uint32_t)atoi(e) / 8 * 8;
     if (const char* e = getenv("BFGPU_OVERLAP")) ctx->overlap_device = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_PIPE_SPLITS")) ctx->pipe_tail_splits = atoi(e);
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
 
     // Poseidon2 constant bank (kb31_poseidon2.rs:35-50): internal constants = column 0 of table rows
@@ -1030,9 +1032,10 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
     // slower per byte, so only the tail is split).
     std::vector<uint32_t> start;
     for (uint32_t c = 0; c < W; c += CB) start.push_back(c);
-    {
+    for (int split = 0; split < ctx->pipe_tail_splits; split++) {  // halve the final block (down to 16 columns)
         uint32_t last = start.back(), len = W - last, half = (len / 2 + 7) / 8 * 8;
-        if (len >= 32 && half < len) start.push_back(last + half);
+        if (len < 32 || half >= len) break;
+        start.push_back(last + half);
     }
     start.push_back(W);
     const uint32_t nb = (uint32_t)start.size() - 1;
