@@ -293,6 +293,17 @@ int32_t bfgpu_shard_num_traces(const bfgpu_shard* shard);
 int32_t bfgpu_shard_trace_info(const bfgpu_shard* shard, int32_t i, const char** name, uint64_t* rows, uint64_t* cols);
 int32_t bfgpu_shard_get_trace(const bfgpu_shard* shard, int32_t i, uint32_t* out);
 
+/* ---- native verifier ---------------------------------------------------------------- */
+/* `Verifier::verify_shard` (crates/stark/src/verifier.rs:27-216) on the serialisation of bfgpu_machine_open: replays the
+ * transcript, verifies the PCS opening (input Merkle openings, reduced openings, FRI fold chain, proof of work), checks
+ * C(zeta) = q(zeta) Z_H(zeta) for every chip with the constraint programs over F_p^4, and that the LogUp cumulative sums
+ * cancel.  Host code only: no context, no device.  vk = preprocessed commitment + (chip name, log2 height) of the
+ * preprocessed traces in proving-key order.  Returns BFGPU_OK (accepted) or BFGPU_ERR_INVALID with the reference's
+ * error name (OodEvaluationMismatch:<chip>, InvalidOpeningArgument:..., CumulativeSumsError, ...) in err. */
+int32_t bfgpu_verify_shard(const uint32_t vk_commit[8], const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep,
+                           const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries,
+                           uint32_t pow_bits, char* err, uint64_t err_len);
+
 #ifdef __cplusplus
 }
 #endif

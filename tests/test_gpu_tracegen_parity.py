@@ -116,8 +116,14 @@ def test_fullsize_program_proof_is_accepted_by_the_restated_verifier(ctx, oracle
     bf.lib().bfgpu_pk_observe_into(pk._h, ch._h)
     shard = prover.commit_record(rec)
     assert shard.names[0] == "Cpu" and shard.heights[0] == cpu_rows
-    proof = prover.open(pk, shard, ch.clone())
+    words = prover.open_raw(pk, shard, ch.clone())
+    proof = prover._parse(words, pk, None)
     shard.free()
+    # native verifier (csrc/verifier.h) on the serialised proof, and rejection of a flipped word in the middle
+    assert bf.verify_shard(pk.commit, pk.names, pk.heights, words) is None
+    bad = words.copy()
+    bad[len(bad) // 2] ^= 1
+    assert bf.verify_shard(pk.commit, pk.names, pk.heights, bad) is not None
     chips = importlib.import_module("zkvm-brainfuck_b200.air.chips").machine_chips()
     local_only = dict((c[0], c[4]) for c in prover.chips)
     vk = dict(commit=pk.commit, chip_information=[(n, h.bit_length() - 1, local_only[n]) for n, h in zip(pk.names, pk.heights)])

@@ -85,6 +85,8 @@ ABI = {
     "bfgpu_shard_num_traces": (C.c_int32, [C.c_void_p]),
     "bfgpu_shard_trace_info": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), _u64p, _u64p]),
     "bfgpu_shard_get_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "bfgpu_verify_shard": (C.c_int32, [_u32p, C.POINTER(C.c_char_p), _u32p, C.c_int32, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                           C.c_char_p, C.c_uint64]),
     "bfgpu_dist_commit_begin": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u32p, C.c_int32, C.POINTER(C.c_void_p)]),
     "bfgpu_dist_commit_local_cols": (C.c_uint32, [C.c_void_p, C.c_int32, _u32p]),
     "bfgpu_dist_commit_recv_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),
@@ -532,6 +534,21 @@ def _named_mats(named):
     arr, keep = _mats([v for _, v in named])
     cn = (C.c_char_p * len(names))(*[n.encode() for n in names])
     return cn, arr, keep
+
+
+def verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1, num_queries=84, pow_bits=16, repr=REPR_CANONICAL):
+    """`Verifier::verify_shard` (crates/stark/src/verifier.rs:27-216) in native host code, on the serialised proof of
+    `CudaProver.open_raw` / `prove_program(raw=True)`.  vk = (preprocessed commitment, names and heights of the
+    preprocessed traces in proving-key order: `pk.commit, pk.names, pk.heights`).  Returns None when the proof is
+    accepted, else the reference's error name.  Needs no GPU."""
+    com = _u32(vk_commit)
+    words = _u32(proof_words)
+    names = (C.c_char_p * len(prep_names))(*[n.encode() for n in prep_names])
+    logs = _u32([int(h).bit_length() - 1 for h in prep_heights])
+    err = C.create_string_buffer(256)
+    rc = lib().bfgpu_verify_shard(com.ctypes.data_as(_u32p), names, logs.ctypes.data_as(_u32p), len(prep_names), words.ctypes.data_as(_u32p), words.size,
+                                  repr, log_blowup, num_queries, pow_bits, err, 256)
+    return None if rc == 0 else (err.value.decode() or f"error {rc}")
 
 
 class Record:

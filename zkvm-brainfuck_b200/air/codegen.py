@@ -220,6 +220,108 @@ def generate():
     return "\n".join(hdr) + "\n\n" + body + "\n\n" + "\n".join(disp) + "\n}  // namespace air\n"
 
 
+# ---- host-side extension-field evaluation (verifier) ------------------------------------------------------------------------
+def _ext_affine(em, aff, tag):
+    """Affine form over the LOCAL row with every variable an extension element (values opened at zeta)."""
+    out = None
+    for (kind, idx), w in aff.terms:
+        v = f"R.{kind}0[{idx}]"
+        t = v if w == 1 else f"kb::ext_scale({v}, 0x{mont(w):08x}u)"
+        out = t if out is None else f"kb::ext_add({out}, {t})"
+    if out is None:
+        out = f"kb::ext_from_base(0x{mont(aff.const):08x}u)"
+    elif aff.const:
+        out = f"kb::ext_add({out}, kb::ext_from_base(0x{mont(aff.const):08x}u))"
+    em.emit(f"const kb::Ext a_{tag} = {out};")
+    return f"a_{tag}"
+
+
+def gen_chip_ext(chip, index):
+    """`Chip::eval` on a `VerifierConstraintFolder` (crates/stark/src/folder.rs:125-230, verifier.rs:242-292): the same
+    constraint program as the quotient kernel, with every trace value an element of F_p^4 (the opened values)."""
+    name = chip.name
+    n_base = len(chip.constraints)
+    total = n_base + (chip.perm_width - 1) + 3
+    em = Emitter()
+    names = {}
+    for n in topo_order(list(chip.constraints)):
+        if n._id in names:
+            continue
+        if n.op == "const":
+            names[n._id] = f"kb::ext_from_base(0x{mont(n.args[0]):08x}u)"
+        elif n.op == "var":
+            kind, off, idx = n.args
+            names[n._id] = f"R.{kind}{off}[{idx}]"
+        elif n.op == "sel":
+            names[n._id] = {"is_first_row": "R.is_first", "is_last_row": "R.is_last", "is_transition": "R.is_trans"}[n.args[0]]
+        else:
+            a, b = names[n.args[0]._id], names[n.args[1]._id]
+            em.emit(f"const kb::Ext t{n._id} = kb::ext_{n.op}({a}, {b});")
+            names[n._id] = f"t{n._id}"
+    for k, c in enumerate(chip.constraints):
+        em.emit(f"acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 1 - k}], {names[c._id]}));")
+    lookups = chip.lookups
+    for j in range(chip.perm_width - 1):
+        chunk = lookups[j * chip.batch_size:(j + 1) * chip.batch_size]
+        rl = []
+        for i, (lk, is_send) in enumerate(chunk):
+            tag = f"{j}_{i}"
+            em.emit(f"kb::Ext rlc_{tag} = ch.alpha;")
+            em.emit(f"rlc_{tag}.c[0] = kb::add(rlc_{tag}.c[0], 0x{mont(lk.kind):08x}u);")
+            for k, v in enumerate(lk.values):
+                if not v.terms and not v.const:
+                    continue
+                val = _ext_affine(em, v, f"{tag}_{k}")
+                em.emit(f"rlc_{tag} = kb::ext_add(rlc_{tag}, kb::ext_mul(ch.beta_pow[{k + 1}], {val}));")
+            m = _ext_affine(em, lk.multiplicity, f"{tag}_m")
+            rl.append((f"rlc_{tag}", m, is_send))
+        em.emit("{")
+        em.emit("    kb::Ext prod = " + rl[0][0] + ";")
+        for r, _, _ in rl[1:]:
+            em.emit(f"    prod = kb::ext_mul(prod, {r});")
+        em.emit("    kb::Ext num = kb::ext_zero();")
+        for i, (r, m, is_send) in enumerate(rl):
+            others = [x[0] for k, x in enumerate(rl) if k != i]
+            term = m
+            for x in others:
+                term = f"kb::ext_mul({term}, {x})"
+            em.emit(f"    num = kb::ext_{'add' if is_send else 'sub'}(num, {term});")
+        em.emit(f"    kb::Ext cst = kb::ext_sub(kb::ext_mul(prod, R.perm0[{j}]), num);")
+        em.emit(f"    acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 1 - (n_base + j)}], cst));")
+        em.emit("}")
+    W = chip.perm_width
+    em.emit("{")
+    em.emit("    kb::Ext sum_local = kb::ext_zero(), sum_next = kb::ext_zero();")
+    for j in range(W - 1):
+        em.emit(f"    sum_local = kb::ext_add(sum_local, R.perm0[{j}]);")
+        em.emit(f"    sum_next = kb::ext_add(sum_next, R.perm1[{j}]);")
+    em.emit(f"    const kb::Ext phi_local = R.perm0[{W - 1}], phi_next = R.perm1[{W - 1}];")
+    k0 = n_base + W - 1
+    em.emit(f"    acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 1 - k0}], kb::ext_mul(kb::ext_sub(phi_local, sum_local), R.is_first)));")
+    em.emit(f"    acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 2 - k0}], kb::ext_mul(kb::ext_sub(kb::ext_sub(phi_next, phi_local), sum_next), R.is_trans)));")
+    em.emit(f"    acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 3 - k0}], kb::ext_mul(kb::ext_sub(phi_local, ch.cumulative_sum), R.is_last)));")
+    em.emit("}")
+    out = [f"// ---- {name}", f"inline void air_constraints_ext_{name}(const ExtRow& R, const Challenges& ch, const kb::Ext* apow, kb::Ext& acc) {{"]
+    out += em.lines
+    out.append("}")
+    return "\n".join(out)
+
+
+def generate_ext():
+    chips = C.machine_chips()
+    hdr = ["// GENERATED by zkvm-brainfuck_b200/air/codegen.py from air/chips.py — do not edit.",
+           "// Host-side constraint programs over F_p^4 for the native verifier (csrc/verifier.h): `Chip::eval` on the",
+           "// reference's VerifierConstraintFolder (crates/stark/src/folder.rs:125-230).", "#pragma once", "namespace air {",
+           "struct ExtRow {  // opened values of one chip at zeta (0) and zeta * g (1), plus the selectors at zeta",
+           "    const kb::Ext *main0, *main1, *prep0, *prep1, *perm0, *perm1;", "    kb::Ext is_first, is_last, is_trans;", "};"]
+    body = "\n\n".join(gen_chip_ext(c, i) for i, c in enumerate(chips))
+    disp = ["inline void air_constraints_ext(int chip, const ExtRow& R, const Challenges& ch, const kb::Ext* apow, kb::Ext& acc) {", "    switch (chip) {"]
+    for i, c in enumerate(chips):
+        disp.append(f"        case {i}: air_constraints_ext_{c.name}(R, ch, apow, acc); break;")
+    disp.append("    }\n}")
+    return "\n".join(hdr) + "\n\n" + body + "\n\n" + "\n".join(disp) + "\n}  // namespace air\n"
+
+
 def generate_layout():
     """csrc/gen_layout.cuh: column indices of every chip's main trace (first index for multi-column fields) for the
     device-side trace generators (csrc/tracegen.cuh)."""
@@ -244,6 +346,8 @@ def generate_layout():
 def main():
     with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "gen_layout.cuh"), "w") as f:
         f.write(generate_layout())
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "gen_air_ext.h"), "w") as f:
+        f.write(generate_ext())
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "gen_air.cuh")
     src = generate()
     with open(out, "w") as f:

@@ -24,6 +24,7 @@
 #include "kernels_ntt.cuh"
 #include "kernels_ntt2.cuh"
 #include <array>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <set>
@@ -2034,3 +2035,8 @@ extern "C" int32_t bfgpu_machine_chip_info(int32_t i, const char** name, int32_t
 // native executor + device-side trace generation
 // =====================================================================================================
 #include "tracegen.cuh"
+
+// =====================================================================================================
+// native verifier (host only)
+// =====================================================================================================
+#include "verifier.h"
