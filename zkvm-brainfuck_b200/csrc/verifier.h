@@ -6,7 +6,7 @@
 // (commit-phase replay, proof of work, per-query input openings, fold chain) and `MerkleTreeMmcs::verify_batch`.
 // a Rust-free verifier so that proofs of both backends can be checked without the reference
 // toolchain.  The constraint programs over F_p^4 come from gen_air_ext.h (same declarative AIR as the prover kernels).
-// Checked against the oracle's verifier (accept / reject verdicts) in tests/test_native_verifier.py.
+// Verdict parity (accept / reject, error names) with the CPU restatement is checked in tests/test_native_verifier.py.
 #pragma once
 #include <cstdarg>
 #include <map>
