@@ -138,3 +138,21 @@ def test_fullsize_program_proof_is_accepted_by_the_restated_verifier(ctx, oracle
     assert S.e_eq(total, S.E_ZERO)
     pk.free()
     rec.free()
+
+
+def test_e2e_core_through_the_sdk_facade():
+    """The reference's own end-to-end test (`test_e2e_core`, crates/sdk/src/lib.rs:185-196) with this backend behind the
+    same calls: setup, prove fibo(17), check the output 85, verify; a proof for another stdin must not verify under a
+    tampered statement."""
+    client = bf.ProverClient()
+    code = _code("fibo.bf")
+    assert client.execute(code, [17]).run() == [85]
+    pk, vk = client.setup(code)
+    proof = client.prove(pk, [17]).run()
+    assert proof.output == [85] and proof.stdin == [17]
+    assert client.verify(proof, vk) is None
+    proof.words[40] ^= 1
+    assert client.verify(proof, vk) is not None
+    other_pk, other_vk = client.setup(_code("hello.bf"))
+    proof = client.prove(pk, [17]).run()
+    assert client.verify(proof, other_vk) is not None  # verifying key of a different program

@@ -812,3 +812,83 @@ class CudaProver:
             chips_out.append(dict(preprocessed=prep, main=lv(main_v[i], not lo), permutation=lv(perm_v[i], True),
                                   quotient=[quot_v[2 * i][0], quot_v[2 * i + 1][0]], cumulative_sum=csum, log_degree=log_degree))
         return dict(commitment=com, opened_values=chips_out, opening_proof=fri, chip_ordering={k: i for i, k in enumerate(names)})
+
+
+# ---- sdk façade -----------------------------------------------------------------------------------------------------------
+class _Action:
+    def __init__(self, fn):
+        self._fn = fn
+
+    def run(self):
+        return self._fn()
+
+
+class ProofWithPublicValues:
+    """`BfProofWithPublicValues` (crates/sdk/src/proof.rs:10-13): the shard proof (serialised words; `.decode()` gives the
+    nested form) and the stdin it was produced for; `output` is what the program wrote."""
+
+    def __init__(self, words, decode, stdin, output):
+        self.words, self._decode, self.stdin, self.output = words, decode, list(stdin), list(output)
+
+    def decode(self):
+        return self._decode()
+
+
+class ProverClient:
+    """`bf_sdk::ProverClient` (crates/sdk/src/lib.rs:19-140) on this backend, same call shapes:
+        client = ProverClient(); pk, vk = client.setup(code); proof = client.prove(pk, [17]).run(); client.verify(proof, vk)
+    `execute(code, stdin).run()` returns the program's output.  setup / prove need a GPU; execute and verify do not."""
+
+    def __init__(self, device=0):
+        self._device, self._ctx, self._prover = device, None, None
+
+    def _gpu(self):
+        if self._prover is None:
+            self._ctx = Context(self._device)
+            self._prover = CudaProver(self._ctx)
+        return self._prover
+
+    def execute(self, code, stdin=()):
+        return _Action(lambda: Record(code, stdin).output)
+
+    def setup(self, code):
+        prover = self._gpu()
+        pk = prover.setup_record(_ProgramOnly(code))
+        pk.code = code
+        vk = dict(commit=pk.commit.copy(), names=list(pk.names), heights=list(pk.heights))
+        return pk, vk
+
+    def prove(self, pk, stdin=()):
+        def run():
+            (words, decode), rec = self._gpu().prove_program(pk.code, stdin, pk=pk, raw=True)
+            return ProofWithPublicValues(words, decode, stdin, rec.output)
+        return _Action(run)
+
+    def verify(self, proof, vk, log_blowup=1, num_queries=None, pow_bits=16):
+        """Returns None when accepted, else the reference's error name (`BfVerificationError`)."""
+        if num_queries is None:
+            num_queries = int(os.environ.get("FRI_QUERIES", 84))  # kb31_poseidon2.rs:59-62
+        return verify_shard(vk["commit"], vk["names"], vk["heights"], proof.words, log_blowup, num_queries, pow_bits)
+
+
+class _ProgramOnly:
+    """Handle for `bfgpu_machine_setup_record` built from the program text alone (no execution)."""
+
+    def __init__(self, code):
+        self._h = C.c_void_p()
+        rc = lib().bfgpu_execute(None, code.encode(), None, 0, 1, C.byref(self._h))
+        # a one-cycle budget: programs longer than one cycle stop with "cycle limit"; the compiled program is kept either way
+        if rc != 0:
+            msg = lib().bfgpu_record_error(self._h).decode() if self._h else ""
+            if "cycle limit" not in msg and "stdin" not in msg:
+                lib().bfgpu_record_free(self._h)
+                self._h = None
+                raise BfGpuError(f"program does not compile: {msg}")
+        c = (C.c_uint64 * 8)()
+        lib().bfgpu_record_info(self._h, c)
+        self.n_instr = int(c[1])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().bfgpu_record_free(self._h)
+            self._h = None
