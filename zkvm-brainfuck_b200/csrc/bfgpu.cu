@@ -204,6 +204,21 @@ static void dfree(bfgpu_ctx* ctx, void* p) {
     ctx->cached_bytes += bytes;
 }
 
+// Scratch device buffers of one entry point: returned to the block cache on every exit path.
+struct Scratch {
+    bfgpu_ctx* ctx;
+    std::vector<void*> bufs;
+    explicit Scratch(bfgpu_ctx* c) : ctx(c) {}
+    int32_t alloc(void** p, size_t bytes) {
+        int32_t rc = dalloc(ctx, p, bytes);
+        if (rc == BFGPU_OK) bufs.push_back(*p);
+        return rc;
+    }
+    ~Scratch() {
+        for (void* p : bufs) dfree(ctx, p);
+    }
+};
+
 // ---- context ----------------------------------------------------------------------------------
 extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (!out) return BFGPU_ERR_INVALID;

@@ -278,7 +278,7 @@ using namespace lay;
 __device__ __forceinline__ uint32_t M(uint32_t v) { return kb::mul(v, kb::R2); }  // any 32-bit value -> Montgomery form of v mod p
 
 struct Dec {
-    uint32_t op, arg, pc, next_pc, mp, next_mp, mv, pv, next_mv, pt, clk;
+    uint32_t op, pc, next_pc, mp, next_mp, mv, pv, next_mv, pt, clk;
     bool acc, nacc;
 };
 __device__ __forceinline__ Dec decode(const uint4* __restrict__ cyc, const uint8_t* __restrict__ ops, uint32_t i) {
@@ -297,7 +297,6 @@ __device__ __forceinline__ Dec decode(const uint4* __restrict__ cyc, const uint8
     d.pv = mem ? 0u : ((c.w >> 8) & 0xFFu);
     d.nacc = d.op == OP_ADD || d.op == OP_SUB;
     d.next_mv = d.op == OP_ADD ? ((d.mv + 1) & 0xFFu) : d.op == OP_SUB ? ((d.mv - 1) & 0xFFu) : 0u;
-    d.arg = 0;
     return d;
 }
 
@@ -539,17 +538,18 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
     const uint32_t n = (uint32_t)rec->n_cycles, n_instr = (uint32_t)rec->ops.size(), n_cells = (uint32_t)(rec->mem_events.size() / 5);
     if (n == 0) return fail(ctx, BFGPU_ERR_INVALID, "empty execution");
     // ---- inputs to the device ----
+    Scratch scratch(ctx);  // inputs and index lists: back to the block cache on every exit path
     uint4 *d_cyc = nullptr, *d_flags = nullptr;
     uint8_t* d_ops = nullptr;
     uint32_t *d_args = nullptr, *d_counts = nullptr, *d_mem = nullptr, *d_idx = nullptr, *d_inv = nullptr;
     unsigned int* d_hist = nullptr;
     {
         Phase ph(ctx, BFGPU_PHASE_H2D);
-        TRY(dalloc(ctx, (void**)&d_cyc, (size_t)(n + 1) * 16));
-        TRY(dalloc(ctx, (void**)&d_ops, n_instr));
-        TRY(dalloc(ctx, (void**)&d_args, (size_t)n_instr * 4));
-        TRY(dalloc(ctx, (void**)&d_counts, (size_t)n_instr * 4));
-        TRY(dalloc(ctx, (void**)&d_mem, std::max<size_t>(rec->mem_events.size(), 1) * 4));
+        TRY(scratch.alloc((void**)&d_cyc, (size_t)(n + 1) * 16));
+        TRY(scratch.alloc((void**)&d_ops, n_instr));
+        TRY(scratch.alloc((void**)&d_args, (size_t)n_instr * 4));
+        TRY(scratch.alloc((void**)&d_counts, (size_t)n_instr * 4));
+        TRY(scratch.alloc((void**)&d_mem, std::max<size_t>(rec->mem_events.size(), 1) * 4));
         CU(cudaMemcpyAsync(d_cyc, rec->cycles, (size_t)(n + 1) * 16, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(d_ops, rec->ops.data(), n_instr, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(d_args, rec->args.data(), (size_t)n_instr * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -561,8 +561,8 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
     const uint64_t ne[4] = {rec->n_alu, rec->n_jump, rec->n_mem, rec->n_io};
     uint64_t off[5] = {0, 0, 0, 0, 0};
     for (int k = 0; k < 4; k++) off[k + 1] = off[k] + ne[k];
-    TRY(dalloc(ctx, (void**)&d_flags, (size_t)n * 16));
-    TRY(dalloc(ctx, (void**)&d_idx, std::max<uint64_t>(off[4], 1) * 4));
+    TRY(scratch.alloc((void**)&d_flags, (size_t)n * 16));
+    TRY(scratch.alloc((void**)&d_idx, std::max<uint64_t>(off[4], 1) * 4));
     const unsigned gb = (n + 255) / 256;
     tg::k_classify<<<gb, 256, 0, ctx->stream>>>(d_cyc, d_ops, n, d_flags);
     LAUNCHED(ctx);
@@ -570,7 +570,7 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
     tg::k_index<<<gb, 256, 0, ctx->stream>>>(d_cyc, d_ops, d_flags, n, d_idx + off[0], d_idx + off[1], d_idx + off[2], d_idx + off[3]);
     LAUNCHED(ctx);
     // ---- byte multiplicities ----
-    TRY(dalloc(ctx, (void**)&d_hist, (256 + 65536) * 4));
+    TRY(scratch.alloc((void**)&d_hist, (256 + 65536) * 4));
     CU(cudaMemsetAsync(d_hist, 0, (256 + 65536) * 4, ctx->stream));
     tg::k_byte_hist<<<std::min(gb, 148u * 8u), tg::HIST_THREADS, 0, ctx->stream>>>(d_cyc, d_ops, n, d_hist, d_hist + 256);
     LAUNCHED(ctx);
@@ -583,7 +583,6 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
     }
     d_inv = ctx->d_inv256;
     // ---- traces, straight into the prover's layout ----
-    struct Gen { const char* name; uint64_t rows; };
     std::vector<std::string> names;
     std::vector<DMat> traces;
     auto new_trace = [&](const char* name, uint64_t rows, DMat* m) -> int32_t {
@@ -592,9 +591,9 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
         m->cols = (uint32_t)air::CHIPS[ci].main_w;
         m->rs = 1;
         TRY(dalloc(ctx, (void**)&m->d, rows * m->cols * 4));
-        CU(cudaMemsetAsync(m->d, 0, rows * m->cols * 4, ctx->stream));
         names.push_back(name);
-        traces.push_back(*m);
+        traces.push_back(*m);  // owned by `traces` from here on (released on the error path below)
+        CU(cudaMemsetAsync(m->d, 0, rows * m->cols * 4, ctx->stream));
         return BFGPU_OK;
     };
     auto blocks = [](uint64_t rows) { return (unsigned)((rows + 255) / 256); };
@@ -638,7 +637,6 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
         if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, BFGPU_ERR_CUDA, "trace generation kernels failed to launch");
     } while (0);
     ph_gen.reset();  // the commit below is accounted under its own phases
-    for (void* p : {(void*)d_cyc, (void*)d_flags, (void*)d_ops, (void*)d_args, (void*)d_counts, (void*)d_mem, (void*)d_idx, (void*)d_hist}) dfree(ctx, p);
     if (rc != BFGPU_OK) {
         for (DMat& t : traces) dfree(ctx, t.d);
         return rc;
