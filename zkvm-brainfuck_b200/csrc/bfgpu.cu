@@ -79,6 +79,7 @@ struct bfgpu_ctx {
     // device-resident single-matrix commits: leaf sponge of block b concurrent with the NTT of block b+1 ($BFGPU_OVERLAP=1).
     // Measured at 2^22 x 256: 75.3 ms against 71.4 ms for the plain sequence (both kernels want the same two integer pipes;
     // the blocked LDE and the parked sponge states cost more than co-scheduling recovers) => off.
+    bool fri_tail = true;  // small FRI rounds in one single-CTA launch (openk::k_fri_tail); $BFGPU_FRI_TAIL=0 disables
     bool overlap_device = false;
     int pipe_tail_splits = 1;  // $BFGPU_PIPE_SPLITS
     uint32_t pipe_cols = 64;  // 256-byte row segments per strided copy: 32 was 3 % slower end to end, 128 19 % (fewer stages)
@@ -235,6 +236,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (const char* e = getenv("BFGPU_PIPE_COLS")) ctx->pipe_cols = (uint32_t)atoi(e) / 8 * 8;
     if (const char* e = getenv("BFGPU_OVERLAP")) ctx->overlap_device = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_FRI_TAIL")) ctx->fri_tail = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_PIPE_SPLITS")) ctx->pipe_tail_splits = atoi(e);
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
 
@@ -1509,6 +1511,74 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
         ++it;
         std::vector<std::array<uint32_t, 8>> commits;
         while (len > (1ull << log_blowup)) {
+            if (ctx->fri_tail && len <= (1ull << openk::TAIL_MAX_LOG) && ilog2(len) - log_blowup <= (unsigned)openk::TAIL_MAX_ROUNDS) {
+                // ---- all remaining rounds in one single-CTA launch (openk::k_fri_tail) ----
+                openk::FriTailArgs ta;
+                memset(&ta, 0, sizeof ta);
+                ta.log_len = ilog2(len);
+                ta.nrounds = ta.log_len - log_blowup;
+                ta.tw = ctx->d_tw;
+                memcpy(ta.ch_state, ch.state, sizeof ta.ch_state);
+                ta.ch_nin = (uint32_t)ch.input.size();
+                for (size_t k = 0; k < ch.input.size(); k++) ta.ch_in[k] = ch.input[k];
+                uint32_t* d_roots = nullptr;
+                TRY(dalloc(ctx, (void**)&d_roots, ta.nrounds * 32));
+                ta.roots = d_roots;
+                ta.vec[0] = folded;
+                int32_t rc = BFGPU_OK;
+                const size_t first_tail_layer = layers.size();
+                for (uint32_t r = 0; r < ta.nrounds && rc == BFGPU_OK; r++) {
+                    const uint64_t nleaves = len >> (r + 1);
+                    bfgpu_tree* t = new bfgpu_tree();
+                    t->ctx = ctx;
+                    DMat leaves;
+                    leaves.d = ta.vec[r];
+                    leaves.rows = nleaves;
+                    leaves.cols = 8;
+                    leaves.rs = 8;
+                    t->mats.push_back(leaves);
+                    t->log_max = ilog2(nleaves);
+                    layers.push_back({ta.vec[r], len >> r, t});
+                    for (unsigned l = 0; l <= t->log_max && rc == BFGPU_OK; l++) {
+                        uint32_t* lay = nullptr;
+                        rc = dalloc(ctx, (void**)&lay, (nleaves >> l) * 32);
+                        t->layers.push_back(lay);
+                        t->layer_len.push_back(nleaves >> l);
+                        ta.layer[r][l] = lay;
+                    }
+                    if (rc == BFGPU_OK) rc = dalloc(ctx, (void**)&ta.vec[r + 1], nleaves * 16);
+                    if (it != reduced.end() && (1ull << it->first) == nleaves) {
+                        ta.add[r] = it->second;
+                        ++it;
+                    }
+                }
+                if (rc != BFGPU_OK) { dfree(ctx, d_roots); release_layers(); return rc; }
+                openk::k_fri_tail<<<1, openk::TAIL_THREADS, 0, ctx->stream>>>(ta);
+                LAUNCHED(ctx);
+                CU(cudaGetLastError());
+                for (uint32_t r = 0; r < ta.nrounds; r++)  // the reduced openings consumed by the tail (stream order keeps them alive)
+                    if (ta.add[r])
+                        for (auto& kv : reduced)
+                            if (kv.second == ta.add[r]) {
+                                dfree(ctx, kv.second);
+                                kv.second = nullptr;
+                            }
+                std::vector<uint32_t> roots(ta.nrounds * 8);
+                CU(cudaMemcpyAsync(roots.data(), d_roots, roots.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                dfree(ctx, d_roots);
+                for (uint32_t r = 0; r < ta.nrounds; r++) {  // advance the host transcript exactly as the kernel did
+                    std::array<uint32_t, 8> root;
+                    memcpy(root.data(), &roots[8 * r], 32);
+                    ch.observe_slice(root.data(), 8);
+                    commits.push_back(root);
+                    (void)ch.sample_ext();
+                }
+                (void)first_tail_layer;
+                folded = ta.vec[ta.nrounds];
+                len = 1ull << log_blowup;
+                break;
+            }
             DMat leaves;
             leaves.d = folded;
             leaves.rows = len / 2;

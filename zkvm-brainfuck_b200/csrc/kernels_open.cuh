@@ -160,10 +160,8 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
 }
 
 // ---- FRI fold: out[i] = (1/2 + b g^-br(i)) in[2i] + (1/2 - b g^-br(i)) in[2i+1] (+ add[i]),  b = beta/2 -----
-__global__ void k_fri_fold(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h /* out length */,
-                           Ext half_beta, const uint32_t* __restrict__ tw) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (1u << log_h)) return;
+__device__ __forceinline__ void fri_fold_one(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h,
+                                             Ext half_beta, const uint32_t* __restrict__ tw, uint32_t i) {
     // g = generator of order 2^(log_h+1); g^-j = w^(2^(log_h+1) - j)
     uint32_t j = kb::bitrev(i, log_h);
     uint32_t ginv = j ? root_pow(tw, log_h + 1, (1u << (log_h + 1)) - j) : kb::ONE;
@@ -176,6 +174,161 @@ __global__ void k_fri_fold(const uint32_t* __restrict__ in, uint32_t* __restrict
     Ext o = kb::ext_add(kb::ext_mul(a, lo), kb::ext_mul(b, hi));
     if (add) o = kb::ext_add(o, ld_ext(add + 4 * (uint64_t)i));
     st_ext(out + 4 * (uint64_t)i, o);
+}
+__global__ void k_fri_fold(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h /* out length */,
+                           Ext half_beta, const uint32_t* __restrict__ tw) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << log_h)) return;
+    fri_fold_one(in, out, add, log_h, half_beta, tw, i);
+}
+
+// ---- FRI tail: every commit-phase round whose input has at most 2^TAIL_MAX_LOG elements, in ONE single-CTA launch -----
+// Per round the host path costs three launches (fold, leaf hash, tree top), a 32-byte device->host copy, a stream
+// synchronisation and the host sponge — ~60 us of latency for microseconds of work, ten times per proof.  Here one CTA
+// runs the rounds back to back: leaf digests and tree levels as in hashk::k_compress_top (four-lane permutation below
+// 256 nodes), then warp 0 plays the DuplexChallenger (observe the root, sample beta: same buffer logic as
+// challenger.h, state handed in by the host), then the fold.  All layers, folded vectors and roots go to global memory
+// in the layout the query phase reads; the host replays the roots through its own challenger to advance it.
+constexpr int TAIL_MAX_LOG = 11, TAIL_THREADS = 1024, TAIL_MAX_ROUNDS = 11;
+struct FriTailArgs {
+    uint32_t* vec[TAIL_MAX_ROUNDS + 1];              // vec[r]: input of round r, 2^(log_len - r) elements; vec[nrounds]: final vector
+    const uint32_t* add[TAIL_MAX_ROUNDS];            // reduced opening added to the output of round r, or null
+    uint32_t* layer[TAIL_MAX_ROUNDS][TAIL_MAX_LOG];  // layer[r][l]: 2^(log_len - r - 1 - l) digests, l = 0 .. log_len - r - 1
+    uint32_t* roots;                                 // nrounds x 8
+    uint32_t log_len, nrounds;
+    uint32_t ch_state[16], ch_in[8], ch_nin;         // challenger at entry (its output buffer is dead: the next operation is an observe)
+    const uint32_t* tw;
+};
+__global__ void __launch_bounds__(TAIL_THREADS) k_fri_tail(FriTailArgs A) {
+    __shared__ __align__(16) uint32_t cur[(1 << (TAIL_MAX_LOG - 1)) * 8];
+    __shared__ uint32_t s_ext[8 * 16], s_int[16], ch_st[16], ch_in[8];
+    __shared__ __align__(16) uint32_t s_beta[4];
+    const uint32_t t = threadIdx.x;
+    const int q = t & 3, lane = t & 31;
+    if (t < 128) s_ext[t] = p2::c_p2.ext_s[t >> 4][t & 15];
+    if (t < 16) {
+        s_int[t] = p2::c_p2.internal_s[t];
+        ch_st[t] = A.ch_state[t];
+    }
+    if (t < 8) ch_in[t] = A.ch_in[t];
+    __syncthreads();
+    const p2::X4 xc = p2::x4_setup(s_ext, s_int, q);
+    uint32_t n_in = A.ch_nin, n_out = 0;  // replicated in every lane of warp 0
+    auto duplex = [&]() {                 // warp 0 only, all 32 lanes
+        if ((uint32_t)lane < n_in) ch_st[lane] = ch_in[lane];
+        __syncwarp();
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = ch_st[4 * q + j];
+        p2::permute_x4(w, xc, q);
+        __syncwarp();
+        if (lane < 4) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ch_st[4 * lane + j] = w[j];
+        }
+        __syncwarp();
+        n_in = 0;
+        n_out = 8;
+    };
+    for (uint32_t r = 0; r < A.nrounds; r++) {
+        const unsigned log_n = A.log_len - r - 1;  // leaves of this round = output length of its fold
+        const uint32_t n = 1u << log_n;
+        const uint32_t* vin = A.vec[r];
+        // ---- leaf digests: sponge of the 8-word row (in[2i], in[2i+1]) = one permutation of (row | 0^8) -------------------
+        if (4 * n <= (uint32_t)TAIL_THREADS) {
+            const uint32_t i = t >> 2;
+            const bool warp_on = ((t & ~31u) >> 2) < n, on = i < n;
+            if (warp_on) {
+                uint32_t w[4] = {0, 0, 0, 0};
+                if (on && q < 2) {
+                    uint4 x = *reinterpret_cast<const uint4*>(vin + 8 * i + 4 * q);
+                    w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+                }
+                p2::permute_x4(w, xc, q);
+                if (on && q < 2) {
+                    uint4 o = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(A.layer[r][0] + 8 * i + 4 * q) = o;
+                    *reinterpret_cast<uint4*>(cur + 8 * i + 4 * q) = o;
+                }
+            }
+        } else {
+            for (uint32_t i = t; i < n; i += TAIL_THREADS) {  // at most one iteration (n <= 1024)
+                uint32_t s[16];
+                uint4 x0 = *reinterpret_cast<const uint4*>(vin + 8 * i), x1 = *reinterpret_cast<const uint4*>(vin + 8 * i + 4);
+                s[0] = x0.x; s[1] = x0.y; s[2] = x0.z; s[3] = x0.w; s[4] = x1.x; s[5] = x1.y; s[6] = x1.z; s[7] = x1.w;
+#pragma unroll
+                for (int k = 8; k < 16; k++) s[k] = 0;
+                p2::permute(s);
+                hashk::store_digest(A.layer[r][0] + 8 * i, s);
+#pragma unroll
+                for (int k = 0; k < 8; k++) cur[8 * i + k] = s[k];
+            }
+        }
+        __syncthreads();
+        // ---- tree levels ------------------------------------------------------------------------------------------------
+        for (unsigned l = 1; l <= log_n; l++) {
+            const uint32_t m = n >> l;
+            if (4 * m <= (uint32_t)TAIL_THREADS) {
+                const uint32_t i = t >> 2;
+                const bool warp_on = ((t & ~31u) >> 2) < m, on = i < m;
+                uint32_t w[4] = {0, 0, 0, 0};
+                if (on) {
+                    uint4 x = *reinterpret_cast<const uint4*>(cur + 16 * i + 4 * q);
+                    w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+                }
+                __syncthreads();
+                if (warp_on) {
+                    p2::permute_x4(w, xc, q);
+                    if (on && q < 2) {
+                        uint4 o = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(A.layer[r][l] + 8 * i + 4 * q) = o;
+                        *reinterpret_cast<uint4*>(cur + 8 * i + 4 * q) = o;
+                    }
+                }
+            } else {
+                uint32_t s[16];
+                const uint32_t i = t;  // m <= 512 here
+                if (i < m) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) s[k] = cur[16 * i + k];
+                }
+                __syncthreads();
+                if (i < m) {
+                    p2::permute(s);
+                    hashk::store_digest(A.layer[r][l] + 8 * i, s);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cur[8 * i + k] = s[k];
+                }
+            }
+            __syncthreads();
+        }
+        // ---- Fiat-Shamir: observe the root, sample beta (DuplexChallenger<_, _, 16, 8>) -----------------------------------------
+        if (t < 32) {
+            for (int k = 0; k < 8; k++) {  // observe: clears the output buffer, duplexes when the rate is full
+                n_out = 0;
+                if (lane == 0) ch_in[n_in] = cur[k];
+                n_in++;
+                __syncwarp();
+                if (n_in == 8) duplex();
+            }
+            uint32_t beta[4];
+            for (int k = 0; k < 4; k++) {  // sample: duplex first if anything was observed since, pop from the back
+                if (n_in != 0 || n_out == 0) duplex();
+                beta[k] = ch_st[--n_out];
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) s_beta[k] = beta[k];
+#pragma unroll
+                for (int k = 0; k < 8; k++) A.roots[8 * r + k] = cur[k];
+            }
+        }
+        __syncthreads();
+        // ---- fold -------------------------------------------------------------------------------------------------------------
+        const Ext half_beta = kb::ext_scale(Ext{{s_beta[0], s_beta[1], s_beta[2], s_beta[3]}}, kb::halve(kb::ONE));
+        for (uint32_t i = t; i < n; i += TAIL_THREADS) fri_fold_one(vin, A.vec[r + 1], A.add[r], log_n, half_beta, A.tw, i);
+        __syncthreads();  // the next round reads vec[r + 1] (same CTA: block-level visibility suffices)
+    }
 }
 
 // ---- proof of work: smallest w in [start, start+count) with (permute(state | w at pos)[7] & mask) == 0 ------
