@@ -1663,59 +1663,49 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
         flat.push_back(witness);
     }
 
-    // ---- (v) queries: every opened word is gathered by one kernel ---------------------------------------------
+    // ---- (v) queries: one descriptor template, one kernel (openk::k_answer_queries) -------------------------------------
     {
         Phase ph(ctx, BFGPU_PHASE_QUERY);
         flat.push_back(ctx->num_queries);
-        std::vector<const uint32_t*> src;
-        std::vector<std::pair<size_t, uint32_t>> index_slots;  // position in flat of each query's index (already written)
-        size_t base = flat.size();
-        std::vector<uint32_t> indices(ctx->num_queries);
-        // first pass: lay out the pointer list in serialisation order, reserving one slot per index word
-        for (uint32_t q = 0; q < ctx->num_queries; q++) {
-            uint32_t index = ch.sample_bits(log_max_height);
-            indices[q] = index;
-            src.push_back(nullptr);  // placeholder for the index word
-            for (int r = 0; r < n_rounds; r++) {
-                const bfgpu_tree* t = rounds[r].data->tree;
-                uint64_t ridx = index >> (log_global_max - t->log_max);
-                for (const DMat& m : t->mats) {
-                    uint64_t row = ridx >> (t->log_max - ilog2(m.rows));
-                    for (uint32_t c = 0; c < m.cols; c++) src.push_back(m.d + (uint64_t)c * m.col_stride() + row * m.rs);
-                }
-                for (unsigned l = 0; l < t->log_max; l++)
-                    for (int k = 0; k < 8; k++) src.push_back(t->layers[l] + 8 * ((ridx >> l) ^ 1) + k);
-            }
-            for (size_t i = 0; i < layers.size(); i++) {
-                uint64_t idx_i = index >> i, pair = idx_i >> 1;
-                for (int k = 0; k < 4; k++) src.push_back(layers[i].vec + 8 * pair + 4 * ((idx_i ^ 1) & 1) + k);
-                const bfgpu_tree* t = layers[i].tree;
-                for (unsigned l = 0; l < t->log_max; l++)
-                    for (int k = 0; k < 8; k++) src.push_back(t->layers[l] + 8 * ((pair >> l) ^ 1) + k);
-            }
+        std::vector<openk::QueryWord> tmpl;
+        tmpl.push_back({nullptr, 0, 0, 0, 0});  // the query index
+        for (int r = 0; r < n_rounds; r++) {
+            const bfgpu_tree* t = rounds[r].data->tree;
+            const uint32_t down = log_global_max - t->log_max;  // ridx = index >> down
+            for (const DMat& m : t->mats)
+                for (uint32_t c = 0; c < m.cols; c++)
+                    tmpl.push_back({m.d + (uint64_t)c * m.col_stride(), m.rs, log_global_max - ilog2(m.rows), 0, 0});
+            for (unsigned l = 0; l < t->log_max; l++)
+                for (uint32_t k = 0; k < 8; k++) tmpl.push_back({t->layers[l] + k, 8, down + l, 1, 0});
         }
-        // placeholders point at a device word holding zero; the index words are patched on the host
-        uint32_t* d_zero = nullptr;
-        TRY(dalloc(ctx, (void**)&d_zero, 4));
-        CU(cudaMemsetAsync(d_zero, 0, 4, ctx->stream));
-        size_t per_query = src.size() / ctx->num_queries;
-        for (uint32_t q = 0; q < ctx->num_queries; q++) src[q * per_query] = d_zero;
-        const uint32_t** d_src = nullptr;
-        uint32_t* d_out = nullptr;
-        TRY(dalloc(ctx, (void**)&d_src, src.size() * sizeof(void*)));
-        TRY(dalloc(ctx, (void**)&d_out, src.size() * 4));
-        CU(cudaMemcpyAsync((void*)d_src, src.data(), src.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-        openk::k_gather_words<<<(unsigned)((src.size() + 255) / 256), 256, 0, ctx->stream>>>(d_src, d_out, src.size(), ctx->repr == BFGPU_REPR_CANONICAL);
-        LAUNCHED(ctx);
-        CU(cudaGetLastError());
-        flat.resize(base + src.size());
-        CU(cudaMemcpyAsync(flat.data() + base, d_out, src.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        for (size_t i = 0; i < layers.size(); i++) {
+            for (uint32_t k = 0; k < 4; k++) tmpl.push_back({layers[i].vec + k, 4, (uint32_t)i, 1, 0});  // 8*pair + 4*((idx^1)&1) = 4*(idx^1)
+            const bfgpu_tree* t = layers[i].tree;
+            for (unsigned l = 0; l < t->log_max; l++)
+                for (uint32_t k = 0; k < 8; k++) tmpl.push_back({t->layers[l] + k, 8, (uint32_t)(i + 1 + l), 1, 0});
+        }
+        std::vector<uint32_t> indices(ctx->num_queries);
+        for (uint32_t q = 0; q < ctx->num_queries; q++) indices[q] = ch.sample_bits(log_max_height);
+        const uint32_t per_query = (uint32_t)tmpl.size();
+        const size_t total = (size_t)per_query * ctx->num_queries;
+        Scratch scratch(ctx);
+        openk::QueryWord* d_tmpl = nullptr;
+        uint32_t *d_idx = nullptr, *d_out = nullptr;
+        TRY(scratch.alloc((void**)&d_tmpl, tmpl.size() * sizeof(openk::QueryWord)));
+        TRY(scratch.alloc((void**)&d_idx, indices.size() * 4 + 4));
+        TRY(scratch.alloc((void**)&d_out, total * 4 + 4));
+        CU(cudaMemcpyAsync(d_tmpl, tmpl.data(), tmpl.size() * sizeof(openk::QueryWord), cudaMemcpyHostToDevice, ctx->stream));
+        if (!indices.empty()) CU(cudaMemcpyAsync(d_idx, indices.data(), indices.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (total) {
+            openk::k_answer_queries<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_tmpl, per_query, d_idx, ctx->num_queries, d_out,
+                                                                                             ctx->repr == BFGPU_REPR_CANONICAL);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            const size_t base = flat.size();
+            flat.resize(base + total);
+            CU(cudaMemcpyAsync(flat.data() + base, d_out, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         CU(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t q = 0; q < ctx->num_queries; q++) flat[base + q * per_query] = indices[q];
-        dfree(ctx, d_zero);
-        dfree(ctx, (void*)d_src);
-        dfree(ctx, d_out);
-        (void)index_slots;
     }
     release_layers();
     guard.keep = true;

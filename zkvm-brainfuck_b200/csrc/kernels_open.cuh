@@ -356,4 +356,30 @@ __global__ void k_gather_words(const uint32_t* const* __restrict__ src, uint32_t
     out[i] = to_canonical ? kb::from_mont(v) : v;
 }
 
+// Query answers from a per-proof TEMPLATE: every query opens the same list of words, only the index differs, and every
+// word's address is base + stride * ((index >> shift) ^ flip):
+//   matrix element  : base = column start,   stride = row stride, shift = log(max height) - log(rows),          flip 0
+//   Merkle sibling  : base = layer + k,       stride = 8,          shift = (log max - log tree) + level,         flip 1
+//   FRI sibling val : base = folded vec + k,  stride = 4,          shift = round,                                 flip 1
+// so the host ships ~3 000 descriptors once instead of 84 x 3 000 pointers (2.3 MB of pageable host memory per proof).
+// A null base yields the query index itself (the serialisation stores it in front of each query).
+struct QueryWord {
+    const uint32_t* base;
+    uint32_t stride, shift, flip, pad;
+};
+__global__ void k_answer_queries(const QueryWord* __restrict__ tmpl, uint32_t per_query, const uint32_t* __restrict__ indices, uint32_t nq,
+                                 uint32_t* __restrict__ out, int to_canonical) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)per_query * nq) return;
+    const uint32_t q = (uint32_t)(i / per_query), e = (uint32_t)(i % per_query);
+    const QueryWord w = tmpl[e];
+    const uint32_t index = indices[q];
+    if (!w.base) {
+        out[i] = index;
+        return;
+    }
+    uint32_t v = w.base[(uint64_t)w.stride * ((index >> w.shift) ^ w.flip)];
+    out[i] = to_canonical ? kb::from_mont(v) : v;
+}
+
 }  // namespace openk
