@@ -79,6 +79,10 @@ struct bfgpu_ctx {
     // device-resident single-matrix commits: leaf sponge of block b concurrent with the NTT of block b+1 ($BFGPU_OVERLAP=1).
     // Measured at 2^22 x 256: 75.3 ms against 71.4 ms for the plain sequence (both kernels want the same two integer pipes;
     // the blocked LDE and the parked sponge states cost more than co-scheduling recovers) => off.
+    // page-locked ring for small host->device parameter uploads (pointer tables, descriptors): the copy becomes truly asynchronous and
+    // the host source may die right after the call (upload_small)
+    uint8_t* ring = nullptr;
+    size_t ring_size = 0, ring_pos = 0;
     bool fri_tail = true;  // small FRI rounds in one single-CTA launch (openk::k_fri_tail); $BFGPU_FRI_TAIL=0 disables
     bool overlap_device = false;
     int pipe_tail_splits = 1;  // $BFGPU_PIPE_SPLITS
@@ -205,6 +209,33 @@ static void dfree(bfgpu_ctx* ctx, void* p) {
     ctx->cached_bytes += bytes;
 }
 
+// Small host->device upload through the context's page-locked ring.  cudaMemcpyAsync from pageable memory blocks the host
+// until the driver has staged the bytes (~8 us each, dozens per proof); from the ring it is a plain enqueue.
+static int32_t upload_small(bfgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return BFGPU_OK;
+    if (!ctx->ring) {
+        ctx->ring_size = 8u << 20;
+        if (cudaHostAlloc((void**)&ctx->ring, ctx->ring_size, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->ring = nullptr;
+            ctx->ring_size = 0;
+        }
+    }
+    const size_t need = (bytes + 63) & ~(size_t)63;
+    if (!ctx->ring || need > ctx->ring_size / 4) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return BFGPU_OK;
+    }
+    if (ctx->ring_pos + need > ctx->ring_size) {
+        CU(cudaStreamSynchronize(ctx->stream));  // every copy out of the ring so far has completed: start over
+        ctx->ring_pos = 0;
+    }
+    memcpy(ctx->ring + ctx->ring_pos, src, bytes);
+    CU(cudaMemcpyAsync(dst, ctx->ring + ctx->ring_pos, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ring_pos += need;
+    return BFGPU_OK;
+}
+
 // Scratch device buffers of one entry point: returned to the block cache on every exit path.
 struct Scratch {
     bfgpu_ctx* ctx;
@@ -300,6 +331,7 @@ extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
     if (ctx->d_inv256) cudaFree(ctx->d_inv256);
+    if (ctx->ring) cudaFreeHost(ctx->ring);
     {
         std::lock_guard<std::mutex> g(g_ctx_mutex);
         g_live_ctx.erase(ctx);
@@ -661,8 +693,32 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
     return BFGPU_OK;
 }
 
-// coset LDE of a caller matrix -> column-major device matrix with bit-reversed rows.
-// shift_mont: Montgomery form of the coset shift.
+// per-coset scale vectors: pw[h*n + k] = (shift * w_N^{bitrev(h)})^k / n  (cached: a proof reuses a handful)
+static int32_t coset_powers(bfgpu_ctx* ctx, unsigned log_n, unsigned added_bits, uint32_t shift_mont, uint32_t** out) {
+    auto key = std::make_tuple(log_n, added_bits, shift_mont);
+    auto it = ctx->pw_cache.find(key);
+    if (it != ctx->pw_cache.end()) {
+        *out = it->second;
+        return BFGPU_OK;
+    }
+    Phase ph(ctx, BFGPU_PHASE_SCALE);
+    const uint64_t n = 1ull << log_n, N = n << added_bits;
+    const uint32_t ncosets = 1u << added_bits;
+    uint32_t* pw = nullptr;
+    CU(cudaMalloc(&pw, N * 4));
+    uint32_t ninv = kb::inv(kb::to_mont((uint32_t)(n % kb::P)));
+    uint32_t wN = kb::two_adic_generator(log_n + added_bits);
+    for (uint32_t h = 0; h < ncosets; h++) {
+        uint32_t sh = kb::mul(shift_mont, kb::pow(wN, kb::bitrev(h, added_bits)));
+        nttk::k_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pw + h * n, sh, ninv, n);
+        LAUNCHED(ctx);
+    }
+    CU(cudaGetLastError());
+    ctx->pw_cache[key] = pw;
+    *out = pw;
+    return BFGPU_OK;
+}
+
 // coset LDE of a column-major device matrix whose rows are already in bit-reversed order (consumed) ->
 // column-major device matrix with bit-reversed rows.  shift_mont: Montgomery form of the coset shift.
 static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, uint32_t shift_mont, DMat* out, bool consume = true,
@@ -671,27 +727,8 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     if (log_n + added_bits > kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
     uint64_t n = coef.rows, N = n << added_bits;
     uint32_t ncosets = 1u << added_bits;
-    // per-coset scale vectors: pw[h*n + k] = (shift * w_N^{bitrev(h)})^k / n  (cached: a proof reuses a handful)
     uint32_t* pw = nullptr;
-    {
-        auto key = std::make_tuple(log_n, added_bits, shift_mont);
-        auto it = ctx->pw_cache.find(key);
-        if (it != ctx->pw_cache.end()) {
-            pw = it->second;
-        } else {
-            Phase ph(ctx, BFGPU_PHASE_SCALE);
-            CU(cudaMalloc(&pw, N * 4));
-            uint32_t ninv = kb::inv(kb::to_mont((uint32_t)(n % kb::P)));
-            uint32_t wN = kb::two_adic_generator(log_n + added_bits);
-            for (uint32_t h = 0; h < ncosets; h++) {
-                uint32_t sh = kb::mul(shift_mont, kb::pow(wN, kb::bitrev(h, added_bits)));
-                nttk::k_powers<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pw + h * n, sh, ninv, n);
-                LAUNCHED(ctx);
-            }
-            CU(cudaGetLastError());
-            ctx->pw_cache[key] = pw;
-        }
-    }
+    TRY(coset_powers(ctx, log_n, added_bits, shift_mont, &pw));
     out->rows = N;
     out->cols = coef.cols;
     if (out_buf) out->d = out_buf;  // caller-provided destination (a column block of a larger matrix)
@@ -714,6 +751,55 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     if (consume) dfree(ctx, coef.d);
     TRY(run_ntt<false>(ctx, out->d, n, log_n, coef.cols * ncosets));
     return BFGPU_OK;
+}
+
+// Coset LDEs of several coefficient matrices (column-major, bit-reversed rows, consumed): columns of at most
+// 2^SMALL_LDE_MAX_LOG points of ALL matrices go through one nttk::k_lde_small launch, the rest through lde_from_bitrev.
+static int32_t lde_many(bfgpu_ctx* ctx, std::vector<DMat>& coefs, unsigned added_bits, const std::vector<uint32_t>& shift_mont, std::vector<DMat>* out) {
+    out->assign(coefs.size(), DMat());
+    nttk::SmallLdeArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.ncosets = 1u << added_bits;
+    sa.tw = ctx->d_tw;
+    std::vector<size_t> small;
+    auto flush = [&]() -> int32_t {
+        if (!sa.nmats) return BFGPU_OK;
+        Phase ph(ctx, BFGPU_PHASE_NTT);
+        nttk::k_lde_small<<<sa.first_cta[sa.nmats], 256, 0, ctx->stream>>>(sa);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        for (size_t i : small) {
+            dfree(ctx, coefs[i].d);
+            coefs[i].d = nullptr;
+        }
+        small.clear();
+        sa.nmats = 0;
+        return BFGPU_OK;
+    };
+    for (size_t i = 0; i < coefs.size(); i++) {
+        const unsigned log_n = ilog2(coefs[i].rows);
+        if (log_n + added_bits > (unsigned)kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
+        if (log_n > (unsigned)nttk::SMALL_LDE_MAX_LOG || coefs[i].cols == 0) {
+            TRY(lde_from_bitrev(ctx, coefs[i], added_bits, shift_mont[i], &(*out)[i]));
+            coefs[i].d = nullptr;
+            continue;
+        }
+        if (sa.nmats == (uint32_t)nttk::SMALL_LDE_MAX_MATS) TRY(flush());
+        DMat& o = (*out)[i];
+        o.rows = coefs[i].rows << added_bits;
+        o.cols = coefs[i].cols;
+        TRY(dalloc(ctx, (void**)&o.d, o.rows * o.cols * 4));
+        uint32_t* pw = nullptr;
+        TRY(coset_powers(ctx, log_n, added_bits, shift_mont[i], &pw));
+        const uint32_t k = sa.nmats++;
+        sa.coef[k] = coefs[i].d;
+        sa.out[k] = o.d;
+        sa.pw[k] = pw;
+        sa.log_n[k] = log_n;
+        sa.first_cta[k + 1] = sa.first_cta[k] + coefs[i].cols;
+        small.push_back(i);
+    }
+    return flush();
 }
 
 // coset LDE of a caller matrix.  keep != null: also return a copy of the ingested trace (column-major,
@@ -810,7 +896,7 @@ static int32_t make_colptr(bfgpu_ctx* ctx, const std::vector<const DMat*>& mats,
         for (uint32_t c = 0; c < m->cols; c++) h.push_back(m->d + (uint64_t)c * m->col_stride());
     *ncols_out = (uint32_t)h.size();
     TRY(dalloc(ctx, (void**)d_out, h.size() * sizeof(void*)));
-    if (!h.empty()) CU(cudaMemcpyAsync((void*)*d_out, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(upload_small(ctx, (void*)*d_out, h.data(), h.size() * sizeof(void*)));
     return BFGPU_OK;
 }
 
@@ -998,8 +1084,8 @@ extern "C" int32_t bfgpu_mmcs_open_batch(bfgpu_tree* t, uint64_t index, uint32_t
     TRY(dalloc(ctx, (void**)&d_cp, nc * sizeof(void*)));
     TRY(dalloc(ctx, (void**)&d_ri, nc * 8));
     TRY(dalloc(ctx, (void**)&d_out, nc * 4));
-    CU(cudaMemcpyAsync((void*)d_cp, cp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d_ri, ri.data(), nc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(upload_small(ctx, (void*)d_cp, cp.data(), nc * sizeof(void*)));
+    TRY(upload_small(ctx, d_ri, ri.data(), nc * 8));
     hashk::k_gather_row<<<(nc + 127) / 128, 128, 0, ctx->stream>>>(d_cp, d_ri, nc, d_out, ctx->repr == BFGPU_REPR_CANONICAL);
     LAUNCHED(ctx);
     CU(cudaGetLastError());
@@ -1431,7 +1517,7 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
         for (uint32_t k = 1; k < maxw; k++) apow[k] = kb::ext_mul(apow[k - 1], alpha);
         uint32_t* d_apow = nullptr;
         TRY(dalloc(ctx, (void**)&d_apow, (size_t)maxw * 16));
-        CU(cudaMemcpyAsync(d_apow, apow.data(), (size_t)maxw * 16, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(upload_small(ctx, d_apow, apow.data(), (size_t)maxw * 16));
         struct Group {
             std::vector<openk::RoMat> mats;
             std::vector<kb::Ext> pts;
@@ -1472,13 +1558,12 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             TRY(dalloc(ctx, (void**)&d_m, g.mats.size() * sizeof(openk::RoMat)));
             TRY(dalloc(ctx, (void**)&d_z, g.pts.size() * 16));
             TRY(dalloc(ctx, (void**)&ro, (size_t)16 << lh));
-            CU(cudaMemcpyAsync(d_m, g.mats.data(), g.mats.size() * sizeof(openk::RoMat), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaMemcpyAsync(d_z, g.pts.data(), g.pts.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
+            TRY(upload_small(ctx, d_m, g.mats.data(), g.mats.size() * sizeof(openk::RoMat)));
+            TRY(upload_small(ctx, d_z, g.pts.data(), g.pts.size() * 16));
             openk::k_reduce_openings<<<((1u << lh) + 127) / 128, 128, 0, ctx->stream>>>(d_m, (uint32_t)g.mats.size(), d_z, (uint32_t)g.pts.size(), d_apow, lh,
                                                                                          gen, ctx->d_tw, ro);
             LAUNCHED(ctx);
             CU(cudaGetLastError());
-            CU(cudaStreamSynchronize(ctx->stream));  // host vectors above must outlive the copies
             dfree(ctx, d_m);
             dfree(ctx, d_z);
             reduced[lh] = ro;
@@ -1642,11 +1727,11 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             unsigned int* d_best = nullptr;
             TRY(dalloc(ctx, (void**)&d_st, 64));
             TRY(dalloc(ctx, (void**)&d_best, 4));
-            CU(cudaMemcpyAsync(d_st, st, 64, cudaMemcpyHostToDevice, ctx->stream));
+            TRY(upload_small(ctx, d_st, st, 64));
             const uint32_t batch = 1u << 20, mask = (1u << ctx->pow_bits) - 1;
             unsigned int best = 0xffffffffu;
             for (uint64_t start = 0; start < kb::P && best == 0xffffffffu; start += batch) {
-                CU(cudaMemcpyAsync(d_best, &best, 4, cudaMemcpyHostToDevice, ctx->stream));
+                TRY(upload_small(ctx, d_best, &best, 4));
                 uint32_t count = (uint32_t)std::min<uint64_t>(batch, kb::P - start);
                 openk::k_pow_grind<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_st, pos, mask, (uint32_t)start, count, d_best);
                 LAUNCHED(ctx);
@@ -1694,8 +1779,8 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
         TRY(scratch.alloc((void**)&d_tmpl, tmpl.size() * sizeof(openk::QueryWord)));
         TRY(scratch.alloc((void**)&d_idx, indices.size() * 4 + 4));
         TRY(scratch.alloc((void**)&d_out, total * 4 + 4));
-        CU(cudaMemcpyAsync(d_tmpl, tmpl.data(), tmpl.size() * sizeof(openk::QueryWord), cudaMemcpyHostToDevice, ctx->stream));
-        if (!indices.empty()) CU(cudaMemcpyAsync(d_idx, indices.data(), indices.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(upload_small(ctx, d_tmpl, tmpl.data(), tmpl.size() * sizeof(openk::QueryWord)));
+        TRY(upload_small(ctx, d_idx, indices.data(), indices.size() * 4));
         if (total) {
             openk::k_answer_queries<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_tmpl, per_query, d_idx, ctx->num_queries, d_out,
                                                                                              ctx->repr == BFGPU_REPR_CANONICAL);
@@ -1771,12 +1856,24 @@ static int32_t machine_commit(bfgpu_ctx* ctx, const char* const* names, const bf
     for (int k = 0; k < n; k++) in_order[k] = mats[order[k]];
     int32_t rc = prestage_all(ctx, in_order.data(), n);
     const uint32_t gen = kb::to_mont(kb::GEN);
-    for (int k = 0; k < n && rc == BFGPU_OK; k++) {
+    std::vector<DMat> coefs(n);
+    for (int k = 0; k < n && rc == BFGPU_OK; k++) {  // ingest (+ the copy the LogUp kernel reads later); the LDEs follow in one batch
         int i = order[k];
         out_names->push_back(names[i]);
         out_chip->push_back(chip_index(names[i]));
-        rc = lde_device(ctx, mats[i], ctx->log_blowup, gen, &pd->ldes[k], &(*out_traces)[k]);
+        if (ilog2(mats[i].rows) + ctx->log_blowup > (unsigned)kb::TWO_ADICITY) rc = fail(ctx, BFGPU_ERR_INVALID, "LDE height exceeds the field's two-adicity");
+        if (rc == BFGPU_OK) rc = ingest(ctx, mats[i], /*bitrev=*/true, &coefs[k]);
+        if (rc == BFGPU_OK) {
+            DMat& keep = (*out_traces)[k];
+            keep = coefs[k];
+            const size_t bytes = (size_t)keep.rows * keep.cols * 4;
+            rc = dalloc(ctx, (void**)&keep.d, bytes);
+            if (rc == BFGPU_OK && cudaMemcpyAsync(keep.d, coefs[k].d, bytes, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+                rc = fail(ctx, BFGPU_ERR_CUDA, "trace copy failed");
+        }
     }
+    if (rc == BFGPU_OK) rc = lde_many(ctx, coefs, ctx->log_blowup, std::vector<uint32_t>(n, gen), &pd->ldes);
+    for (DMat& c : coefs) dfree(ctx, c.d);  // only non-null after an error
     prestage_clear(ctx);
     if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree);
     if (rc == BFGPU_OK) {
@@ -1868,12 +1965,7 @@ static int32_t commit_bitrev_device(bfgpu_ctx* ctx, std::vector<DMat>& coefs, co
                                     uint32_t root_mont[8]) {
     bfgpu_pcs_data* pd = new bfgpu_pcs_data();
     pd->ctx = ctx;
-    pd->ldes.resize(coefs.size());
-    int32_t rc = BFGPU_OK;
-    for (size_t i = 0; i < coefs.size() && rc == BFGPU_OK; i++) {
-        rc = lde_from_bitrev(ctx, coefs[i], ctx->log_blowup, shift_mont[i], &pd->ldes[i]);
-        coefs[i].d = nullptr;
-    }
+    int32_t rc = lde_many(ctx, coefs, ctx->log_blowup, shift_mont, &pd->ldes);
     if (rc == BFGPU_OK) rc = build_tree(ctx, pd->ldes, false, &pd->tree);
     if (rc == BFGPU_OK) {
         CU(cudaMemcpyAsync(root_mont, pd->tree->layers.back(), 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1975,7 +2067,7 @@ extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const 
         for (int k = 1; k < air::MAX_CONSTRAINTS; k++) apow[k] = kb::ext_mul(apow[k - 1], alpha);
         kb::Ext* d_apow = nullptr;
         TRY(dalloc(ctx, (void**)&d_apow, apow.size() * sizeof(kb::Ext)));
-        CU(cudaMemcpyAsync(d_apow, apow.data(), apow.size() * sizeof(kb::Ext), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(upload_small(ctx, d_apow, apow.data(), apow.size() * sizeof(kb::Ext)));
         for (size_t i = 0; i < nchips; i++) {
             const air::ChipInfo& ci = air::CHIPS[sd->chip[i]];
             unsigned log_n = ilog2(sd->traces[i].rows);

@@ -96,6 +96,69 @@ __global__ void k_egress(const uint32_t* __restrict__ src, uint32_t* __restrict_
     }
 }
 
+// ---- whole coset LDE of SMALL columns (<= 2^SMALL_LDE_MAX_LOG points), many matrices per launch -----------------------
+// A proof commits to a handful of short matrices (Program, Memory, IO, AddSub, ... : 16 to a few thousand rows) three
+// times; through the general path each costs 4-5 launches of a few microseconds.  Here one CTA owns one column of one
+// matrix and does the whole chain in shared memory — inverse DIT (bit-reversed in, natural out), per-coset scaling,
+// forward DIF (natural in, bit-reversed out) — and one launch covers every small matrix of the commitment.
+constexpr int SMALL_LDE_MAX_LOG = 11, SMALL_LDE_MAX_MATS = 24;
+struct SmallLdeArgs {
+    uint32_t* coef[SMALL_LDE_MAX_MATS];       // column-major, bit-reversed rows, 2^log_n rows
+    uint32_t* out[SMALL_LDE_MAX_MATS];        // column-major, ncosets * 2^log_n rows
+    const uint32_t* pw[SMALL_LDE_MAX_MATS];   // pw[h * n + k] = shift_h^k / n
+    uint32_t log_n[SMALL_LDE_MAX_MATS];
+    uint32_t first_cta[SMALL_LDE_MAX_MATS + 1];  // prefix sums of the column counts
+    uint32_t nmats, ncosets;
+    const uint32_t* tw;                       // w_{2^24}^e table
+};
+__device__ __forceinline__ uint32_t small_root(const uint32_t* __restrict__ tw, unsigned log_m, uint32_t j) {  // w_{2^log_m}^j, j < 2^log_m
+    if (log_m == 0) return kb::ONE;
+    uint32_t half = 1u << (log_m - 1);
+    uint32_t v = __ldg(tw + ((uint64_t)(j & (half - 1)) << (TW_LOG - log_m)));
+    return (j & half) ? kb::neg(v) : v;
+}
+__global__ void __launch_bounds__(256) k_lde_small(SmallLdeArgs A) {
+    __shared__ uint32_t x[1 << SMALL_LDE_MAX_LOG], y[1 << SMALL_LDE_MAX_LOG];
+    uint32_t m = 0;
+    while (m + 1 < A.nmats && blockIdx.x >= A.first_cta[m + 1]) m++;
+    const uint32_t c = blockIdx.x - A.first_cta[m];
+    const unsigned log_n = A.log_n[m];
+    const uint32_t n = 1u << log_n;
+    const uint32_t* src = A.coef[m] + (uint64_t)c * n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) x[i] = src[i];
+    __syncthreads();
+    for (unsigned s = 0; s < log_n; s++) {  // inverse, decimation in time
+        const uint32_t half = 1u << s;
+        for (uint32_t q = threadIdx.x; q < n / 2; q += blockDim.x) {
+            const uint32_t j = q & (half - 1), i0 = ((q >> s) << (s + 1)) | j, i1 = i0 + half;
+            const uint32_t w = j ? small_root(A.tw, s + 1, (2 * half) - j) : kb::ONE;  // w_{2^(s+1)}^{-j}
+            const uint32_t a = x[i0], b = kb::mul(x[i1], w);
+            x[i0] = kb::add(a, b);
+            x[i1] = kb::sub(a, b);
+        }
+        __syncthreads();
+    }
+    for (uint32_t h = 0; h < A.ncosets; h++) {
+        const uint32_t* pw = A.pw[m] + (uint64_t)h * n;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) y[i] = kb::mul(x[i], __ldg(pw + i));
+        __syncthreads();
+        for (int s = (int)log_n - 1; s >= 0; s--) {  // forward, decimation in frequency
+            const uint32_t half = 1u << s;
+            for (uint32_t q = threadIdx.x; q < n / 2; q += blockDim.x) {
+                const uint32_t j = q & (half - 1), i0 = ((q >> s) << (s + 1)) | j, i1 = i0 + half;
+                const uint32_t a = y[i0], b = y[i1];
+                y[i0] = kb::add(a, b);
+                const uint32_t d = kb::sub(a, b);
+                y[i1] = j ? kb::mul(d, small_root(A.tw, s + 1, j)) : d;
+            }
+            __syncthreads();
+        }
+        uint32_t* dst = A.out[m] + ((uint64_t)c * A.ncosets + h) * n;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = y[i];
+        __syncthreads();
+    }
+}
+
 // ---- coset scaling: coefficients -> 2^added_bits scaled copies ---------------------------------
 // out[c][h*n + k] = in[c][k] * pw[h*n + k]   (pw[h*n+k] = (shift_h)^k / n)
 __global__ void k_scale_cosets(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ pw, uint64_t n,
