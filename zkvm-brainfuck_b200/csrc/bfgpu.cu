@@ -1450,6 +1450,8 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
                 }
         uint32_t* sums_all = nullptr;
         TRY(dalloc(ctx, (void**)&sums_all, total_words * 4));
+        std::vector<openk::BaryJob> batch[2];  // single-chunk jobs with 1 / 2 opening points
+        uint32_t batch_groups[2] = {0, 0};
         for (Job& jb : jobs) {
             const DMat& m = *jb.mp->m;
             uint32_t h = (uint32_t)(m.rows >> log_blowup);
@@ -1458,6 +1460,11 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             uint32_t *w0 = nullptr, *w1 = nullptr;
             TRY(weights(log_h, jb.mp->pts[jb.t0], &w0));
             if (jb.np == 2) TRY(weights(log_h, jb.mp->pts[jb.t0 + 1], &w1));
+            if (nchunks == 1) {
+                batch[jb.np - 1].push_back({m.d, m.rows, w0, w1, sums_all + jb.off, m.cols, h});
+                batch_groups[jb.np - 1] = std::max(batch_groups[jb.np - 1], (m.cols + openk::BARY_COLS - 1) / openk::BARY_COLS);
+                continue;
+            }
             uint32_t* partial = nullptr;
             size_t nsum = (size_t)m.cols * jb.np * 4;
             TRY(dalloc(ctx, (void**)&partial, nsum * nchunks * 4));
@@ -1469,6 +1476,18 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             LAUNCHED(ctx);
             CU(cudaGetLastError());
             dfree(ctx, partial);
+        }
+        for (int k = 0; k < 2; k++) {
+            if (batch[k].empty()) continue;
+            openk::BaryJob* d_jobs = nullptr;
+            TRY(dalloc(ctx, (void**)&d_jobs, batch[k].size() * sizeof(openk::BaryJob)));
+            TRY(upload_small(ctx, d_jobs, batch[k].data(), batch[k].size() * sizeof(openk::BaryJob)));
+            dim3 grid(batch_groups[k], (unsigned)batch[k].size());
+            if (k == 0) openk::k_bary_dot_batch<1><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(d_jobs);
+            else openk::k_bary_dot_batch<2><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(d_jobs);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            dfree(ctx, d_jobs);
         }
         std::vector<uint32_t> hs(total_words);
         CU(cudaMemcpyAsync(hs.data(), sums_all, total_words * 4, cudaMemcpyDeviceToHost, ctx->stream));

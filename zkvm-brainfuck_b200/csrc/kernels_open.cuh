@@ -50,10 +50,9 @@ __global__ void k_bary_weights(uint32_t* __restrict__ w, unsigned log_h, uint32_
 #endif
 constexpr int BARY_THREADS = 256, BARY_ROWS = 4096, BARY_COLS = BFGPU_BARY_COLS, BARY_UNROLL = BFGPU_BARY_UNROLL;  // BARY_COLS columns share each pair of 16-byte weights
 template <int NP>
-__global__ void __launch_bounds__(BARY_THREADS) k_bary_dot(const uint32_t* __restrict__ mat, uint64_t col_stride, uint32_t ncols, uint32_t h,
-                                                           const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
-                                                           uint32_t* __restrict__ partial, uint32_t nchunks) {
-    const uint32_t chunk = blockIdx.x, c0 = blockIdx.y * BARY_COLS;
+__device__ __forceinline__ void bary_dot_body(const uint32_t* __restrict__ mat, uint64_t col_stride, uint32_t ncols, uint32_t h,
+                                              const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1, uint32_t* __restrict__ partial,
+                                              uint32_t nchunks, const uint32_t chunk, const uint32_t c0) {
     uint64_t acc[BARY_COLS][NP][4];
 #pragma unroll
     for (int c = 0; c < BARY_COLS; c++)
@@ -100,6 +99,29 @@ __global__ void __launch_bounds__(BARY_THREADS) k_bary_dot(const uint32_t* __res
         int c = threadIdx.x / (NP * 4), rem = threadIdx.x % (NP * 4);
         if (c0 + c < ncols) partial[(((uint64_t)(c0 + c) * nchunks + chunk) * NP) * 4 + rem] = v;
     }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(BARY_THREADS) k_bary_dot(const uint32_t* __restrict__ mat, uint64_t col_stride, uint32_t ncols, uint32_t h,
+                                                           const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
+                                                           uint32_t* __restrict__ partial, uint32_t nchunks) {
+    bary_dot_body<NP>(mat, col_stride, ncols, h, w0, w1, partial, nchunks, blockIdx.x, blockIdx.y * BARY_COLS);
+}
+// every matrix whose low coset fits one chunk (h <= BARY_ROWS), in one launch: blockIdx.y = job, blockIdx.x = column group;
+// with a single chunk the partial sums ARE the sums, written straight to their final place
+struct BaryJob {
+    const uint32_t* mat;
+    uint64_t col_stride;
+    const uint32_t *w0, *w1;
+    uint32_t* out;
+    uint32_t ncols, h;
+};
+template <int NP>
+__global__ void __launch_bounds__(BARY_THREADS) k_bary_dot_batch(const BaryJob* __restrict__ jobs) {
+    const BaryJob j = jobs[blockIdx.y];
+    const uint32_t c0 = blockIdx.x * BARY_COLS;
+    if (c0 >= j.ncols) return;
+    bary_dot_body<NP>(j.mat, j.col_stride, j.ncols, j.h, j.w0, j.w1, j.out, 1, 0, c0);
 }
 
 // out[i] = sum over chunks of partial[i][chunk]   (i over ncols*NP*4 words; layout as above)
