@@ -416,17 +416,20 @@ def main():
         del trace
         torch.cuda.empty_cache()
 
-        def dist_case(total_cols, exchange):
+        def dist_case(total_cols, exchange, nmats=1):
+            """one commitment of `nmats` matrices (nmats = 8: BASELINE config 5, "2^24 rows" as 8 x (2^21 x 64) in ONE commit, the same
+            number of cells as 2^22 x 256), every matrix column-sharded over the ranks"""
+            rows = R if nmats == 1 else 4 * R // nmats
             c0, nloc = shard.col_range(total_cols, world, rank)
             gg = torch.Generator(device="cuda")
             gg.manual_seed(0xD157 + rank)
-            cols = torch.randint(0, P, (R, nloc), dtype=torch.int32, device="cuda", generator=gg)
+            mats = [torch.randint(0, P, (rows, nloc), dtype=torch.int32, device="cuda", generator=gg) for _ in range(nmats)]
             torch.cuda.synchronize()
             roots = []
 
             def step():
-                dc = shard.DistributedCommit(ctx, dist, [R], [total_cols], exchange=exchange)
-                roots.append(dc.commit([(cols.data_ptr(), R, nloc)]).copy())
+                dc = shard.DistributedCommit(ctx, dist, [rows] * nmats, [total_cols] * nmats, exchange=exchange)
+                roots.append(dc.commit([(m.data_ptr(), rows, nloc) for m in mats]).copy())
                 dc.free()
 
             for _ in range(2):
@@ -441,10 +444,11 @@ def main():
             barrier()
             ms = shard.max_over_ranks(e0.elapsed_time(e1), dist, "cuda") / args.steps
             assert all((r == roots[0]).all() for r in roots)
-            del cols
+            del mats
             torch.cuda.empty_cache()
-            return {"workload": workload_name(args.log_rows, total_cols), "exchange": exchange, "ms_per_step": ms,
-                    "value": algorithmic_bytes(R, total_cols) / (ms * 1e-3) / 1e9, "unit": "GB/s",
+            name = workload_name(args.log_rows, total_cols) if nmats == 1 else f"pcs_commit of {nmats} x (2^{rows.bit_length() - 1} x {total_cols}) in one commitment"
+            return {"workload": name, "exchange": exchange, "ms_per_step": ms,
+                    "value": algorithmic_bytes(rows * nmats, total_cols) / (ms * 1e-3) / 1e9, "unit": "GB/s",
                     "launches_per_step_per_rank": (ctx.launch_count - l0) // args.steps, "root": [int(x) for x in roots[0]]}
 
         one_commitment = {
@@ -455,6 +459,8 @@ def main():
             "weak_p2p": dist_case(W * world, "p2p"),
             "weak_staged_nccl": dist_case(W * world, "staged"),
         }
+        if args.log_rows >= 5:  # BASELINE config 5 shape: eight matrices (2^24 rows x 64 columns in total at the default size)
+            one_commitment["config5_8_matrices_p2p"] = dist_case(max(W // 4, 8), "p2p", nmats=8)
 
     if rank == 0:
         peaks = {}
