@@ -135,6 +135,10 @@ __global__ void k_bary_finish(const uint32_t* __restrict__ partial, uint32_t* __
 }
 
 // ---- reduced openings of one height group ---------------------------------------------------------------
+#ifndef BFGPU_RO_UNROLL
+#define BFGPU_RO_UNROLL 4
+#endif
+constexpr int RO_UNROLL = BFGPU_RO_UNROLL;  // column loads in flight per thread in k_reduce_openings
 struct RoMat {
     const uint32_t* d;  // column-major LDE, `rows` rows
     uint32_t width;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
         const RoMat& M = mats[m];
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // unreduced sum_k alpha^k M[r][k]
         const uint32_t* col = M.d + r;
-#pragma unroll 4
+#pragma unroll RO_UNROLL
         for (uint32_t k = 0; k < M.width; k++) {
             uint32_t v = col[(uint64_t)k << log_h];
             Ext a = ld_ext(apow + 4 * k);
