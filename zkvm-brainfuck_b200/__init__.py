@@ -233,7 +233,10 @@ class Context:
             self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     # ---- Poseidon2 primitives -----------------------------------------------------------------
     def permute(self, states):
@@ -312,7 +315,10 @@ class MerkleTree:
         self._h = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class MerkleTreeMmcs:
@@ -361,7 +367,10 @@ class PcsProverData:
             self.tree._h = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class Challenger:
@@ -412,9 +421,12 @@ class Challenger:
         return st, ib[:ni.value].copy(), ob[:no.value].copy()
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().bfgpu_challenger_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().bfgpu_challenger_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class TwoAdicFriPcs:
@@ -526,7 +538,10 @@ class _Named:
             self._h = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
 
 def _named_mats(named):
@@ -595,7 +610,10 @@ class Record:
             self._h = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class CudaProver:
@@ -889,6 +907,9 @@ class _ProgramOnly:
         self.n_instr = int(c[1])
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().bfgpu_record_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().bfgpu_record_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass

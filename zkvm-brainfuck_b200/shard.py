@@ -180,4 +180,7 @@ class DistributedCommit:
             self._h = None
 
     def __del__(self):
-        self.free()
+        try:
+            self.free()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
