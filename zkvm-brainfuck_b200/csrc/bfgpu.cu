@@ -83,6 +83,7 @@ struct bfgpu_ctx {
     // the host source may die right after the call (upload_small)
     uint8_t* ring = nullptr;
     size_t ring_size = 0, ring_pos = 0;
+    uint64_t x4_layer_max = 1u << 15;  // Merkle layers up to this many nodes use k_compress_layer_x4 ($BFGPU_X4_MAX)
     bool fri_tail = true;  // small FRI rounds in one single-CTA launch (openk::k_fri_tail); $BFGPU_FRI_TAIL=0 disables
     bool overlap_device = false;
     int pipe_tail_splits = 1;  // $BFGPU_PIPE_SPLITS
@@ -268,6 +269,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (const char* e = getenv("BFGPU_PIPE_COLS")) ctx->pipe_cols = (uint32_t)atoi(e) / 8 * 8;
     if (const char* e = getenv("BFGPU_OVERLAP")) ctx->overlap_device = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_FRI_TAIL")) ctx->fri_tail = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_X4_MAX")) ctx->x4_layer_max = strtoull(e, nullptr, 10);
     if (const char* e = getenv("BFGPU_PIPE_SPLITS")) ctx->pipe_tail_splits = atoi(e);
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
 
@@ -1022,8 +1024,12 @@ static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfg
             colptrs_to_free.push_back((void*)colptr);
             continue;
         }
-        hashk::k_compress_layer<<<(unsigned)((len + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(
-            t->layers[l - 1], layer, len, colptr, ncols, rs);
+        if (len <= ctx->x4_layer_max)  // narrow layer: latency-bound, four lanes per node
+            hashk::k_compress_layer_x4<<<(unsigned)((4 * len + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(
+                t->layers[l - 1], layer, len, colptr, ncols, rs);
+        else
+            hashk::k_compress_layer<<<(unsigned)((len + hashk::HASH_THREADS - 1) / hashk::HASH_THREADS), hashk::HASH_THREADS, 0, ctx->stream>>>(
+                t->layers[l - 1], layer, len, colptr, ncols, rs);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
         dfree(ctx, (void*)colptr);

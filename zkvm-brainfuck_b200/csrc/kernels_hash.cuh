@@ -113,6 +113,47 @@ __global__ void __launch_bounds__(HASH_THREADS) k_compress_layer(const uint32_t*
     store_digest(out + 8 * i, s);
 }
 
+// Same layer step with FOUR lanes per node (p2::permute_x4): for layers too narrow to fill the machine (a 2^14-node layer
+// occupies 5 % of the thread slots) the launch costs one permutation LATENCY, and the four-lane form has a third of the
+// dependent chain (ncu: every one-thread layer launch between 2^10 and 2^16 nodes takes ~10.5 us whatever its width).
+__global__ void __launch_bounds__(HASH_THREADS) k_compress_layer_x4(const uint32_t* __restrict__ prev, uint32_t* __restrict__ out, uint64_t len,
+                                                                    const uint32_t* const* __restrict__ colptr, uint32_t ncols, uint32_t row_stride) {
+    __shared__ uint32_t s_ext[8 * 16], s_int[16];
+    const uint32_t t = threadIdx.x;
+    if (t < 128) s_ext[t] = p2::c_p2.ext_s[t >> 4][t & 15];
+    if (t < 16) s_int[t] = p2::c_p2.internal_s[t];
+    __syncthreads();
+    const int q = t & 3;
+    const p2::X4 xc = p2::x4_setup(s_ext, s_int, q);
+    const uint64_t i = (blockIdx.x * (uint64_t)HASH_THREADS + t) >> 2;
+    const bool on = i < len;
+    if (((blockIdx.x * (uint64_t)HASH_THREADS + (t & ~31u)) >> 2) >= len) return;  // whole warp past the end
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (on) {
+        uint4 x = *reinterpret_cast<const uint4*>(prev + 16 * i + 4 * q);
+        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+    }
+    p2::permute_x4(w, xc, q);
+    if (ncols) {
+        uint32_t h[4] = {0, 0, 0, 0};
+        for (uint32_t c0 = 0; c0 < ncols; c0 += 8) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t c = c0 + 4 * q + j;
+                if (on && q < 2 && c < ncols) h[j] = __ldg(colptr[c] + i * row_stride);
+            }
+            p2::permute_x4(h, xc, q);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t from_low = __shfl_xor_sync(0xffffffffu, h[j], 2);
+            if (q >= 2) w[j] = from_low;
+        }
+        p2::permute_x4(w, xc, q);
+    }
+    if (on && q < 2) *reinterpret_cast<uint4*>(out + 8 * i + 4 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // Top of the tree in ONE launch: starting from a layer of `len0` <= TOP_MAX digests, computes every remaining layer
 // down to the root inside a single CTA (the layer being consumed sits in shared memory), writing each layer to its
 // global array.  Removes ~10 launches per tree, which dominate small proofs and the FRI commit phase.
