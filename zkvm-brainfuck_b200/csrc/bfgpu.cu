@@ -1620,6 +1620,22 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
         it->second = nullptr;
         ++it;
         std::vector<std::array<uint32_t, 8>> commits;
+        // The challenger rides along on the device for the whole commit phase (openk::k_challenger_round, k_fri_tail): rounds
+        // are enqueued back to back with no host round trip; all roots come back in ONE copy and the host challenger replays them.
+        Scratch fs(ctx);
+        uint32_t *d_ch = nullptr, *d_roots = nullptr, *d_betas = nullptr;
+        const uint32_t total_rounds = ilog2(len) - log_blowup;
+        TRY(fs.alloc((void**)&d_ch, 32 * 4));
+        TRY(fs.alloc((void**)&d_roots, (size_t)std::max(total_rounds, 1u) * 32));
+        TRY(fs.alloc((void**)&d_betas, (size_t)std::max(total_rounds, 1u) * 16));
+        {
+            uint32_t h[32] = {0};
+            memcpy(h, ch.state, 64);
+            for (size_t k = 0; k < ch.input.size(); k++) h[16 + k] = ch.input[k];
+            h[24] = (uint32_t)ch.input.size();
+            TRY(upload_small(ctx, d_ch, h, sizeof h));
+        }
+        uint32_t round = 0;
         while (len > (1ull << log_blowup)) {
             if (ctx->fri_tail && len <= (1ull << openk::TAIL_MAX_LOG) && ilog2(len) - log_blowup <= (unsigned)openk::TAIL_MAX_ROUNDS) {
                 // ---- all remaining rounds in one single-CTA launch (openk::k_fri_tail) ----
@@ -1628,15 +1644,10 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
                 ta.log_len = ilog2(len);
                 ta.nrounds = ta.log_len - log_blowup;
                 ta.tw = ctx->d_tw;
-                memcpy(ta.ch_state, ch.state, sizeof ta.ch_state);
-                ta.ch_nin = (uint32_t)ch.input.size();
-                for (size_t k = 0; k < ch.input.size(); k++) ta.ch_in[k] = ch.input[k];
-                uint32_t* d_roots = nullptr;
-                TRY(dalloc(ctx, (void**)&d_roots, ta.nrounds * 32));
-                ta.roots = d_roots;
+                ta.ch = d_ch;
+                ta.roots = d_roots + 8 * (size_t)round;
                 ta.vec[0] = folded;
                 int32_t rc = BFGPU_OK;
-                const size_t first_tail_layer = layers.size();
                 for (uint32_t r = 0; r < ta.nrounds && rc == BFGPU_OK; r++) {
                     const uint64_t nleaves = len >> (r + 1);
                     bfgpu_tree* t = new bfgpu_tree();
@@ -1662,7 +1673,7 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
                         ++it;
                     }
                 }
-                if (rc != BFGPU_OK) { dfree(ctx, d_roots); release_layers(); return rc; }
+                if (rc != BFGPU_OK) { release_layers(); return rc; }
                 openk::k_fri_tail<<<1, openk::TAIL_THREADS, 0, ctx->stream>>>(ta);
                 LAUNCHED(ctx);
                 CU(cudaGetLastError());
@@ -1673,18 +1684,7 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
                                 dfree(ctx, kv.second);
                                 kv.second = nullptr;
                             }
-                std::vector<uint32_t> roots(ta.nrounds * 8);
-                CU(cudaMemcpyAsync(roots.data(), d_roots, roots.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaStreamSynchronize(ctx->stream));
-                dfree(ctx, d_roots);
-                for (uint32_t r = 0; r < ta.nrounds; r++) {  // advance the host transcript exactly as the kernel did
-                    std::array<uint32_t, 8> root;
-                    memcpy(root.data(), &roots[8 * r], 32);
-                    ch.observe_slice(root.data(), 8);
-                    commits.push_back(root);
-                    (void)ch.sample_ext();
-                }
-                (void)first_tail_layer;
+                round += ta.nrounds;
                 folded = ta.vec[ta.nrounds];
                 len = 1ull << log_blowup;
                 break;
@@ -1698,20 +1698,15 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             int32_t rc = build_tree(ctx, {leaves}, false, &t);
             layers.push_back({folded, len, t});
             if (rc != BFGPU_OK) { release_layers(); return rc; }
-            std::array<uint32_t, 8> root;
-            CU(cudaMemcpyAsync(root.data(), t->layers.back(), 32, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            ch.observe_slice(root.data(), 8);
-            commits.push_back(root);
-            kb::Ext beta = ch.sample_ext();
-            kb::Ext half_beta = kb::ext_scale(beta, kb::halve(kb::ONE));
+            openk::k_challenger_round<<<1, 32, 0, ctx->stream>>>(d_ch, t->layers.back(), d_betas + 4 * (size_t)round, d_roots + 8 * (size_t)round);
+            LAUNCHED(ctx);
             uint64_t nlen = len / 2;
             unsigned log_nlen = ilog2(nlen);
             uint32_t* next = nullptr;
             TRY(dalloc(ctx, (void**)&next, nlen * 16));
             const uint32_t* add = nullptr;
             if (it != reduced.end() && (1ull << it->first) == nlen) add = it->second;
-            openk::k_fri_fold<<<(unsigned)((nlen + 127) / 128), 128, 0, ctx->stream>>>(folded, next, add, log_nlen, half_beta, ctx->d_tw);
+            openk::k_fri_fold_dev<<<(unsigned)((nlen + 127) / 128), 128, 0, ctx->stream>>>(folded, next, add, log_nlen, d_betas + 4 * (size_t)round, ctx->d_tw);
             LAUNCHED(ctx);
             CU(cudaGetLastError());
             if (add) {
@@ -1721,6 +1716,19 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             }
             folded = next;
             len = nlen;
+            round++;
+        }
+        {   // one copy for every root of the phase; the host transcript catches up
+            std::vector<uint32_t> roots((size_t)round * 8);
+            if (round) CU(cudaMemcpyAsync(roots.data(), d_roots, roots.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t r = 0; r < round; r++) {
+                std::array<uint32_t, 8> root;
+                memcpy(root.data(), &roots[8 * r], 32);
+                ch.observe_slice(root.data(), 8);
+                commits.push_back(root);
+                (void)ch.sample_ext();
+            }
         }
         if (it != reduced.end()) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "FRI inputs left over after the commit phase"); }
         std::vector<uint32_t> fin(len * 4);

@@ -208,6 +208,71 @@ __global__ void k_fri_fold(const uint32_t* __restrict__ in, uint32_t* __restrict
     fri_fold_one(in, out, add, log_h, half_beta, tw, i);
 }
 
+// ---- Fiat-Shamir on the device for the rounds that are too big for the tail kernel --------------------------------------------
+// One warp: observe the 8-word root, sample beta (DuplexChallenger<_, _, 16, 8>, same buffer logic as challenger.h).  The
+// challenger lives in device memory (ch[0..16) state, ch[16..24) input buffer, ch[24] its fill), so a commit-phase round is
+// leaf hash -> tree -> this kernel -> fold with NO host round trip; the host replays all roots once at the end.
+__global__ void __launch_bounds__(32) k_challenger_round(uint32_t* __restrict__ ch, const uint32_t* __restrict__ root, uint32_t* __restrict__ beta_out,
+                                                         uint32_t* __restrict__ root_log) {
+    __shared__ uint32_t s_ext[8 * 16], s_int[16], st[16], in[8];
+    const int lane = threadIdx.x, q = lane & 3;
+    for (int k = lane; k < 128; k += 32) s_ext[k] = p2::c_p2.ext_s[k >> 4][k & 15];
+    if (lane < 16) {
+        s_int[lane] = p2::c_p2.internal_s[lane];
+        st[lane] = ch[lane];
+    }
+    if (lane < 8) in[lane] = ch[16 + lane];
+    __syncwarp();
+    const p2::X4 xc = p2::x4_setup(s_ext, s_int, q);
+    uint32_t n_in = ch[24], n_out = 0;
+    auto duplex = [&]() {
+        if ((uint32_t)lane < n_in) st[lane] = in[lane];
+        __syncwarp();
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = st[4 * q + j];
+        p2::permute_x4(w, xc, q);
+        __syncwarp();
+        if (lane < 4) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) st[4 * lane + j] = w[j];
+        }
+        __syncwarp();
+        n_in = 0;
+        n_out = 8;
+    };
+    for (int k = 0; k < 8; k++) {
+        n_out = 0;
+        if (lane == 0) in[n_in] = root[k];
+        n_in++;
+        __syncwarp();
+        if (n_in == 8) duplex();
+    }
+    uint32_t beta[4];
+    for (int k = 0; k < 4; k++) {
+        if (n_in != 0 || n_out == 0) duplex();
+        beta[k] = st[--n_out];
+    }
+    __syncwarp();
+    // after the samples the output buffer still holds n_out words, but the next transcript operation is an observe
+    // (next root or the final polynomial), which discards it: only state, input buffer and its fill are carried
+    if (lane < 16) ch[lane] = st[lane];
+    if (lane < 8) {
+        ch[16 + lane] = in[lane];
+        root_log[lane] = root[lane];
+    }
+    if (lane == 0) ch[24] = n_in;
+    if (lane < 4) beta_out[lane] = beta[lane];
+}
+// fold with beta read from device memory (written by k_challenger_round)
+__global__ void k_fri_fold_dev(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h,
+                               const uint32_t* __restrict__ beta, const uint32_t* __restrict__ tw) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << log_h)) return;
+    const Ext half_beta = kb::ext_scale(ld_ext(beta), kb::halve(kb::ONE));
+    fri_fold_one(in, out, add, log_h, half_beta, tw, i);
+}
+
 // ---- FRI tail: every commit-phase round whose input has at most 2^TAIL_MAX_LOG elements, in ONE single-CTA launch -----
 // Per round the host path costs three launches (fold, leaf hash, tree top), a 32-byte device->host copy, a stream
 // synchronisation and the host sponge — ~60 us of latency for microseconds of work, ten times per proof.  Here one CTA
@@ -222,7 +287,7 @@ struct FriTailArgs {
     uint32_t* layer[TAIL_MAX_ROUNDS][TAIL_MAX_LOG];  // layer[r][l]: 2^(log_len - r - 1 - l) digests, l = 0 .. log_len - r - 1
     uint32_t* roots;                                 // nrounds x 8
     uint32_t log_len, nrounds;
-    uint32_t ch_state[16], ch_in[8], ch_nin;         // challenger at entry (its output buffer is dead: the next operation is an observe)
+    const uint32_t* ch;                              // device challenger at entry: state[16], input[8], n_in (DevChallenger layout)
     const uint32_t* tw;
 };
 __global__ void __launch_bounds__(TAIL_THREADS) k_fri_tail(FriTailArgs A) {
@@ -234,12 +299,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_fri_tail(FriTailArgs A) {
     if (t < 128) s_ext[t] = p2::c_p2.ext_s[t >> 4][t & 15];
     if (t < 16) {
         s_int[t] = p2::c_p2.internal_s[t];
-        ch_st[t] = A.ch_state[t];
+        ch_st[t] = A.ch[t];
     }
-    if (t < 8) ch_in[t] = A.ch_in[t];
+    if (t < 8) ch_in[t] = A.ch[16 + t];
     __syncthreads();
     const p2::X4 xc = p2::x4_setup(s_ext, s_int, q);
-    uint32_t n_in = A.ch_nin, n_out = 0;  // replicated in every lane of warp 0
+    uint32_t n_in = A.ch[24], n_out = 0;  // replicated in every lane of warp 0 (the output buffer is dead: an observe comes next)
     auto duplex = [&]() {                 // warp 0 only, all 32 lanes
         if ((uint32_t)lane < n_in) ch_st[lane] = ch_in[lane];
         __syncwarp();
