@@ -51,3 +51,45 @@ def test_fibo_output_is_pinned_by_the_reference():
 def test_executor_errors(code, stdin, msg):
     with pytest.raises(bf.BfGpuError, match=msg):
         bf.Record(code, stdin, max_cycles=1 << 16)
+
+
+def _random_program(rng, n_ops, depth=0):
+    """Random Brainfuck text with balanced brackets; loops are of the form [-...] so that they terminate quickly."""
+    out = []
+    while n_ops > 0:
+        r = rng.random()
+        if r < 0.12 and depth < 3 and n_ops > 4:
+            body_len = int(rng.integers(1, min(n_ops - 2, 6) + 1))
+            inner = _random_program(rng, body_len, depth + 1)
+            # move away and back inside the body would break termination: keep the loop cell fixed by balancing moves
+            bal = inner.count(">") - inner.count("<")
+            inner += "<" * bal if bal > 0 else ">" * (-bal)
+            out.append("[-" + inner + "]")
+            n_ops -= body_len + 2
+        else:
+            out.append(str(rng.choice(list("+-><.,"), p=[0.3, 0.15, 0.2, 0.15, 0.1, 0.1])))
+            n_ops -= 1
+    return "".join(out)
+
+
+def test_random_programs_match_the_python_executor():
+    """200 random terminating programs (nested loops, pointer wrap-around below cell 0, input and output)."""
+    rng = np.random.default_rng(2024)
+    done = 0
+    for _ in range(400):
+        code = _random_program(rng, int(rng.integers(1, 40)))
+        stdin = [int(rng.integers(0, 256))]
+        try:
+            rec = bf.Record(code, stdin, max_cycles=20000)
+        except bf.BfGpuError as e:
+            assert "cycle limit" in str(e)  # nested decrement loops over 255 can be long: skip those
+            continue
+        ref = ex.execute(ex.Program(code), stdin)
+        assert rec.cycles == ref.cycles and rec.output == ref.output, code
+        cyc = rec.cycle_records().astype(np.int64)
+        if rec.cycles:
+            assert (cyc[:-1, 0] == ref.cpu[:, 1]).all() and (cyc[:-1, 1] == ref.cpu[:, 3]).all(), code
+            assert ((cyc[:-1, 3] & 0xFF) == ref.cpu[:, 5]).all() and (cyc[:-1, 2] == ref.cpu[:, 10]).all(), code
+        assert (rec.memory_events().astype(np.int64).reshape(-1, 5) == ref.memory.reshape(-1, 5)).all(), code
+        done += 1
+    assert done >= 200

@@ -156,3 +156,32 @@ def test_e2e_core_through_the_sdk_facade():
     other_pk, other_vk = client.setup(_code("hello.bf"))
     proof = client.prove(pk, [17]).run()
     assert client.verify(proof, other_vk) is not None  # verifying key of a different program
+
+
+def test_random_programs_device_traces(ctx):
+    """Random terminating programs (nested loops, pointer wrap-around, input/output): every device-generated trace equals
+    the numpy restatement and the device commitment equals the commitment of the host traces."""
+    from tests.test_executor_parity import _random_program
+    rng = np.random.default_rng(77)
+    prover = bf.CudaProver(ctx)
+    done = 0
+    while done < 25:
+        code = _random_program(rng, int(rng.integers(1, 60)))
+        stdin = [int(rng.integers(0, 256))]
+        try:
+            rec = prover.execute(code, stdin)
+        except bf.BfGpuError:
+            continue
+        if rec.cycles == 0 or rec.cycles > 50000:
+            continue
+        ref = tg.generate_traces(ex.execute(ex.Program(code), stdin))
+        shard = prover.commit_record(rec)
+        got = prover.shard_traces(shard)
+        assert sorted(got) == sorted(ref), code
+        for name in ref:
+            assert got[name].shape == ref[name].shape and (got[name] == ref[name]).all(), (code, name)
+        host = prover.commit(ref)
+        assert (shard.commit == host.commit).all(), code
+        shard.free()
+        host.free()
+        done += 1
