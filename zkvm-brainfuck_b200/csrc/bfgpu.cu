@@ -518,9 +518,14 @@ static void prestage_clear(bfgpu_ctx* ctx) {
 // row-major device words in the caller's representation -> column-major Montgomery words at dst
 static int32_t ingest_device(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows, uint32_t cols, bool bitrev, uint32_t* dst, uint64_t src_pitch = 0) {
     Phase ph(ctx, BFGPU_PHASE_INGEST);
-    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
-    nttk::k_ingest<<<grid, block, 0, ctx->stream>>>(src, dst, rows, cols, ilog2(rows), bitrev ? 1 : 0, ctx->repr == BFGPU_REPR_CANONICAL,
-                                                     src_pitch ? src_pitch : cols);
+    const uint64_t pitch = src_pitch ? src_pitch : cols;
+    if (rows >= 128 && rows % 128 == 0 && cols % 4 == 0 && pitch % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+        dim3 grid((unsigned)(rows / 128), (unsigned)((cols + 31) / 32));
+        nttk::k_ingest_wide<<<grid, 256, 0, ctx->stream>>>(src, dst, rows, cols, ilog2(rows), bitrev ? 1 : 0, ctx->repr == BFGPU_REPR_CANONICAL, pitch);
+    } else {
+        dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
+        nttk::k_ingest<<<grid, block, 0, ctx->stream>>>(src, dst, rows, cols, ilog2(rows), bitrev ? 1 : 0, ctx->repr == BFGPU_REPR_CANONICAL, pitch);
+    }
     LAUNCHED(ctx);
     CU(cudaGetLastError());
     return BFGPU_OK;
