@@ -1766,9 +1766,12 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             TRY(dalloc(ctx, (void**)&d_st, 64));
             TRY(dalloc(ctx, (void**)&d_best, 4));
             TRY(upload_small(ctx, d_st, st, 64));
-            const uint32_t batch = 1u << 20, mask = (1u << ctx->pow_bits) - 1;
+            // batches in increasing order keep "the smallest witness"; the first one covers 4x the expected search length
+            // (2^bits candidates on average), the following ones are bigger
+            const uint32_t mask = (1u << ctx->pow_bits) - 1;
+            uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(4ull << ctx->pow_bits, 1u << 14), 1u << 22);
             unsigned int best = 0xffffffffu;
-            for (uint64_t start = 0; start < kb::P && best == 0xffffffffu; start += batch) {
+            for (uint64_t start = 0; start < kb::P && best == 0xffffffffu; start += batch, batch = std::min<uint64_t>(batch * 4, 1u << 24)) {
                 TRY(upload_small(ctx, d_best, &best, 4));
                 uint32_t count = (uint32_t)std::min<uint64_t>(batch, kb::P - start);
                 openk::k_pow_grind<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_st, pos, mask, (uint32_t)start, count, d_best);
