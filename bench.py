@@ -80,6 +80,8 @@ def cpu_commit_sample(log_rows, cols, steps, warmup):
     import numpy as np
     import oracle
 
+    # every host thread, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    oracle.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     rng = np.random.default_rng(0xB200)
     m = rng.integers(0, P, (1 << log_rows, cols), dtype=np.uint32)
     times = []

@@ -178,6 +178,10 @@ static void trim_cache(bfgpu_ctx* ctx) {
 }
 static int32_t dalloc(bfgpu_ctx* ctx, void** p, size_t bytes) {
     *p = nullptr;
+    // every compute entry point allocates before it launches: make the context's device current here, so that a process
+    // holding contexts on several devices (or calling from a fresh thread) launches on the right one
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) CU(cudaSetDevice(ctx->device));
     bytes = (std::max<size_t>(bytes, 4) + 255) & ~(size_t)255;
     auto it = ctx->free_blocks.find(bytes);
     if (it != ctx->free_blocks.end()) {
