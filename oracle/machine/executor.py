@@ -1,6 +1,7 @@
-"""Brainfuck compiler + interpreter emitting the event streams the chips' traces are built from.
-
-Host-side input generation (not accelerated: a sequential interpreter).  Restates the reference's
+"""TEST INFRASTRUCTURE (part of the CPU oracle; PARITY UNPINNED like the rest of it): Brainfuck compiler + interpreter
+emitting the event streams the chips' traces are built from.  The product's executor is the native one behind
+`bfgpu_execute` (csrc/tracegen.cuh); this Python restatement is what it is tested against and what feeds the numpy prover.
+  Restates the reference's
 `Program::from` (crates/core/executor/src/program.rs:22-44) and `Executor::{run, execute_instruction,
 emit_events, rr_traced, rw_traced}` (crates/core/executor/src/executor.rs:71-79,106-325), including its quirks:
 `+` and `-` both land in `add_events` (:219-226), `,` never advances the input pointer (:183), a jump event's

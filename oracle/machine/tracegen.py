@@ -1,6 +1,6 @@
-"""Trace generation for the eight chips (numpy, vectorised over events).
-
-Host-side input generation.  Restates the reference's `MachineAir::generate_trace` /
+"""TEST INFRASTRUCTURE (part of the CPU oracle; PARITY UNPINNED like the rest of it): trace generation for the eight
+chips (numpy, vectorised over events).  The product generates the traces on the device (csrc/tracegen.cuh); this is the
+restatement it is tested against.  Restates the reference's `MachineAir::generate_trace` /
 `generate_preprocessed_trace` / `generate_dependencies` of every chip:
   Cpu cpu/trace.rs:28-150 (+ memory/consistency/trace.rs:9-77), Program program/mod.rs:64-137,
   AddSub alu/mod.rs:62-157 (+ operations/add.rs:21-40), Jump jump/trace.rs:31-96
@@ -11,7 +11,9 @@ everything else to >= 16 rows).  All values are canonical residues (uint32).
 """
 import numpy as np
 
-from ..air import chips as C
+import importlib
+
+C = importlib.import_module("zkvm-brainfuck_b200.air.chips")  # the declarative AIR (layouts, opcodes) is shared with the code generator
 
 P = 2130706433
 

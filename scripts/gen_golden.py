@@ -21,8 +21,8 @@ import oracle  # noqa: E402
 from oracle import prover as PR, stark as S  # noqa: E402
 
 P = 2130706433
-ex = importlib.import_module("zkvm-brainfuck_b200.machine.executor")
-tg = importlib.import_module("zkvm-brainfuck_b200.machine.tracegen")
+ex = importlib.import_module("oracle.machine.executor")
+tg = importlib.import_module("oracle.machine.tracegen")
 chips = importlib.import_module("zkvm-brainfuck_b200.air.chips").machine_chips()
 GOLD = os.path.join(ROOT, "tests", "golden")
 

@@ -1,5 +1,5 @@
 """Native executor (`bfgpu_execute`, csrc/tracegen.cuh) against the Python restatement of the reference's
-`Program::from` / `Executor::run` (zkvm-brainfuck_b200/machine/executor.py; reference crates/core/executor/src/
+`Program::from` / `Executor::run` (oracle/machine/executor.py; reference crates/core/executor/src/
 program.rs:22-44, executor.rs:71-79,106-325) on the reference's own test programs.  Runs without a GPU: with no
 context the cycle records live in ordinary host memory."""
 import importlib
@@ -10,7 +10,7 @@ import pytest
 
 import zkvm_brainfuck_b200 as bf
 
-ex = importlib.import_module("zkvm-brainfuck_b200.machine.executor")
+ex = importlib.import_module("oracle.machine.executor")
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PROGRAMS = [("++-.", []), (">><", []), ("[----]", []), (",.", [7]), ("++[>+<-]>.", []), ("<+>+", []), ("loop.bf", []), ("move.bf", []),
             ("printa.bf", []), ("hello.bf", []), ("fibo.bf", [17]), ("-[>-[>+>+>+<<<-]<-]", [])]

@@ -27,8 +27,8 @@ def ctx():
 @pytest.fixture(scope="module")
 def env(oracle):
     from oracle import prover as PR, stark as S
-    ex = importlib.import_module("zkvm-brainfuck_b200.machine.executor")
-    tg = importlib.import_module("zkvm-brainfuck_b200.machine.tracegen")
+    ex = importlib.import_module("oracle.machine.executor")
+    tg = importlib.import_module("oracle.machine.tracegen")
     chips = importlib.import_module("zkvm-brainfuck_b200.air.chips").machine_chips()
     return PR, S, ex, tg, chips
 

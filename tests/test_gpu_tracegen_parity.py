@@ -1,6 +1,6 @@
 """Device-side trace generation (csrc/tracegen.cuh: `bfgpu_machine_commit_record`) against the numpy restatement of the
 reference's `MachineAir::generate_trace` implementations and `generate_dependencies`
-(zkvm-brainfuck_b200/machine/tracegen.py; reference files cited there): every chip's main trace word for word, the
+(oracle/machine/tracegen.py; reference files cited there): every chip's main trace word for word, the
 main commitment, and the whole proof from `prove_program` equal to the proof obtained from host traces (which
 tests/test_gpu_prove_parity.py pins against the oracle prover and verifier)."""
 import importlib
@@ -13,8 +13,8 @@ import zkvm_brainfuck_b200 as bf
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ex = importlib.import_module("zkvm-brainfuck_b200.machine.executor")
-tg = importlib.import_module("zkvm-brainfuck_b200.machine.tracegen")
+ex = importlib.import_module("oracle.machine.executor")
+tg = importlib.import_module("oracle.machine.tracegen")
 
 PROGRAMS = [("++-.", []), (">><", []), ("[----]", []), (",.", [7]), ("++[>+<-]>.", []), ("<+>+", []), ("loop.bf", []), ("move.bf", []),
             ("printa.bf", []), ("hello.bf", []), ("fibo.bf", [17]), ("-[>-[>+>+>+<<<-]<-]", []), ("+>" * 3000 + ",.", [255])]

@@ -10,8 +10,8 @@ import pytest
 import zkvm_brainfuck_b200 as bf
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ex = importlib.import_module("zkvm-brainfuck_b200.machine.executor")
-tg = importlib.import_module("zkvm-brainfuck_b200.machine.tracegen")
+ex = importlib.import_module("oracle.machine.executor")
+tg = importlib.import_module("oracle.machine.tracegen")
 chips = importlib.import_module("zkvm-brainfuck_b200.air.chips").machine_chips()
 FRI = (1, 10, 5)
 

@@ -9,8 +9,8 @@ import numpy as np
 import pytest
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ex = importlib.import_module("zkvm-brainfuck_b200.machine.executor")
-tg = importlib.import_module("zkvm-brainfuck_b200.machine.tracegen")
+ex = importlib.import_module("oracle.machine.executor")
+tg = importlib.import_module("oracle.machine.tracegen")
 chips_mod = importlib.import_module("zkvm-brainfuck_b200.air.chips")
 
 

@@ -13,8 +13,8 @@ import numpy as np
 
 import zkvm_brainfuck_b200 as bf
 
-ex = importlib.import_module("zkvm-brainfuck_b200.machine.executor")
-tg = importlib.import_module("zkvm-brainfuck_b200.machine.tracegen")
+ex = importlib.import_module("oracle.machine.executor")
+tg = importlib.import_module("oracle.machine.tracegen")
 GOLD = os.path.join(ROOT, "tests", "golden")
 PROGRAMS = {
     "fibo": (open(os.path.join(GOLD, "fibo.bf")).read(), [17]),      # BASELINE config 1 (test_e2e_core)

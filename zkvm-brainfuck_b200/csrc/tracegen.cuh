@@ -15,8 +15,8 @@
 //   k_classify + prefix scan + k_index : event index lists of the AddSub / Jump / MemoryInstrs / IO chips
 //   k_byte_hist                        : u8 / u16 lookup multiplicities (shared-memory privatised histograms)
 //   k_*_trace                          : one thread per stored row; reads its cycle record(s), writes its row coalesced
-// Parity: tests/test_gpu_tracegen_parity.py compares every generated trace with the numpy restatement
-// (zkvm-brainfuck_b200/machine/tracegen.py) and the resulting proofs word for word.
+// Parity: tests/test_gpu_tracegen_parity.py compares every generated trace with the numpy restatement of the reference's
+// generators and the resulting proofs word for word.
 #pragma once
 #include <unordered_map>
 
