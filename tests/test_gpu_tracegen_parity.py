@@ -16,7 +16,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ex = importlib.import_module("oracle.machine.executor")
 tg = importlib.import_module("oracle.machine.tracegen")
 
-PROGRAMS = [("++-.", []), (">><", []), ("[----]", []), (",.", [7]), ("++[>+<-]>.", []), ("<+>+", []), ("loop.bf", []), ("move.bf", []),
+PROGRAMS = [("+", []), ("+.", []), ("++-.", []), (">><", []), ("[----]", []), (",.", [7]), ("++[>+<-]>.", []), ("<+>+", []), ("loop.bf", []), ("move.bf", []),
             ("printa.bf", []), ("hello.bf", []), ("fibo.bf", [17]), ("-[>-[>+>+>+<<<-]<-]", []), ("+>" * 3000 + ",.", [255])]
 
 

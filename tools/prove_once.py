@@ -4,7 +4,6 @@ import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import zkvm_brainfuck_b200 as bf
-pb = importlib.import_module("tools.prove_bench") if False else None
 ex = importlib.import_module("oracle.machine.executor")
 tg = importlib.import_module("oracle.machine.tracegen")
 PROGRAMS = {"fibo": (open(os.path.join(ROOT, "tests/golden/fibo.bf")).read(), [17]), "hello": (open(os.path.join(ROOT, "tests/golden/hello.bf")).read(), []),
