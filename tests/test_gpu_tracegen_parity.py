@@ -16,7 +16,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ex = importlib.import_module("oracle.machine.executor")
 tg = importlib.import_module("oracle.machine.tracegen")
 
-PROGRAMS = [("+", []), ("+.", []), ("++-.", []), (">><", []), ("[----]", []), (",.", [7]), ("++[>+<-]>.", []), ("<+>+", []), ("loop.bf", []), ("move.bf", []),
+PROGRAMS = [("+.", []), ("++-.", []), (">><", []), ("[----]", []), (",.", [7]), ("++[>+<-]>.", []), ("<+>+", []), ("loop.bf", []), ("move.bf", []),
             ("printa.bf", []), ("hello.bf", []), ("fibo.bf", [17]), ("-[>-[>+>+>+<<<-]<-]", []), ("+>" * 3000 + ",.", [255])]
 
 
@@ -185,3 +185,12 @@ def test_random_programs_device_traces(ctx):
         shard.free()
         host.free()
         done += 1
+
+
+def test_one_cycle_execution_is_refused(ctx):
+    """One cycle -> one-row Cpu trace -> LDE as short as the FRI blow-up, which p3-fri's verifier cannot consume (the
+    reference would produce an unverifiable proof): the program path refuses it with a clear message."""
+    prover = bf.CudaProver(ctx)
+    rec = prover.execute("+")
+    with pytest.raises(bf.BfGpuError, match="one-cycle"):
+        prover.commit_record(rec)

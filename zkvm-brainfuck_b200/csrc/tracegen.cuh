@@ -537,6 +537,10 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
     *out = nullptr;
     const uint32_t n = (uint32_t)rec->n_cycles, n_instr = (uint32_t)rec->ops.size(), n_cells = (uint32_t)(rec->mem_events.size() / 5);
     if (n == 0) return fail(ctx, BFGPU_ERR_INVALID, "empty execution");
+    // The Cpu trace is padded to a power of two with no minimum (utils/mod.rs:25-53): one cycle gives a ONE-row trace whose
+    // LDE is as short as the FRI blow-up, and p3-fri's verifier never consumes a reduced opening of that height — the
+    // reference would emit an unverifiable proof.  Refuse instead.
+    if (n == 1) return fail(ctx, BFGPU_ERR_INVALID, "a one-cycle execution cannot be proven: its one-row Cpu trace is below the FRI verifier's minimum height");
     // ---- inputs to the device ----
     Scratch scratch(ctx);  // inputs and index lists: back to the block cache on every exit path
     uint4 *d_cyc = nullptr, *d_flags = nullptr;
