@@ -1727,9 +1727,11 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             len = nlen;
             round++;
         }
-        {   // one copy for every root of the phase; the host transcript catches up
+        std::vector<uint32_t> fin(len * 4);
+        {   // one copy for every root of the phase (and the final vector); the host transcript catches up
             std::vector<uint32_t> roots((size_t)round * 8);
             if (round) CU(cudaMemcpyAsync(roots.data(), d_roots, roots.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(fin.data(), folded, len * 16, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             for (uint32_t r = 0; r < round; r++) {
                 std::array<uint32_t, 8> root;
@@ -1740,9 +1742,6 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             }
         }
         if (it != reduced.end()) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "FRI inputs left over after the commit phase"); }
-        std::vector<uint32_t> fin(len * 4);
-        CU(cudaMemcpyAsync(fin.data(), folded, len * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
         dfree(ctx, folded);
         for (uint64_t i = 1; i < len; i++)
             if (memcmp(&fin[0], &fin[4 * i], 16)) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "FRI final layer is not constant: a committed matrix is not low-degree"); }
@@ -2056,6 +2055,9 @@ extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const 
     // ---- permutation traces (prover.rs:280-296 -> permutation.rs:75-148) --------------------------------------------
     std::vector<DMat> perm(nchips);
     std::vector<kb::Ext> csum(nchips);
+    Scratch csum_scratch(ctx);
+    uint32_t* d_csums = nullptr;
+    TRY(csum_scratch.alloc((void**)&d_csums, nchips * 16));
     {
         Phase ph(ctx, BFGPU_PHASE_PERM);
         for (size_t i = 0; i < nchips; i++) {
@@ -2082,10 +2084,12 @@ extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const 
                 (const uint4*)rowsum, n, nullptr, log_n, perm[i].d + (uint64_t)4 * (ci.perm_w - 1) * n);
             LAUNCHED(ctx);
             CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(csum[i].c, rowsum + 4 * (n - 1), 16, cudaMemcpyDeviceToHost, ctx->stream));
+            // cumulative sum = last running total: parked on the device, fetched with ONE copy after the permutation commit
+            // (a device->host copy into pageable memory blocks the host: eight of them plus a synchronisation cost more than
+            // the kernels of a small proof)
+            CU(cudaMemcpyAsync(d_csums + 4 * i, rowsum + 4 * (n - 1), 16, cudaMemcpyDeviceToDevice, ctx->stream));
             dfree(ctx, rowsum);  // stream-ordered reuse: the copy above is enqueued before any later writer
         }
-        CU(cudaStreamSynchronize(ctx->stream));
     }
     bfgpu_pcs_data* perm_data = nullptr;
     uint32_t perm_root[8];
@@ -2098,6 +2102,7 @@ extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const 
         ~Cleanup() { bfgpu_pcs_data_free(a); bfgpu_pcs_data_free(b); }
     } cleanup;
     cleanup.a = perm_data;
+    CU(cudaMemcpy(csum.data(), d_csums, nchips * 16, cudaMemcpyDeviceToHost));  // the stream is idle: the commit just returned its root
     ch.observe_slice(perm_root, 8);
     for (size_t i = 0; i < nchips; i++) ch.observe_ext(csum[i]);
 
@@ -2160,8 +2165,7 @@ extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const 
             dfree(ctx, q);
             (void)ci;
         }
-        CU(cudaStreamSynchronize(ctx->stream));
-        dfree(ctx, d_apow);
+        dfree(ctx, d_apow);  // stream order keeps it alive for the kernels above; no host synchronisation needed
     }
     bfgpu_pcs_data* quot_data = nullptr;
     uint32_t quot_root[8];
