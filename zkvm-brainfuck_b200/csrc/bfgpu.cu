@@ -1483,7 +1483,7 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
             uint32_t* partial = nullptr;
             size_t nsum = (size_t)m.cols * jb.np * 4;
             TRY(dalloc(ctx, (void**)&partial, nsum * nchunks * 4));
-            dim3 grid(nchunks, (m.cols + openk::BARY_COLS - 1) / openk::BARY_COLS);
+            dim3 grid((m.cols + openk::BARY_COLS - 1) / openk::BARY_COLS, nchunks);
             if (jb.np == 1) openk::k_bary_dot<1><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(m.d, m.rows, m.cols, h, w0, w1, partial, nchunks);
             else openk::k_bary_dot<2><<<grid, openk::BARY_THREADS, 0, ctx->stream>>>(m.d, m.rows, m.cols, h, w0, w1, partial, nchunks);
             LAUNCHED(ctx);

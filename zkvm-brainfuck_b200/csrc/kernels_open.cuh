@@ -105,7 +105,9 @@ template <int NP>
 __global__ void __launch_bounds__(BARY_THREADS) k_bary_dot(const uint32_t* __restrict__ mat, uint64_t col_stride, uint32_t ncols, uint32_t h,
                                                            const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
                                                            uint32_t* __restrict__ partial, uint32_t nchunks) {
-    bary_dot_body<NP>(mat, col_stride, ncols, h, w0, w1, partial, nchunks, blockIdx.x, blockIdx.y * BARY_COLS);
+    // column group is the FAST grid index: the blocks in flight share a row chunk, so its weights (2 x 16 B per row, two thirds of
+    // the kernel's traffic when every column group re-read them from DRAM) are served by L2
+    bary_dot_body<NP>(mat, col_stride, ncols, h, w0, w1, partial, nchunks, blockIdx.y, blockIdx.x * BARY_COLS);
 }
 // every matrix whose low coset fits one chunk (h <= BARY_ROWS), in one launch: blockIdx.y = job, blockIdx.x = column group;
 // with a single chunk the partial sums ARE the sums, written straight to their final place
