@@ -101,8 +101,11 @@ __device__ __forceinline__ void bary_dot_body(const uint32_t* __restrict__ mat, 
     }
 }
 
+#ifndef BFGPU_BARY_MINBLOCKS
+#define BFGPU_BARY_MINBLOCKS 1  // forcing 3 or 4 CTAs/SM spills the 64-bit accumulators: open_eval 2.69 -> 3.26 / 5.0 ms at 2^22 rows
+#endif
 template <int NP>
-__global__ void __launch_bounds__(BARY_THREADS) k_bary_dot(const uint32_t* __restrict__ mat, uint64_t col_stride, uint32_t ncols, uint32_t h,
+__global__ void __launch_bounds__(BARY_THREADS, BFGPU_BARY_MINBLOCKS) k_bary_dot(const uint32_t* __restrict__ mat, uint64_t col_stride, uint32_t ncols, uint32_t h,
                                                            const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
                                                            uint32_t* __restrict__ partial, uint32_t nchunks) {
     // column group is the FAST grid index: the blocks in flight share a row chunk, so its weights (2 x 16 B per row, two thirds of
