@@ -79,7 +79,21 @@ KB_HD uint32_t pow(uint32_t a_mont, uint64_t e) {
     }
     return r;
 }
-KB_HD uint32_t inv(uint32_t a_mont) { return pow(a_mont, (uint64_t)P - 2); }
+// a^(p-2) by a fixed addition chain: p - 2 = 2^31 - 2^24 - 1 = (2^6 - 1) * 2^25 + (2^24 - 1), so with x_k = a^(2^k - 1)
+// (x2, x3, x6, x12, x24 by doubling) the inverse is x6^(2^25) * x24: 48 squarings + 6 products, no data-dependent branch
+// (the generic square-and-multiply ladder takes 31 + 30 with a loop and a branch per bit).
+KB_HD uint32_t sqr_n(uint32_t a, int n) {
+    for (int i = 0; i < n; i++) a = sqr(a);
+    return a;
+}
+KB_HD uint32_t inv(uint32_t a) {
+    uint32_t x2 = mul(sqr(a), a);
+    uint32_t x3 = mul(sqr(x2), a);
+    uint32_t x6 = mul(sqr_n(x3, 3), x3);
+    uint32_t x12 = mul(sqr_n(x6, 6), x6);
+    uint32_t x24 = mul(sqr_n(x12, 12), x12);
+    return mul(sqr_n(x6, 25), x24);
+}
 // generator of the order-2^bits subgroup, Montgomery form: 3^((p-1)/2^bits)
 KB_HD uint32_t two_adic_generator(unsigned bits) { return pow(to_mont(GEN), (uint64_t)(P - 1) >> bits); }
 
