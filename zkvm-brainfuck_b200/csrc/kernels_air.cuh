@@ -171,9 +171,12 @@ __global__ void __launch_bounds__(128, BFGPU_QUOT_MINBLOCKS) k_quotient(Quotient
     const uint32_t x = kb::mul(A.shift, root_pow_(A.tw, L, i));
     const uint32_t zh = A.zh[i & ((1u << A.lqd) - 1)], zh_inv = A.zh_inv[i & ((1u << A.lqd) - 1)];
     Selectors sel;
-    sel.is_first = kb::mul(zh, kb::inv(kb::sub(x, kb::ONE)));
-    sel.is_last = kb::mul(zh, kb::inv(kb::sub(x, A.g_inv)));
-    sel.is_trans = kb::sub(x, A.g_inv);
+    // 1/(x - 1) and 1/(x - g^-1) with one inversion (x runs over a coset disjoint from the trace domain: neither is zero)
+    const uint32_t d_first = kb::sub(x, kb::ONE), d_last = kb::sub(x, A.g_inv);
+    const uint32_t ip = kb::mul(zh, kb::inv(kb::mul(d_first, d_last)));
+    sel.is_first = kb::mul(ip, d_last);
+    sel.is_last = kb::mul(ip, d_first);
+    sel.is_trans = d_last;
     kb::Ext acc = kb::ext_zero();
     air_constraints(CHIP, ld, sel, ch, A.apow, acc);
     acc = kb::ext_scale(acc, zh_inv);

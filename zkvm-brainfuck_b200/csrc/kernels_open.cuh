@@ -159,11 +159,24 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= (1u << log_h)) return;
     uint32_t x = kb::mul(shift, root_pow(tw, log_h, kb::bitrev(r, log_h)));
-    Ext inv[4];
-    for (uint32_t t = 0; t < npts && t < 4; t++) {
+    // 1 / (z_t - x) for the (at most four) opening points of this height: Montgomery's trick, ONE extension inversion per row
+    // (an inversion is ~1 200 instructions, an extension product ~140; the two inversions were 60 % of this kernel)
+    Ext inv[4], pre[4];
+    const uint32_t np = npts < 4 ? npts : 4;
+    for (uint32_t t = 0; t < np; t++) {
         Ext d = ld_ext(zs + 4 * t);
         d.c[0] = kb::sub(d.c[0], x);
-        inv[t] = kb::ext_inv(d);
+        inv[t] = d;
+        pre[t] = t ? kb::ext_mul(pre[t - 1], d) : d;
+    }
+    if (np) {
+        Ext acc_inv = kb::ext_inv(pre[np - 1]);
+        for (uint32_t t = np; t-- > 1;) {
+            Ext d = inv[t];
+            inv[t] = kb::ext_mul(acc_inv, pre[t - 1]);
+            acc_inv = kb::ext_mul(acc_inv, d);
+        }
+        inv[0] = acc_inv;
     }
     Ext acc = kb::ext_zero();
     for (uint32_t m = 0; m < nmats; m++) {
