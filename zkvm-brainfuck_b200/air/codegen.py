@@ -163,20 +163,25 @@ def gen_chip(chip, index):
         for i, (lk, is_send) in enumerate(chunk):
             r, m = _emit_rlc(em, lk, f"{j}_{i}")
             terms.append((r, m, is_send))
-        em.emit("{")
+        # batch value = num / den:  +-m0/r0 +- m1/r1 = (+-m0 r1 +- m1 r0) / (r0 r1);  a single lookup is +-m / r
         if len(terms) == 2:
-            # +-m0/r0 +- m1/r1 = (+-m0 r1 +- m1 r0) / (r0 r1): one extension inversion per batch instead of two
             (r0, m0, s0), (r1, m1, s1) = terms
-            em.emit("    kb::ExtAcc num = kb::ext_acc_zero();")
-            em.emit(f"    kb::ext_mac(num, {r1}, {m0 if s0 else f'kb::neg({m0})'});")
-            em.emit(f"    kb::ext_mac(num, {r0}, {m1 if s1 else f'kb::neg({m1})'});")
-            em.emit(f"    out[{j}] = kb::ext_mul(kb::ext_acc_reduce(num), kb::ext_inv(kb::ext_mul({r0}, {r1})));")
+            em.emit(f"kb::ExtAcc nacc_{j} = kb::ext_acc_zero();")
+            em.emit(f"kb::ext_mac(nacc_{j}, {r1}, {m0 if s0 else f'kb::neg({m0})'});")
+            em.emit(f"kb::ext_mac(nacc_{j}, {r0}, {m1 if s1 else f'kb::neg({m1})'});")
+            em.emit(f"const kb::Ext num_{j} = kb::ext_acc_reduce(nacc_{j}), den_{j} = kb::ext_mul({r0}, {r1});")
         else:
-            em.emit("    kb::Ext s = kb::ext_zero();")
-            for r, m, is_send in terms:
-                em.emit(f"    s = kb::ext_{'add' if is_send else 'sub'}(s, kb::ext_scale(kb::ext_inv({r}), {m}));")
-            em.emit(f"    out[{j}] = s;")
-        em.emit("}")
+            (r0, m0, s0), = terms
+            em.emit(f"const kb::Ext num_{j} = kb::ext_from_base({m0 if s0 else f'kb::neg({m0})'}), den_{j} = {r0};")
+        # Montgomery's trick over PAIRS of batches: one extension inversion (~1 200 instructions) per two batches
+        if j % 2 == 1:
+            em.emit("{")
+            em.emit(f"    const kb::Ext ip = kb::ext_inv(kb::ext_mul(den_{j - 1}, den_{j}));")
+            em.emit(f"    out[{j - 1}] = kb::ext_mul(num_{j - 1}, kb::ext_mul(ip, den_{j}));")
+            em.emit(f"    out[{j}] = kb::ext_mul(num_{j}, kb::ext_mul(ip, den_{j - 1}));")
+            em.emit("}")
+        elif j == chip.perm_width - 2:
+            em.emit(f"out[{j}] = kb::ext_mul(num_{j}, kb::ext_inv(den_{j}));")
     out.append(f"template <class L>\n__device__ __forceinline__ void air_perm_row_{name}(const L& ld, const Challenges& ch, kb::Ext* out) {{")
     out += em.lines
     out.append("}")
