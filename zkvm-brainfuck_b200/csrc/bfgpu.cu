@@ -84,6 +84,9 @@ struct bfgpu_ctx {
     uint8_t* ring = nullptr;
     size_t ring_size = 0, ring_pos = 0;
     uint64_t x4_layer_max = 1u << 15;  // Merkle layers up to this many nodes use k_compress_layer_x4 ($BFGPU_X4_MAX)
+    // opening points evaluated per pass over a matrix; one pass per point ($BFGPU_BARY_POINTS=1, 66 instead of 110 registers but the
+    // matrix read twice) measured slower: open_eval 2.91 vs 2.51 ms at 2^22 rows
+    uint32_t bary_points_per_pass = 2;
     bool fri_tail = true;  // small FRI rounds in one single-CTA launch (openk::k_fri_tail); $BFGPU_FRI_TAIL=0 disables
     bool overlap_device = false;
     int pipe_tail_splits = 1;  // $BFGPU_PIPE_SPLITS
@@ -273,6 +276,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (const char* e = getenv("BFGPU_PIPE_COLS")) ctx->pipe_cols = (uint32_t)atoi(e) / 8 * 8;
     if (const char* e = getenv("BFGPU_OVERLAP")) ctx->overlap_device = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_FRI_TAIL")) ctx->fri_tail = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_BARY_POINTS")) ctx->bary_points_per_pass = atoi(e) == 1 ? 1 : 2;
     if (const char* e = getenv("BFGPU_X4_MAX")) ctx->x4_layer_max = strtoull(e, nullptr, 10);
     if (const char* e = getenv("BFGPU_PIPE_SPLITS")) ctx->pipe_tail_splits = atoi(e);
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
@@ -1458,8 +1462,8 @@ extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds
         size_t total_words = 0;
         for (auto& rv : R)
             for (auto& mp : rv)
-                for (size_t t0 = 0; t0 < mp.pts.size(); t0 += 2) {
-                    uint32_t np = (uint32_t)std::min<size_t>(2, mp.pts.size() - t0);
+                for (size_t t0 = 0; t0 < mp.pts.size(); t0 += ctx->bary_points_per_pass) {
+                    uint32_t np = (uint32_t)std::min<size_t>(ctx->bary_points_per_pass, mp.pts.size() - t0);
                     jobs.push_back({&mp, t0, np, total_words});
                     total_words += (size_t)mp.m->cols * np * 4;
                 }
