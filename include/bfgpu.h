@@ -75,6 +75,10 @@ int32_t bfgpu_synchronize(bfgpu_ctx* ctx);
 int32_t bfgpu_set_fri_params(bfgpu_ctx* ctx, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits);
 /* number of this library's kernels launched on the context since creation (bench evidence) */
 uint64_t bfgpu_launch_count(const bfgpu_ctx* ctx);
+/* test hooks for the error paths: number of device blocks the context currently has handed out, and "the nth device allocation
+ * from now fails with BFGPU_ERR_OOM" (nth < 0 disarms).  A failed entry point must leave live_blocks where it found it. */
+uint64_t bfgpu_debug_live_blocks(const bfgpu_ctx* ctx);
+int32_t bfgpu_debug_fail_alloc(bfgpu_ctx* ctx, int64_t nth);
 
 /* page-locked host memory for caller matrices: cudaMemcpyAsync from pageable memory is staged by the driver at
  * ~11 GB/s, from pinned memory it runs at PCIe speed (~55 GB/s measured).  Trace generators should write

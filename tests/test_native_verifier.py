@@ -195,3 +195,41 @@ def test_out_of_domain_check_and_cumulative_sums(oracle):
     eo = PR.verify_shard(chips, vk, proof, ch.clone(), cfg)
     ev = bf.verify_shard(pk.commit, pk.names, heights, serialize(proof, pk.names), *FRI)
     assert eo == "CumulativeSumsError" and ev == eo
+
+
+def test_rejects_hostile_shapes_and_noncanonical_words(hello):
+    """Untrusted 32-bit shape words must not wrap the range checks (log_degree = 2^32 - 1 once passed `ld + blowup > 24`),
+    a field word >= p is a second encoding of the same proof and is refused, and a verifying key without preprocessed
+    matrices is a shape error, not an out-of-bounds read."""
+    PR, S, pk, vk, proof, words = hello
+    n = len(proof["opened_values"])
+    for ld in (0xFFFFFFFF, 0xFFFFFFF0, 24, 200):
+        bad = words.copy()
+        bad[24 + 1 + 1] = ld  # log_degree of the first chip
+        assert "InvalidProofShape" in native(pk, bad)
+    head = 24 + 1 + 6 * n
+    nc = len(proof["opening_proof"]["commit_phase_commits"])
+    # number of FRI commit-phase commitments: the word right before nc * 8 digest words, final poly, witness, query count
+    cand = [i for i in range(head, len(words) - 8 * nc - 6) if int(words[i]) == nc and int(words[i + 8 * nc + 6]) == FRI[1]]
+    assert cand
+    for v in (0xFFFFFFFF, 24, 0):
+        bad = words.copy()
+        bad[cand[0]] = v
+        assert native(pk, bad) is not None
+    # non-canonical encodings: same residue, different word
+    bad = words.copy()
+    assert int(bad[0]) + bf.P < 2 ** 32
+    bad[0] = int(bad[0]) + bf.P  # first word of the main commitment
+    assert native(pk, bad) is not None
+    bad = words.copy()
+    bad[head] = int(bad[head]) + bf.P if int(bad[head]) + bf.P < 2 ** 32 else bad[head]
+    if int(bad[head]) != int(words[head]):
+        assert native(pk, bad) is not None
+    com = np.asarray(pk.commit, np.uint64).copy()
+    com[0] += bf.P
+    assert bf.verify_shard(com.astype(np.uint32), pk.names, [t.shape[0] for t in pk.traces], words, *FRI) is not None
+    # no preprocessed matrices at all / an absurd preprocessed height
+    e = bf.verify_shard(pk.commit, [], [], words, *FRI)
+    assert e is not None and "InvalidProofShape" in e
+    e = bf.verify_shard(pk.commit, pk.names, [1 << 40 for _ in pk.traces], words, *FRI)
+    assert e is not None

@@ -74,16 +74,26 @@ int main() {
     h_buf = (uint32_t*)malloc(n * 4);
     run<Base>("baseline (poseidon2.cuh rolled)", d, n);
     //            rc  m4 sum out isum iout lazy shoup
-    run<Perm<Cfg<0, 0, 0, 0, 0, 0, false, false>>>("variant, no forcing", d, n);
-    run<Perm<Cfg<0, 0, 0, 0, 0, 0, true, false>>>("lazy sbox", d, n);
-    run<Perm<Cfg<0, 0, 0, 0, 0, 0, true, true>>>("lazy sbox + shoup diag", d, n);
-    run<Perm<Cfg<0, 44, 0, 0, 0, 0, true, true>>>("lazy+shoup, m4->ALU", d, n);
-    run<Perm<Cfg<0, 44, 12, 0, 0, 0, true, true>>>("lazy+shoup, m4+sum->ALU", d, n);
-    run<Perm<Cfg<0, 22, 0, 0, 0, 0, true, true>>>("lazy+shoup, half m4->ALU", d, n);
-    run<Perm<Cfg<0, 44, 0, 0, 14, 0, true, true>>>("lazy+shoup, m4 + isum->ALU", d, n);
-    run<Perm<Cfg<0, 44, 12, 0, 14, 0, true, true>>>("lazy+shoup, m4+sum + isum->ALU", d, n);
-    run<Perm<Cfg<16, 44, 12, 16, 14, 15, true, true>>>("lazy+shoup, everything->ALU", d, n);
-    run<Perm<Cfg<0, 33, 0, 0, 8, 0, true, true>>>("lazy+shoup, 33 m4 + 8 isum->ALU", d, n);
-    run<Perm<Cfg<0, 44, 0, 0, 14, 0, false, false>>>("plain, m4 + isum->ALU", d, n);
+    run<Perm<Cfg<0, 0, 0, 0, 0, 0, false, 0>>>("variant, no forcing", d, n);
+    run<Perm<Cfg<0, 0, 0, 0, 0, 0, true, 0>>>("lazy sbox", d, n);
+    run<Perm<Cfg<0, 0, 0, 0, 0, 0, true, 1>>>("lazy sbox + shoup diag", d, n);
+    run<Perm<Cfg<0, 44, 0, 0, 0, 0, true, 1>>>("lazy+shoup, m4->ALU", d, n);
+    run<Perm<Cfg<0, 44, 12, 0, 0, 0, true, 1>>>("lazy+shoup, m4+sum->ALU", d, n);
+    run<Perm<Cfg<0, 22, 0, 0, 0, 0, true, 1>>>("lazy+shoup, half m4->ALU", d, n);
+    run<Perm<Cfg<0, 44, 0, 0, 14, 0, true, 1>>>("lazy+shoup, m4 + isum->ALU", d, n);
+    run<Perm<Cfg<0, 44, 12, 0, 14, 0, true, 1>>>("lazy+shoup, m4+sum + isum->ALU", d, n);
+    run<Perm<Cfg<16, 44, 12, 16, 14, 15, true, 1>>>("lazy+shoup, everything->ALU", d, n);
+    run<Perm<Cfg<0, 33, 0, 0, 8, 0, true, 1>>>("lazy+shoup, 33 m4 + 8 isum->ALU", d, n);
+    run<Perm<Cfg<0, 44, 0, 0, 14, 0, false, 0>>>("plain, m4 + isum->ALU", d, n);
+    // round 2: shift-based diagonal, with increasing numbers of M4 / column-sum additions pinned to the ALU pipe
+    run<Perm<Cfg<0, 0, 0, 0, 0, 0, true, 2>>>("lazy + shift diag", d, n);
+    run<Perm<Cfg<0, 8, 0, 0, 0, 0, true, 2>>>("lazy + shift diag, 8 m4->ALU", d, n);
+    run<Perm<Cfg<0, 16, 0, 0, 0, 0, true, 2>>>("lazy + shift diag, 16 m4->ALU", d, n);
+    run<Perm<Cfg<0, 24, 0, 0, 0, 0, true, 2>>>("lazy + shift diag, 24 m4->ALU", d, n);
+    run<Perm<Cfg<0, 32, 0, 0, 0, 0, true, 2>>>("lazy + shift diag, 32 m4->ALU", d, n);
+    run<Perm<Cfg<0, 44, 0, 0, 0, 0, true, 2>>>("lazy + shift diag, 44 m4->ALU", d, n);
+    run<Perm<Cfg<0, 44, 12, 0, 0, 0, true, 2>>>("lazy + shift diag, m4+sum->ALU", d, n);
+    run<Perm<Cfg<0, 44, 12, 8, 0, 0, true, 2>>>("lazy + shift diag, m4+sum+8 out->ALU", d, n);
+    run<Perm<Cfg<8, 44, 12, 0, 0, 0, true, 2>>>("lazy + shift diag, 8 rc+m4+sum->ALU", d, n);
     return 0;
 }

@@ -37,10 +37,11 @@ KB_D uint32_t sbox(uint32_t x) {
     return umin_(r, r + P);
 }
 
-template <int RC_ALU, int M4_ALU, int SUM_ALU, int OUT_ALU, int ISUM_ALU, int IOUT_ALU, bool LAZY, bool SHOUP>
+template <int RC_ALU, int M4_ALU, int SUM_ALU, int OUT_ALU, int ISUM_ALU, int IOUT_ALU, bool LAZY, int SHOUP /* 0 Montgomery, 1 Shoup, 2 shift-based 2^-k */>
 struct Cfg {
     static constexpr int rc = RC_ALU, m4 = M4_ALU, sum = SUM_ALU, out = OUT_ALU, isum = ISUM_ALU, iout = IOUT_ALU;
-    static constexpr bool lazy = LAZY, shoup = SHOUP;
+    static constexpr bool lazy = LAZY;
+    static constexpr int shoup = SHOUP;
 };
 
 // knob values are COUNTS: the first `n` adds of a category go to the ALU pipe
@@ -94,6 +95,24 @@ struct Perm {
         v[6] = kb::halve(s[6]);
         v[7] = kb::add(kb::dbl(s[7]), s[7]);
         v[8] = kb::dbl(kb::dbl(s[8]));
+        if (C::shoup == 2) {  // round 2: diagonal +-2^-k without a field multiplication (p2::diag_pow2)
+            s[1] = addm<false>(sum, v[1], big);
+            s[2] = addm<false>(sum, v[2], big);
+            s[3] = addm<false>(sum, v[3], big);
+            s[4] = addm<false>(sum, v[4], big);
+            s[5] = addm<false>(sum, v[5], big);
+            s[6] = subm<false>(sum, v[6], big);
+            s[7] = subm<false>(sum, v[7], big);
+            s[8] = subm<false>(sum, v[8], big);
+            s[9] = p2::diag_pow2<8, false>(s[9], sum);
+            s[10] = p2::diag_pow2<3, false>(s[10], sum);
+            s[11] = p2::diag_pow2<24, false>(s[11], sum);
+            s[12] = p2::diag_pow2<8, true>(s[12], sum);
+            s[13] = p2::diag_pow2<3, true>(s[13], sum);
+            s[14] = p2::diag_pow2<4, true>(s[14], sum);
+            s[15] = p2::diag_pow2<24, true>(s[15], sum);
+            return;
+        }
 #pragma unroll
         for (int i = 9; i < 16; i++) {
             if (C::shoup) {

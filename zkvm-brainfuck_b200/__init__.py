@@ -49,6 +49,8 @@ ABI = {
     "bfgpu_synchronize": (C.c_int32, [C.c_void_p]),
     "bfgpu_set_fri_params": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "bfgpu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "bfgpu_debug_live_blocks": (C.c_uint64, [C.c_void_p]),
+    "bfgpu_debug_fail_alloc": (C.c_int32, [C.c_void_p, C.c_int64]),
     "bfgpu_host_alloc": (C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bfgpu_host_free": (None, [C.c_void_p]),
     "bfgpu_profile_enable": (C.c_int32, [C.c_void_p, C.c_int]),
@@ -226,6 +228,15 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().bfgpu_launch_count(self._h))
+
+    @property
+    def live_blocks(self):
+        """device blocks currently handed out by the context's allocator (error-path tests)"""
+        return int(lib().bfgpu_debug_live_blocks(self._h))
+
+    def fail_alloc(self, nth):
+        """test hook: the nth device allocation from now fails with BFGPU_ERR_OOM (nth < 0 disarms)"""
+        self.check(lib().bfgpu_debug_fail_alloc(self._h, int(nth)))
 
     def close(self):
         if getattr(self, "_h", None):

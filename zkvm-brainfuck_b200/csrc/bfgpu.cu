@@ -95,6 +95,14 @@ struct bfgpu_ctx {
     uint32_t* d_inv256 = nullptr;  // Montgomery inverses of 0..255 (tracegen.cuh, Jump chip)
     // peer receive buffers mapped through CUDA IPC (dist_commit.cuh), keyed by the 64-byte handle
     std::map<std::array<uint8_t, 64>, void*> ipc_open;
+    // buffers whose IPC handle has been given to peers: their own pool (plain cudaMalloc, kept until the context dies, never
+    // trimmed) so that a block a peer still has mapped is never returned to the driver behind its back
+    std::multimap<size_t, void*> export_free;
+    std::unordered_map<void*, size_t> export_live;
+    // allocation scopes (AllocScope): blocks taken by an entry point that has not yet handed them to a returned object
+    std::vector<std::vector<void*>*> scopes;
+    // test hook (bfgpu_debug_fail_alloc): the n-th dalloc from now fails with BFGPU_ERR_OOM
+    int64_t fail_alloc_in = -1;
 };
 
 struct bfgpu_tree {
@@ -186,6 +194,7 @@ static int32_t dalloc(bfgpu_ctx* ctx, void** p, size_t bytes) {
     int cur = -1;
     if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) CU(cudaSetDevice(ctx->device));
     bytes = (std::max<size_t>(bytes, 4) + 255) & ~(size_t)255;
+    if (ctx->fail_alloc_in >= 0 && ctx->fail_alloc_in-- == 0) return fail(ctx, BFGPU_ERR_OOM, "injected allocation failure (%zu bytes)", bytes);
     auto it = ctx->free_blocks.find(bytes);
     if (it != ctx->free_blocks.end()) {
         *p = it->second;
@@ -205,6 +214,7 @@ static int32_t dalloc(bfgpu_ctx* ctx, void** p, size_t bytes) {
         }
     }
     ctx->live[*p] = bytes;
+    if (!ctx->scopes.empty()) ctx->scopes.back()->push_back(*p);
     return BFGPU_OK;
 }
 static void dfree(bfgpu_ctx* ctx, void* p) {
@@ -256,6 +266,41 @@ struct Scratch {
     }
     ~Scratch() {
         for (void* p : bufs) dfree(ctx, p);
+    }
+};
+
+static void prestage_clear(bfgpu_ctx* ctx);
+// Every compute entry point opens one: CU()/TRY() return early from anywhere, and whatever the call had taken from dalloc() by
+// then and not yet released goes back to the block cache when the scope closes without ok() — the objects an entry point returns
+// are only handed out after ok().  Nested scopes (bfgpu_pcs_open inside bfgpu_machine_open) pass their blocks up on success.
+struct AllocScope {
+    bfgpu_ctx* ctx;
+    std::vector<void*> taken;
+    bool success = false;
+    explicit AllocScope(bfgpu_ctx* c) : ctx(c) {
+        if (ctx) ctx->scopes.push_back(&taken);
+    }
+    int32_t ok(int32_t rc = BFGPU_OK) {
+        success = rc == BFGPU_OK;
+        return rc;
+    }
+    ~AllocScope() {
+        if (!ctx) return;
+        ctx->scopes.pop_back();
+        if (success) {
+            if (!ctx->scopes.empty()) {
+                auto* up = ctx->scopes.back();
+                for (void* p : taken)
+                    if (ctx->live.count(p)) up->push_back(p);
+            }
+            return;
+        }
+        // kernels of the failed call may still be running on either stream: drain before the blocks can be handed out again
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        cudaGetLastError();
+        prestage_clear(ctx);
+        for (void* p : taken) dfree(ctx, p);  // dfree ignores blocks that were already released
     }
 };
 
@@ -349,6 +394,8 @@ extern "C" void bfgpu_ctx_destroy(bfgpu_ctx* ctx) {
         ctx->pinned_pool.clear();
     }
     for (auto& kv : ctx->ipc_open) cudaIpcCloseMemHandle(kv.second);
+    for (auto& kv : ctx->export_free) cudaFree(kv.second);
+    for (auto& kv : ctx->export_live) cudaFree(kv.first);
     trim_cache(ctx);
     for (auto& kv : ctx->live) cudaFree(kv.first);
     for (auto& kv : ctx->pw_cache) cudaFree(kv.second);
@@ -398,6 +445,45 @@ extern "C" int32_t bfgpu_set_fri_params(bfgpu_ctx* ctx, uint32_t log_blowup, uin
     return BFGPU_OK;
 }
 extern "C" uint64_t bfgpu_launch_count(const bfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t bfgpu_debug_live_blocks(const bfgpu_ctx* ctx) { return ctx ? ctx->live.size() : 0; }
+extern "C" int32_t bfgpu_debug_fail_alloc(bfgpu_ctx* ctx, int64_t nth) {
+    if (!ctx) return BFGPU_ERR_INVALID;
+    ctx->fail_alloc_in = nth;
+    return BFGPU_OK;
+}
+
+// exported (IPC-shared) blocks: see bfgpu_ctx::export_free
+static int32_t dalloc_export(bfgpu_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) CU(cudaSetDevice(ctx->device));
+    bytes = (std::max<size_t>(bytes, 4) + 255) & ~(size_t)255;
+    auto it = ctx->export_free.find(bytes);
+    if (it != ctx->export_free.end()) {
+        *p = it->second;
+        ctx->export_free.erase(it);
+    } else {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            trim_cache(ctx);
+            e = cudaMalloc(p, bytes);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            *p = nullptr;
+            return fail(ctx, e == cudaErrorMemoryAllocation ? BFGPU_ERR_OOM : BFGPU_ERR_CUDA, "cudaMalloc(%zu bytes, exported): %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    ctx->export_live[*p] = bytes;
+    return BFGPU_OK;
+}
+static void dfree_export(bfgpu_ctx* ctx, void* p) {
+    auto it = ctx->export_live.find(p);
+    if (it == ctx->export_live.end()) return;
+    ctx->export_free.emplace(it->second, p);
+    ctx->export_live.erase(it);
+}
 
 extern "C" int32_t bfgpu_host_alloc(bfgpu_ctx* ctx, uint64_t bytes, void** out) {
     if (!ctx || !out) return BFGPU_ERR_INVALID;
@@ -462,7 +548,12 @@ __global__ void __launch_bounds__(256) k_int32_probe(uint32_t* out, uint32_t ite
     for (int k = 0; k < 8; k++) r ^= a[k];
     if (r == 0x12345678u) out[0] = r;  // practically never; keeps the chains alive
 }
+static int32_t int32_peak_probe_impl(bfgpu_ctx* ctx, double* giops);
 extern "C" int32_t bfgpu_int32_peak_probe(bfgpu_ctx* ctx, double* giops) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(int32_peak_probe_impl(ctx, giops));
+}
+static int32_t int32_peak_probe_impl(bfgpu_ctx* ctx, double* giops) {
     if (!ctx || !giops) return BFGPU_ERR_INVALID;
     uint32_t* d = nullptr;
     TRY(dalloc(ctx, (void**)&d, 4));
@@ -833,7 +924,14 @@ static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bit
     return lde_from_bitrev(ctx, coef, added_bits, shift_mont, out);
 }
 
+static int32_t coset_lde_batch_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t added_bits, uint32_t shift, int bit_reversed_rows,
+                                         uint32_t* out);
 extern "C" int32_t bfgpu_coset_lde_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t added_bits, uint32_t shift, int bit_reversed_rows,
+                                         uint32_t* out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(coset_lde_batch_impl(ctx, mat, added_bits, shift, bit_reversed_rows, out));
+}
+static int32_t coset_lde_batch_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t added_bits, uint32_t shift, int bit_reversed_rows,
                                          uint32_t* out) {
     if (!ctx || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     TRY(check_mat(ctx, mat, true));
@@ -845,7 +943,12 @@ extern "C" int32_t bfgpu_coset_lde_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, u
     return rc;
 }
 
+static int32_t dft_batch_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out);
 extern "C" int32_t bfgpu_dft_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(dft_batch_impl(ctx, mat, out));
+}
+static int32_t dft_batch_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out) {
     if (!ctx || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     TRY(check_mat(ctx, mat, true));
     DMat d;
@@ -856,7 +959,12 @@ extern "C" int32_t bfgpu_dft_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_
     return rc;
 }
 
+static int32_t idft_batch_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out);
 extern "C" int32_t bfgpu_idft_batch(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(idft_batch_impl(ctx, mat, out));
+}
+static int32_t idft_batch_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* out) {
     if (!ctx || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     TRY(check_mat(ctx, mat, true));
     DMat d;
@@ -880,7 +988,12 @@ static int32_t convert_inplace(bfgpu_ctx* ctx, uint32_t* d, uint64_t n, bool to_
     return BFGPU_OK;
 }
 
+static int32_t poseidon2_permute_impl(bfgpu_ctx* ctx, uint32_t* states, uint64_t n);
 extern "C" int32_t bfgpu_poseidon2_permute(bfgpu_ctx* ctx, uint32_t* states, uint64_t n) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(poseidon2_permute_impl(ctx, states, n));
+}
+static int32_t poseidon2_permute_impl(bfgpu_ctx* ctx, uint32_t* states, uint64_t n) {
     if (!ctx || (!states && n)) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     if (n == 0) return BFGPU_OK;
     uint32_t* d = nullptr;
@@ -915,7 +1028,12 @@ static int32_t make_colptr(bfgpu_ctx* ctx, const std::vector<const DMat*>& mats,
     return BFGPU_OK;
 }
 
+static int32_t sponge_hash_rows_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* digests);
 extern "C" int32_t bfgpu_sponge_hash_rows(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* digests) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(sponge_hash_rows_impl(ctx, mat, digests));
+}
+static int32_t sponge_hash_rows_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t* digests) {
     if (!ctx || !digests) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     TRY(check_mat(ctx, mat, false));
     DMat d;
@@ -937,7 +1055,12 @@ extern "C" int32_t bfgpu_sponge_hash_rows(bfgpu_ctx* ctx, const bfgpu_mat* mat, 
     return BFGPU_OK;
 }
 
+static int32_t compress_impl(bfgpu_ctx* ctx, const uint32_t* left, const uint32_t* right, uint64_t n, uint32_t* out);
 extern "C" int32_t bfgpu_compress(bfgpu_ctx* ctx, const uint32_t* left, const uint32_t* right, uint64_t n, uint32_t* out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(compress_impl(ctx, left, right, n, out));
+}
+static int32_t compress_impl(bfgpu_ctx* ctx, const uint32_t* left, const uint32_t* right, uint64_t n, uint32_t* out) {
     if (!ctx || !left || !right || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     if (n == 0) return BFGPU_OK;
     uint32_t *l = nullptr, *r = nullptr, *o = nullptr;
@@ -1065,7 +1188,12 @@ static int32_t read_digest(bfgpu_ctx* ctx, const uint32_t* d, uint32_t out[8]) {
     return BFGPU_OK;
 }
 
+static int32_t mmcs_commit_impl(bfgpu_ctx* ctx, const bfgpu_mat* mats, int32_t n, uint32_t root[8], bfgpu_tree** out);
 extern "C" int32_t bfgpu_mmcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* mats, int32_t n, uint32_t root[8], bfgpu_tree** out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(mmcs_commit_impl(ctx, mats, n, root, out));
+}
+static int32_t mmcs_commit_impl(bfgpu_ctx* ctx, const bfgpu_mat* mats, int32_t n, uint32_t root[8], bfgpu_tree** out) {
     if (!ctx || !mats || n <= 0 || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     *out = nullptr;
     for (int i = 0; i < n; i++) TRY(check_mat(ctx, &mats[i], true));
@@ -1082,7 +1210,12 @@ extern "C" int32_t bfgpu_mmcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* mats, int3
     return BFGPU_OK;
 }
 
+static int32_t mmcs_open_batch_impl(bfgpu_tree* t, uint64_t index, uint32_t* opened_rows, uint32_t* siblings);
 extern "C" int32_t bfgpu_mmcs_open_batch(bfgpu_tree* t, uint64_t index, uint32_t* opened_rows, uint32_t* siblings) {
+    AllocScope scope(t ? t->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(mmcs_open_batch_impl(t, index, opened_rows, siblings));
+}
+static int32_t mmcs_open_batch_impl(bfgpu_tree* t, uint64_t index, uint32_t* opened_rows, uint32_t* siblings) {
     if (!t) return BFGPU_ERR_INVALID;
     bfgpu_ctx* ctx = t->ctx;
     if (!opened_rows || (!siblings && t->log_max)) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
@@ -1124,7 +1257,12 @@ extern "C" int32_t bfgpu_tree_num_layers(const bfgpu_tree* t) { return t ? (int3
 extern "C" uint64_t bfgpu_tree_layer_len(const bfgpu_tree* t, int32_t l) {
     return (t && l >= 0 && (size_t)l < t->layers.size()) ? t->layer_len[l] : 0;
 }
+static int32_t tree_get_layer_impl(bfgpu_tree* t, int32_t l, uint32_t* digests);
 extern "C" int32_t bfgpu_tree_get_layer(bfgpu_tree* t, int32_t l, uint32_t* digests) {
+    AllocScope scope(t ? t->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(tree_get_layer_impl(t, l, digests));
+}
+static int32_t tree_get_layer_impl(bfgpu_tree* t, int32_t l, uint32_t* digests) {
     if (!t) return BFGPU_ERR_INVALID;
     bfgpu_ctx* ctx = t->ctx;
     if (l < 0 || (size_t)l >= t->layers.size() || !digests) return fail(ctx, BFGPU_ERR_INVALID, "bad layer");
@@ -1175,7 +1313,16 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
     }
     TRY(dalloc(ctx, (void**)&state, N * 16 * 4));
     TRY(dalloc(ctx, (void**)&layer, N * 32));
-    cudaEvent_t ready[2], consumed[2], fence;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, fence;
+    struct EventGuard {  // CU() below may return from inside the block loop
+        cudaEvent_t *a, *b;
+        ~EventGuard() {
+            for (int k = 0; k < 2; k++) {
+                if (a[k]) cudaEventDestroy(a[k]);
+                if (b[k]) cudaEventDestroy(b[k]);
+            }
+        }
+    } event_guard{ready, consumed};
     for (int k = 0; k < 2; k++) {
         CU(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&consumed[k], cudaEventDisableTiming));
@@ -1229,10 +1376,6 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
         CU(cudaEventRecord(consumed[0], ctx->copy_stream));
         CU(cudaStreamWaitEvent(ctx->stream, consumed[0], 0));
     }
-    for (int k = 0; k < 2; k++) {
-        cudaEventDestroy(ready[k]);
-        cudaEventDestroy(consumed[k]);
-    }
     if (rc != BFGPU_OK) cudaStreamSynchronize(ctx->copy_stream);
     dfree(ctx, staged[0]);
     dfree(ctx, staged[1]);
@@ -1247,7 +1390,14 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
     return BFGPU_OK;
 }
 
+static int32_t pcs_commit_impl(bfgpu_ctx* ctx, const bfgpu_mat* evals, const uint32_t* domain_shifts, int32_t n, uint32_t root[8],
+                                    bfgpu_pcs_data** out);
 extern "C" int32_t bfgpu_pcs_commit(bfgpu_ctx* ctx, const bfgpu_mat* evals, const uint32_t* domain_shifts, int32_t n, uint32_t root[8],
+                                    bfgpu_pcs_data** out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(pcs_commit_impl(ctx, evals, domain_shifts, n, root, out));
+}
+static int32_t pcs_commit_impl(bfgpu_ctx* ctx, const bfgpu_mat* evals, const uint32_t* domain_shifts, int32_t n, uint32_t root[8],
                                     bfgpu_pcs_data** out) {
     if (!ctx || !evals || n <= 0 || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -1289,7 +1439,12 @@ extern "C" int32_t bfgpu_pcs_lde_dims(const bfgpu_pcs_data* d, int32_t idx, uint
     if (cols) *cols = d->ldes[idx].cols;
     return BFGPU_OK;
 }
+static int32_t pcs_get_evaluations_impl(bfgpu_pcs_data* d, int32_t idx, int bit_reversed_rows, uint32_t* out);
 extern "C" int32_t bfgpu_pcs_get_evaluations(bfgpu_pcs_data* d, int32_t idx, int bit_reversed_rows, uint32_t* out) {
+    AllocScope scope(d ? d->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(pcs_get_evaluations_impl(d, idx, bit_reversed_rows, out));
+}
+static int32_t pcs_get_evaluations_impl(bfgpu_pcs_data* d, int32_t idx, int bit_reversed_rows, uint32_t* out) {
     if (!d) return BFGPU_ERR_INVALID;
     bfgpu_ctx* ctx = d->ctx;
     if (idx < 0 || (size_t)idx >= d->ldes.size() || !out) return fail(ctx, BFGPU_ERR_INVALID, "bad matrix index");
@@ -1398,7 +1553,14 @@ struct ExtKey {
     bool operator<(const ExtKey& o) const { return log_h != o.log_h ? log_h < o.log_h : z < o.z; }
 };
 
+static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int32_t n_rounds, bfgpu_challenger* chh,
+                                  int64_t fixed_pow_witness, bfgpu_opening** out);
 extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int32_t n_rounds, bfgpu_challenger* chh,
+                                  int64_t fixed_pow_witness, bfgpu_opening** out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(pcs_open_impl(ctx, rounds, n_rounds, chh, fixed_pow_witness, out));
+}
+static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int32_t n_rounds, bfgpu_challenger* chh,
                                   int64_t fixed_pow_witness, bfgpu_opening** out) {
     if (!ctx || !rounds || n_rounds <= 0 || !chh || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -1937,7 +2099,14 @@ static int32_t machine_commit(bfgpu_ctx* ctx, const char* const* names, const bf
     return BFGPU_OK;
 }
 
+static int32_t machine_setup_impl(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* prep_traces, int32_t n, uint32_t commit[8],
+                                       bfgpu_pk** out);
 extern "C" int32_t bfgpu_machine_setup(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* prep_traces, int32_t n, uint32_t commit[8],
+                                       bfgpu_pk** out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(machine_setup_impl(ctx, names, prep_traces, n, commit, out));
+}
+static int32_t machine_setup_impl(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* prep_traces, int32_t n, uint32_t commit[8],
                                        bfgpu_pk** out) {
     if (!ctx || !names || !prep_traces || n <= 0 || !commit || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     auto* pk = new bfgpu_pk();
@@ -1965,7 +2134,14 @@ extern "C" int32_t bfgpu_pk_observe_into(const bfgpu_pk* pk, bfgpu_challenger* c
     return BFGPU_OK;
 }
 
+static int32_t machine_commit_impl(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* traces, int32_t n, uint32_t root[8],
+                                        bfgpu_shard** out);
 extern "C" int32_t bfgpu_machine_commit(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* traces, int32_t n, uint32_t root[8],
+                                        bfgpu_shard** out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(machine_commit_impl(ctx, names, traces, n, root, out));
+}
+static int32_t machine_commit_impl(bfgpu_ctx* ctx, const char* const* names, const bfgpu_mat* traces, int32_t n, uint32_t root[8],
                                         bfgpu_shard** out) {
     if (!ctx || !names || !traces || n <= 0 || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     auto* sd = new bfgpu_shard();
@@ -2028,7 +2204,14 @@ static int32_t commit_bitrev_device(bfgpu_ctx* ctx, std::vector<DMat>& coefs, co
 }
 
 // CpuProver::open (prover.rs:242-553)
+static int32_t machine_open_impl(bfgpu_ctx* ctx, const bfgpu_pk* pk, const bfgpu_shard* sd, bfgpu_challenger* chh, int64_t fixed_pow_witness,
+                                      bfgpu_shard_proof** out);
 extern "C" int32_t bfgpu_machine_open(bfgpu_ctx* ctx, const bfgpu_pk* pk, const bfgpu_shard* sd, bfgpu_challenger* chh, int64_t fixed_pow_witness,
+                                      bfgpu_shard_proof** out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(machine_open_impl(ctx, pk, sd, chh, fixed_pow_witness, out));
+}
+static int32_t machine_open_impl(bfgpu_ctx* ctx, const bfgpu_pk* pk, const bfgpu_shard* sd, bfgpu_challenger* chh, int64_t fixed_pow_witness,
                                       bfgpu_shard_proof** out) {
     if (!ctx || !pk || !sd || !chh || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     *out = nullptr;

@@ -102,7 +102,8 @@ extern "C" int32_t bfgpu_dist_commit_begin(bfgpu_ctx* ctx, uint32_t rank, uint32
         m.send_off = dc->block_words;
         dc->block_words += m.rpg * m.ncols;
     }
-    TRY(dalloc(ctx, (void**)&dc->recv, dc->recv_words * 4));
+    // the receive matrix is IPC-exported to the peers: it lives in the context's exported pool, never in the trimmable block cache
+    TRY(dalloc_export(ctx, (void**)&dc->recv, dc->recv_words * 4));
     *out = dc.release();
     return BFGPU_OK;
 }
@@ -207,7 +208,12 @@ static int32_t dist_scatter(bfgpu_dist_commit* dc, const bfgpu_dist_commit::Mat&
 // everything is enqueued.  Before bfgpu_dist_commit_finish every rank must have synchronised its context and the
 // ranks must have passed a barrier (P2P mode) or completed the all-to-all + _unpack (staged mode).
 constexpr uint32_t DIST_CHUNK_COLS = 64;
+static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts);
 extern "C" int32_t bfgpu_dist_commit_lde(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts) {
+    AllocScope scope(dc ? dc->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(dist_commit_lde_impl(dc, local, domain_shifts));
+}
+static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts) {
     if (!dc || !local) return BFGPU_ERR_INVALID;
     bfgpu_ctx* ctx = dc->ctx;
     if (dc->lde_done) return fail(ctx, BFGPU_ERR_STATE, "LDE already done");
@@ -276,7 +282,12 @@ extern "C" int32_t bfgpu_dist_commit_lde(bfgpu_dist_commit* dc, const bfgpu_mat*
 }
 
 // staged mode: dev_recv = [source rank][matrix][source's columns][own rows]  ->  the receive matrices
+static int32_t dist_commit_unpack_impl(bfgpu_dist_commit* dc, const uint32_t* dev_recv);
 extern "C" int32_t bfgpu_dist_commit_unpack(bfgpu_dist_commit* dc, const uint32_t* dev_recv) {
+    AllocScope scope(dc ? dc->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(dist_commit_unpack_impl(dc, dev_recv));
+}
+static int32_t dist_commit_unpack_impl(bfgpu_dist_commit* dc, const uint32_t* dev_recv) {
     if (!dc || !dev_recv) return BFGPU_ERR_INVALID;
     bfgpu_ctx* ctx = dc->ctx;
     Phase ph(ctx, BFGPU_PHASE_EXCHANGE);
@@ -293,7 +304,12 @@ extern "C" int32_t bfgpu_dist_commit_unpack(bfgpu_dist_commit* dc, const uint32_
 }
 
 // leaf hashes + subtree over this rank's rows; cap = root of the subtree
+static int32_t dist_commit_finish_impl(bfgpu_dist_commit* dc, uint32_t cap[8]);
 extern "C" int32_t bfgpu_dist_commit_finish(bfgpu_dist_commit* dc, uint32_t cap[8]) {
+    AllocScope scope(dc ? dc->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(dist_commit_finish_impl(dc, cap));
+}
+static int32_t dist_commit_finish_impl(bfgpu_dist_commit* dc, uint32_t cap[8]) {
     if (!dc || !cap) return BFGPU_ERR_INVALID;
     bfgpu_ctx* ctx = dc->ctx;
     if (!dc->lde_done || dc->tree) return fail(ctx, BFGPU_ERR_STATE, "finish needs a completed LDE/exchange and runs once");
@@ -303,8 +319,13 @@ extern "C" int32_t bfgpu_dist_commit_finish(bfgpu_dist_commit* dc, uint32_t cap[
         shards[i].rows = dc->mats[i].rpg;
         shards[i].cols = dc->mats[i].total_cols;
     }
-    TRY(build_tree(ctx, std::move(shards), false, &dc->tree));
-    return read_digest(ctx, dc->tree->layers.back(), cap);
+    int32_t rc = build_tree(ctx, std::move(shards), false, &dc->tree);
+    if (rc == BFGPU_OK) rc = read_digest(ctx, dc->tree->layers.back(), cap);
+    if (rc != BFGPU_OK) {  // no half-built tree stays behind in the handle
+        tree_release(dc->tree);
+        dc->tree = nullptr;
+    }
+    return rc;
 }
 
 // top of the tree from the all-gathered caps (caps[r] = rank r's cap, caller representation)
@@ -333,7 +354,12 @@ extern "C" int32_t bfgpu_dist_commit_root(bfgpu_dist_commit* dc, const uint32_t*
 
 // Mmcs::open_batch for a GLOBAL leaf index owned by this rank (index / (max LDE height / world) == rank):
 // rows of every matrix + log2(max height) siblings, leaf level first.
+static int32_t dist_commit_open_batch_impl(bfgpu_dist_commit* dc, uint64_t index, uint32_t* opened_rows, uint32_t* siblings);
 extern "C" int32_t bfgpu_dist_commit_open_batch(bfgpu_dist_commit* dc, uint64_t index, uint32_t* opened_rows, uint32_t* siblings) {
+    AllocScope scope(dc ? dc->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(dist_commit_open_batch_impl(dc, index, opened_rows, siblings));
+}
+static int32_t dist_commit_open_batch_impl(bfgpu_dist_commit* dc, uint64_t index, uint32_t* opened_rows, uint32_t* siblings) {
     if (!dc) return BFGPU_ERR_INVALID;
     bfgpu_ctx* ctx = dc->ctx;
     if (!dc->tree || dc->top.empty()) return fail(ctx, BFGPU_ERR_STATE, "commit not finished");
@@ -354,6 +380,6 @@ extern "C" uint64_t bfgpu_dist_commit_rows_per_rank(const bfgpu_dist_commit* dc)
 extern "C" void bfgpu_dist_commit_free(bfgpu_dist_commit* dc) {
     if (!dc) return;
     tree_release(dc->tree);
-    dfree(dc->ctx, dc->recv);
+    dfree_export(dc->ctx, dc->recv);
     delete dc;
 }

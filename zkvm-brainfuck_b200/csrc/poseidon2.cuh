@@ -95,6 +95,27 @@ KB_D uint32_t mul_diag(uint32_t x, int i) {
     return kb::umin_(r, r - kb::P);
 }
 
+// sum +- x / 2^k for the diagonal entries +-2^-k (k <= 24) WITHOUT a multiplication by a field constant: p = 2^31 - 2^24 + 1 is
+// 1 mod 2^k, so with lo = x mod 2^k the integer x - lo*p is divisible by 2^k and
+//     x / 2^k  =  (x >> k) - lo * (2^(31-k) - 2^(24-k))   (mod p),      0 <= lo * (2^(31-k) - 2^(24-k)) < p,  x >> k < 2^(31-k)
+// (a Montgomery reduction by 2^k whose quotient digit is read off the low bits).  The Shoup product this replaces costs
+// IMAD.HI + 2 IMAD on the FMA-heavy pipe, the busy one in the hash kernels (profiles/r1_leaf_hash_final.md); this form is
+// AND + shift + one small multiply (or shift/subtract, P2_DIAG_SHIFT=2) and two modular add/subs on the ALU pipe.
+#ifndef P2_DIAG_SHIFT
+#define P2_DIAG_SHIFT 1
+#endif
+template <int K, bool NEG>
+KB_D uint32_t diag_pow2(uint32_t x, uint32_t sum) {
+    static_assert(K >= 1 && K <= 24, "needs p = 1 mod 2^K");
+    const uint32_t lo = x & ((1u << K) - 1), u = x >> K;
+#if P2_DIAG_SHIFT == 2
+    const uint32_t t = ((lo << 7) - lo) << (24 - K);  // lo * 127 * 2^(24-K)
+#else
+    const uint32_t t = lo * (127u << (24 - K));
+#endif
+    return NEG ? sub(add(sum, t), u) : add(sub(sum, t), u);
+}
+
 // M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]]
 KB_D void mat4(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     // 9 additions + 2 doublings
@@ -134,8 +155,18 @@ KB_D void internal_linear(uint32_t (&s)[16]) {
     s[6] = sub(sum, kb::halve(s[6]));
     s[7] = sub(sum, add(dbl(s[7]), s[7]));
     s[8] = sub(sum, dbl(dbl(s[8])));
+#if P2_DIAG_SHIFT
+    s[9] = diag_pow2<8, false>(s[9], sum);
+    s[10] = diag_pow2<3, false>(s[10], sum);
+    s[11] = diag_pow2<24, false>(s[11], sum);
+    s[12] = diag_pow2<8, true>(s[12], sum);
+    s[13] = diag_pow2<3, true>(s[13], sum);
+    s[14] = diag_pow2<4, true>(s[14], sum);
+    s[15] = diag_pow2<24, true>(s[15], sum);
+#else
 #pragma unroll
     for (int i = 9; i < 16; i++) s[i] = add(mul_diag(s[i], i), sum);
+#endif
 }
 
 // Rounds are kept as rolled loops on purpose: the fully unrolled permutation is ~64 KB of SASS and

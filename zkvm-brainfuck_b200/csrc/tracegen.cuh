@@ -163,7 +163,8 @@ extern "C" int32_t bfgpu_execute(bfgpu_ctx* ctx, const char* code, const uint8_t
     const uint32_t* args = r->args.data();
     uint32_t* counts = r->prog_counts.data();
     uint4* cyc = r->cycles;
-    uint64_t cap = r->cap, n_alu = 0, n_jump = 0, n_mem = 0, n_io = 0;
+    // the limit applies to recycled (pooled, already large) record buffers as well: clamp before the loop, not only after a growth
+    uint64_t cap = std::min<uint64_t>(r->cap, max_cycles + 1), n_alu = 0, n_jump = 0, n_mem = 0, n_io = 0;
     uint32_t pc = 0, mp = 0;
     uint64_t i = 0;
     while (pc != n) {
@@ -532,7 +533,12 @@ static uint64_t tg_pow2(uint64_t n, uint64_t minimum) {  // utils/mod.rs:25-53
 }
 
 // MachineProver::commit (prover.rs:209-236) fed by the execution record instead of host traces
+static int32_t machine_commit_record_impl(bfgpu_ctx* ctx, const bfgpu_record* rec, uint32_t root[8], bfgpu_shard** out);
 extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_record* rec, uint32_t root[8], bfgpu_shard** out) {
+    AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(machine_commit_record_impl(ctx, rec, root, out));
+}
+static int32_t machine_commit_record_impl(bfgpu_ctx* ctx, const bfgpu_record* rec, uint32_t root[8], bfgpu_shard** out) {
     if (!ctx || !rec || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
     *out = nullptr;
     const uint32_t n = (uint32_t)rec->n_cycles, n_instr = (uint32_t)rec->ops.size(), n_cells = (uint32_t)(rec->mem_events.size() / 5);
@@ -718,7 +724,12 @@ extern "C" int32_t bfgpu_shard_trace_info(const bfgpu_shard* sd, int32_t i, cons
     if (cols) *cols = sd->traces[i].cols;
     return BFGPU_OK;
 }
+static int32_t shard_get_trace_impl(const bfgpu_shard* sd, int32_t i, uint32_t* out);
 extern "C" int32_t bfgpu_shard_get_trace(const bfgpu_shard* sd, int32_t i, uint32_t* out) {
+    AllocScope scope(sd ? sd->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(shard_get_trace_impl(sd, i, out));
+}
+static int32_t shard_get_trace_impl(const bfgpu_shard* sd, int32_t i, uint32_t* out) {
     if (!sd || i < 0 || (size_t)i >= sd->traces.size() || !out) return BFGPU_ERR_INVALID;
     return egress(sd->ctx, sd->traces[i], /*bitrev=*/true, out);  // stored bit-reversed: undo for natural order
 }

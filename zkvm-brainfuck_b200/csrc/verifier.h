@@ -31,9 +31,13 @@ struct Reader {
         }
         return p[pos++];
     }
-    uint32_t fe() {
+    uint32_t fe() {  // a field element must be the unique representative in [0, p): anything else is a second encoding of the same proof
         uint32_t v = raw();
-        return monty ? v : kb::to_mont(v % kb::P);
+        if (v >= kb::P) {
+            ok = false;
+            return 0;
+        }
+        return monty ? v : kb::to_mont(v);
     }
     Ext ext() {
         Ext e;
@@ -86,6 +90,7 @@ static bool verify_batch(const uint32_t root[8], const std::vector<uint64_t>& he
                          const std::vector<std::array<uint32_t, 8>>& siblings) {
     std::vector<size_t> order(heights.size());
     for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    if (order.empty()) return false;  // a round without matrices opens nothing
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return heights[a] > heights[b]; });
     size_t pos = 0;
     auto group_digest = [&](uint64_t h, uint32_t out[8]) -> bool {  // sponge over the concatenated rows of height h
@@ -145,7 +150,10 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
                           const uint32_t* words, uint64_t n_words, bool monty, unsigned log_blowup, unsigned num_queries, unsigned pow_bits) {
     Reader rd{words, n_words, 0, monty};
     uint32_t vk_commit[8];
-    for (int i = 0; i < 8; i++) vk_commit[i] = monty ? vk_commit_in[i] : kb::to_mont(vk_commit_in[i] % kb::P);
+    for (int i = 0; i < 8; i++) {
+        if (vk_commit_in[i] >= kb::P) return "InvalidProofShape: non-canonical verifying key";
+        vk_commit[i] = monty ? vk_commit_in[i] : kb::to_mont(vk_commit_in[i]);
+    }
     Round rounds[4];
     memcpy(rounds[0].commit, vk_commit, 32);
     rd.digest(rounds[1].commit);
@@ -160,7 +168,9 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
         c.chip = (int)rd.raw();
         c.log_degree = rd.raw();
         c.csum = rd.ext();
-        if (!rd.ok || c.chip < 0 || c.chip >= air::NUM_CHIPS || c.log_degree + log_blowup > (unsigned)kb::TWO_ADICITY || where.count(c.chip)) return "InvalidProofShape";
+        if (!rd.ok || c.chip < 0 || c.chip >= air::NUM_CHIPS || log_blowup > (unsigned)kb::TWO_ADICITY ||
+            c.log_degree > (unsigned)kb::TWO_ADICITY - log_blowup || where.count(c.chip))
+            return "InvalidProofShape";  // (the sum is not formed: log_degree is an untrusted 32-bit word)
         where[c.chip] = &c - chips.data();
     }
     // ---- transcript (verifier.rs:60-104); the caller's challenger has observed the verifying key --------------------
@@ -190,6 +200,11 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
         rounds[2].mats.push_back(OpenedMat{c.log_degree, 4u * (uint32_t)info.perm_w, {zeta, next_point(c.log_degree)}, {}});
         for (int d = 0; d < (1 << info.log_quotient_degree); d++) rounds[3].mats.push_back(OpenedMat{c.log_degree, 4, {zeta}, {}});
     }
+    for (auto& r : rounds) {
+        if (r.mats.empty()) return "InvalidProofShape: commitment round without matrices";
+        for (auto& m : r.mats)
+            if (m.log_n > (unsigned)kb::TWO_ADICITY - log_blowup) return "InvalidProofShape";
+    }
     for (auto& r : rounds)
         for (auto& m : r.mats)
             for (size_t t = 0; t < m.points.size(); t++) {
@@ -205,7 +220,9 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
                 for (auto& e : v) ch.observe_ext(e);
     const Ext fri_alpha = ch.sample_ext();
     const uint32_t n_commit = rd.raw();
-    if (!rd.ok || n_commit == 0 || n_commit + log_blowup > (unsigned)kb::TWO_ADICITY) return "InvalidProofShape";
+    if (!rd.ok || n_commit == 0 || n_commit > (unsigned)kb::TWO_ADICITY - log_blowup) return "InvalidProofShape";
+    for (auto& c : chips)  // every committed LDE must fit under the first FRI layer
+        if (c.log_degree > n_commit) return "InvalidProofShape: chip taller than the FRI domain";
     std::vector<std::array<uint32_t, 8>> fri_commits(n_commit);
     std::vector<Ext> betas(n_commit);
     for (uint32_t k = 0; k < n_commit; k++) {

@@ -162,7 +162,8 @@ class DistributedCommit:
 
     def open_batch(self, index):
         """Mmcs::open_batch(index) on the rank that owns the leaf: ([row of every matrix], siblings (log2 h, 8))."""
-        nl = (int(self.rows.max()) << 1).bit_length() - 1  # log_blowup = 1 (kb31_poseidon2.rs:57)
+        # what the library writes: log2(rows per rank) local siblings + log2(world) cap-tree siblings (follows the context's log_blowup)
+        nl = (self.rows_per_rank.bit_length() - 1) + (self.world.bit_length() - 1)
         total = int(self.total_cols.sum())
         rows = np.zeros(total, np.uint32)
         sib = np.zeros((nl, 8), np.uint32)
