@@ -73,6 +73,15 @@ int32_t bfgpu_set_input_space(bfgpu_ctx* ctx, int mem_space);
 int32_t bfgpu_set_stream(bfgpu_ctx* ctx, void* cuda_stream);
 int32_t bfgpu_synchronize(bfgpu_ctx* ctx);
 int32_t bfgpu_set_fri_params(bfgpu_ctx* ctx, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits);
+/* Transcript options: every choice INSIDE Plonky3 (git dependency pinned at rev 93967fce, not vendored: SURVEY.md "P3" marks) that the
+ * restatement could not confirm offline is a switch here, mirrored by the native verifier (bfgpu_verify_shard_ex) and by the
+ * CPU oracle, so that pinning against the real Rust prover flips a flag instead of rewriting kernels.  Defaults = Plonky3 of the
+ * pinned API era as published.
+ *   OBSERVE_OPENED_VALUES 1: TwoAdicFriPcs::open/verify write every opened value into the challenger before sampling alpha; 0: they do not
+ *   FRI_ROLLIN            0: a reduced opening joins the folded vector as `folded[i] += ro[i]`; 1: as `folded[i] += beta^2 * ro[i]`
+ *   POW_ORDER             0: grind returns the smallest witness; 1: the largest (the reference's rayon find_any returns any valid one) */
+enum { BFGPU_OPT_OBSERVE_OPENED_VALUES = 0, BFGPU_OPT_FRI_ROLLIN = 1, BFGPU_OPT_POW_ORDER = 2, BFGPU_NUM_OPTS = 3 };
+int32_t bfgpu_set_transcript_option(bfgpu_ctx* ctx, int32_t option, uint32_t value);
 /* number of this library's kernels launched on the context since creation (bench evidence) */
 uint64_t bfgpu_launch_count(const bfgpu_ctx* ctx);
 /* test hooks for the error paths: number of device blocks the context currently has handed out, and "the nth device allocation
@@ -307,6 +316,10 @@ int32_t bfgpu_shard_get_trace(const bfgpu_shard* shard, int32_t i, uint32_t* out
 int32_t bfgpu_verify_shard(const uint32_t vk_commit[8], const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep,
                            const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries,
                            uint32_t pow_bits, char* err, uint64_t err_len);
+/* same with explicit transcript options: options[BFGPU_OPT_*] for the first n_options options (NULL / 0 = all defaults) */
+int32_t bfgpu_verify_shard_ex(const uint32_t vk_commit[8], const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep,
+                              const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries,
+                              uint32_t pow_bits, const uint32_t* options, int32_t n_options, char* err, uint64_t err_len);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,11 @@ def lib():
         L.bfo_pcs_lde.restype = u32p
         L.bfo_pcs_tree.argtypes = [C.c_void_p]
         L.bfo_pcs_tree.restype = C.c_void_p
+        L.bfo_fast_available.restype = C.c_int
+        L.bfo_fast_pcs_commit.argtypes = [u32p, C.c_uint64, C.c_uint64, u32p, u32p, C.POINTER(C.c_double)]
+        L.bfo_fast_pcs_commit.restype = C.c_int
+        L.bfo_fast_permute_many.argtypes = [u32p, C.c_uint64]
+        L.bfo_fast_permute_many.restype = C.c_int
         L.bfo_set_threads.argtypes = [C.c_int]
         L.bfo_get_threads.restype = C.c_int
         _LIB = L
@@ -246,3 +251,34 @@ class PcsData:
             self.ldes = []
             lib().bfo_pcs_data_free(self._h)
             self._h = None
+
+
+# ---- tuned CPU baseline (oracle/fast_commit.c) -------------------------------------------------------------------------
+def fast_available():
+    return bool(lib().bfo_fast_available())
+
+
+def fast_pcs_commit(mat, want_lde=False):
+    """`Pcs::commit` of ONE matrix on the natural domain with the AVX-512 / Montgomery / cache-blocked implementation
+    (the CPU arm bench.py times).  Returns (root, lde or None, {phase: seconds}); raises if the host has no AVX-512 or the
+    shape is outside what the fast path covers (rows < 16)."""
+    m = _u32(mat)
+    rows, cols = m.shape
+    root = np.zeros(8, np.uint32)
+    lde = np.zeros((2 * rows, cols), np.uint32) if want_lde else None
+    ph = (C.c_double * 3)()
+    rc = lib().bfo_fast_pcs_commit(_p(m), rows, cols, _p(root), _p(lde) if want_lde else None, ph)
+    if rc != 0:
+        raise RuntimeError("bfo_fast_pcs_commit: unsupported shape or no AVX-512 on this host")
+    return root, lde, dict(lde=ph[0], leaf_hash=ph[1], compress=ph[2])
+
+
+def fast_release():
+    lib().bfo_fast_release()
+
+
+def fast_permute_many(states):
+    s = _u32(states).copy()
+    if lib().bfo_fast_permute_many(_p(s), s.shape[0]) != 0:
+        raise RuntimeError("bfo_fast_permute_many: needs AVX-512 and a multiple of 16 states")
+    return s

@@ -67,6 +67,14 @@ int bfo_pcs_num_mats(const bfo_pcs_data* d);
 const uint32_t* bfo_pcs_lde(const bfo_pcs_data* d, int i, uint64_t* rows, uint64_t* cols); /* bit-reversed rows */
 const bfo_tree* bfo_pcs_tree(const bfo_pcs_data* d);
 
+/* ---- tuned CPU baseline (fast_commit.c: AVX-512 Montgomery, packed Poseidon2, cache-blocked row NTT) ------------------ */
+int bfo_fast_available(void);
+/* Pcs::commit of one rows x cols matrix (natural domain, log_blowup 1): same root as bfo_pcs_commit.  lde_out may be NULL.
+   phase_sec = {LDE, leaf hashing, compression layers}.  Returns 0, -1 if unsupported (rows < 16, no AVX-512). */
+int bfo_fast_pcs_commit(const uint32_t* in, uint64_t rows, uint64_t cols, uint32_t root[8], uint32_t* lde_out, double phase_sec[3]);
+int bfo_fast_permute_many(uint32_t* states, uint64_t n);
+void bfo_fast_release(void); /* drop the work buffers bfo_fast_pcs_commit keeps between calls */
+
 void bfo_set_threads(int n);
 int bfo_get_threads(void);
 

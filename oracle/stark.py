@@ -25,6 +25,12 @@ GEN = 3
 # Plonky3's TwoAdicFriPcs::open/verify of this API era write every opened value into the challenger
 # before sampling the batching challenge alpha ("Write evaluations to challenger").
 OBSERVE_OPENED_VALUES = True
+# How a reduced opening joins the folded FRI vector when their lengths match: 0 = `folded[i] += ro[i]` (Plonky3 of the pinned API era
+# as published), 1 = `folded[i] += beta^2 * ro[i]` (the later upstream rule).  Mirrors BFGPU_OPT_FRI_ROLLIN.
+FRI_ROLLIN = 0
+# Which valid proof-of-work witness grind() returns: 0 = the smallest, 1 = the largest (BFGPU_OPT_POW_ORDER; the reference's rayon
+# find_any returns an arbitrary one, every valid witness verifies)
+POW_ORDER = 0
 
 U = np.uint64
 
@@ -262,12 +268,12 @@ class Challenger:
 
     def grind(self, bits):
         """smallest witness (the reference searches in parallel with find_any: any valid one is accepted)."""
-        w = 0
+        w, step = (P - 1, -1) if POW_ORDER == 1 else (0, 1)
         while True:
             if self.clone().check_witness(bits, w):
                 assert self.check_witness(bits, w)
                 return w
-            w += 1
+            w += step
 
 
 # ---- two-adic coset domains ---------------------------------------------------------------------------
@@ -418,7 +424,10 @@ def fri_commit_phase(cfg, inputs, ch):
         commits.append(t.root.copy())
         trees.append(t)
         if inputs and inputs[0].shape[0] == folded.shape[0]:
-            folded = e_add(folded, inputs.pop(0))
+            ro = inputs.pop(0)
+            if FRI_ROLLIN == 1:
+                ro = e_mul(np.broadcast_to(e_mul(beta, beta), ro.shape), ro)
+            folded = e_add(folded, ro)
     assert folded.shape[0] == (1 << cfg.log_blowup) and not inputs
     final_poly = folded[0]
     for x in folded:
@@ -468,7 +477,10 @@ def fri_verify(cfg, proof, ch, open_input):
         for k, (beta, comm, step) in enumerate(zip(betas, proof["commit_phase_commits"], qp["commit_phase_openings"])):
             log_folded_height = log_max_height - 1 - k
             if ro and ro[0][0] == log_folded_height + 1:
-                folded = e_add(folded, ro.pop(0)[1])
+                r = ro.pop(0)[1]
+                if FRI_ROLLIN == 1 and k > 0:
+                    r = e_mul(e_mul(betas[k - 1], betas[k - 1]), r)
+                folded = e_add(folded, r)
             evals = [folded, folded]
             evals[(idx ^ 1) % 2] = np.asarray(step["sibling_value"], U)
             flat = np.concatenate(evals).astype(np.uint32)

@@ -17,7 +17,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle  # noqa: E402
+from proofio import serialize, proof_sha256  # noqa: E402
 from oracle import prover as PR, stark as S  # noqa: E402
 
 P = 2130706433
@@ -66,6 +68,22 @@ def main():
             final_poly=np.asarray(proof["opening_proof"]["final_poly"]).tolist(),
             pow_witness=int(proof["opening_proof"]["pow_witness"]),
             query_indices=[int(q["index"]) for q in proof["opening_proof"]["query_proofs"]])
+        proof.pop("_debug", None)
+        words = serialize(proof, pk.names)
+        proofs[name]["proof_words"] = int(words.size)
+        proofs[name]["proof_sha256"] = proof_sha256(words)  # the WHOLE serialised proof (layout: include/bfgpu.h, bfgpu_machine_open)
+        if name == "fibo":
+            # BASELINE config 1 (`test_e2e_core`) at the reference's full parameters: 84 queries, 16 proof-of-work bits
+            # (kb31_poseidon2.rs:54-64), smallest witness.  Only digests are committed (the proof is ~1 MB).
+            full = PR.prove_shard(chips, pk, traces, ch.clone(), S.FriConfig(1, 84, 16))
+            full.pop("_debug", None)
+            fw = serialize(full, pk.names)
+            proofs["fibo_full_parameters"] = dict(
+                stdin=stdin, fri=[1, 84, 16], proof_words=int(fw.size), proof_sha256=proof_sha256(fw),
+                pow_witness=int(full["opening_proof"]["pow_witness"]),
+                commitments={k: np.asarray(full["commitment"][k]).tolist() for k in ("main", "permutation", "quotient")},
+                final_poly=np.asarray(full["opening_proof"]["final_poly"]).tolist(),
+                query_indices=[int(q["index"]) for q in full["opening_proof"]["query_proofs"]])
     v["proofs"] = proofs
     with open(os.path.join(GOLD, "vectors.json"), "w") as f:
         json.dump(v, f, indent=1, sort_keys=True)

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import zkvm_brainfuck_b200 as bf
+from proofio import proof_sha256
 
 pytestmark = pytest.mark.gpu
 P = 2130706433
@@ -72,6 +73,51 @@ def test_program_proof_vectors(ctx, name):
         assert [np.asarray(c).tolist() for c in fri["commit_phase_commits"]] == g["fri_commit_phase_commits"]
         assert np.asarray(fri["final_poly"]).tolist() == g["final_poly"] and int(fri["pow_witness"]) == g["pow_witness"]
         assert [int(q["index"]) for q in fri["query_proofs"]] == g["query_indices"]
+        # the whole serialised proof, byte for byte, against the digest of the oracle's proof
+        words = prover.open_raw(pk, (shard2 := prover.commit_record(rec)), ch.clone())
+        shard2.free()
+        assert int(words.size) == g["proof_words"] and proof_sha256(words) == g["proof_sha256"]
         pk.free()
     finally:
         ctx.set_fri_params(1, 84, 16)
+
+
+def test_fibo_proof_at_full_parameters_is_the_oracle_proof(ctx):
+    """BASELINE config 1 (`test_e2e_core`: fibo.bf, stdin [17]) at the reference's own FRI parameters (84 queries, 16 PoW bits,
+    kb31_poseidon2.rs:54-64): the GPU proof, produced from the program, is byte-identical to the CPU oracle's proof
+    (SHA-256 of the ~0.7 MB serialisation, committed by scripts/gen_golden.py), same PoW witness, same query indices."""
+    g = V["proofs"]["fibo_full_parameters"]
+    ctx.set_fri_params(*g["fri"])
+    prover = bf.CudaProver(ctx)
+    (words, decode), rec = prover.prove_program(open(os.path.join(GOLD, "fibo.bf")).read(), g["stdin"], raw=True)
+    assert rec.output == [85]
+    proof = decode()
+    assert int(proof["opening_proof"]["pow_witness"]) == g["pow_witness"]
+    assert [int(q["index"]) for q in proof["opening_proof"]["query_proofs"]] == g["query_indices"]
+    assert {k: np.asarray(proof["commitment"][k]).tolist() for k in g["commitments"]} == g["commitments"]
+    assert int(words.size) == g["proof_words"] and proof_sha256(words) == g["proof_sha256"]
+
+
+@pytest.mark.parametrize("log_rows", [16, 22])
+def test_bench_workload_root_equals_cpu_oracle_root(ctx, log_rows):
+    """The exact bench.py input (bench_workload, seed 0xB200, 2^22 x 256 = BASELINE config 4) committed on the GPU gives the
+    root the CPU oracle computed for it (tests/golden/bench_roots.json)."""
+    import ctypes as C
+    import torch
+    import bench_workload as W
+    gold = json.load(open(os.path.join(GOLD, "bench_roots.json")))["roots"]
+    key = "log_rows=16,seed=0xB200" if log_rows == 16 else "log_rows=22,seed=0xB200+0"
+    trace = W.trace_torch(1 << log_rows, 256, device="cuda")
+    torch.cuda.synchronize()
+    ctx.set_input_space(bf.MEM_DEVICE)
+    try:
+        mat = bf.Mat(trace.data_ptr(), 1 << log_rows, 256)
+        root = np.zeros(8, np.uint32)
+        h = C.c_void_p()
+        ctx.check(bf.lib().bfgpu_pcs_commit(ctx._h, C.byref(mat), None, 1, root.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(h)))
+        bf.lib().bfgpu_pcs_data_free(h)
+        assert root.tolist() == gold[key]
+    finally:
+        ctx.set_input_space(bf.MEM_HOST)
+        del trace
+        torch.cuda.empty_cache()

@@ -48,6 +48,7 @@ ABI = {
     "bfgpu_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "bfgpu_synchronize": (C.c_int32, [C.c_void_p]),
     "bfgpu_set_fri_params": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "bfgpu_set_transcript_option": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32]),
     "bfgpu_launch_count": (C.c_uint64, [C.c_void_p]),
     "bfgpu_debug_live_blocks": (C.c_uint64, [C.c_void_p]),
     "bfgpu_debug_fail_alloc": (C.c_int32, [C.c_void_p, C.c_int64]),
@@ -89,6 +90,8 @@ ABI = {
     "bfgpu_shard_get_trace": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "bfgpu_verify_shard": (C.c_int32, [_u32p, C.POINTER(C.c_char_p), _u32p, C.c_int32, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                            C.c_char_p, C.c_uint64]),
+    "bfgpu_verify_shard_ex": (C.c_int32, [_u32p, C.POINTER(C.c_char_p), _u32p, C.c_int32, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                              _u32p, C.c_int32, C.c_char_p, C.c_uint64]),
     "bfgpu_dist_commit_begin": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u32p, C.c_int32, C.POINTER(C.c_void_p)]),
     "bfgpu_dist_commit_local_cols": (C.c_uint32, [C.c_void_p, C.c_int32, _u32p]),
     "bfgpu_dist_commit_recv_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),
@@ -183,6 +186,12 @@ class Context:
 
     def set_repr(self, repr):
         self.check(lib().bfgpu_set_repr(self._h, repr))
+
+    OPTIONS = {"observe_opened_values": 0, "fri_rollin": 1, "pow_order": 2}
+
+    def set_transcript_option(self, name, value):
+        """bfgpu_set_transcript_option: the Plonky3-internal choices that cannot be confirmed offline (include/bfgpu.h)."""
+        self.check(lib().bfgpu_set_transcript_option(self._h, self.OPTIONS[name], int(value)))
 
     def set_fri_params(self, log_blowup=1, num_queries=84, pow_bits=16):
         self.check(lib().bfgpu_set_fri_params(self._h, log_blowup, num_queries, pow_bits))
@@ -562,7 +571,7 @@ def _named_mats(named):
     return cn, arr, keep
 
 
-def verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1, num_queries=84, pow_bits=16, repr=REPR_CANONICAL):
+def verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1, num_queries=84, pow_bits=16, repr=REPR_CANONICAL, options=None):
     """`Verifier::verify_shard` (crates/stark/src/verifier.rs:27-216) in native host code, on the serialised proof of
     `CudaProver.open_raw` / `prove_program(raw=True)`.  vk = (preprocessed commitment, names and heights of the
     preprocessed traces in proving-key order: `pk.commit, pk.names, pk.heights`).  Returns None when the proof is
@@ -572,8 +581,11 @@ def verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1,
     names = (C.c_char_p * len(prep_names))(*[n.encode() for n in prep_names])
     logs = _u32([int(h).bit_length() - 1 for h in prep_heights])
     err = C.create_string_buffer(256)
-    rc = lib().bfgpu_verify_shard(com.ctypes.data_as(_u32p), names, logs.ctypes.data_as(_u32p), len(prep_names), words.ctypes.data_as(_u32p), words.size,
-                                  repr, log_blowup, num_queries, pow_bits, err, 256)
+    opt = _u32([1, 0, 0])  # defaults of bfgpu_set_transcript_option
+    for k, v in (options or {}).items():
+        opt[Context.OPTIONS[k]] = int(v)
+    rc = lib().bfgpu_verify_shard_ex(com.ctypes.data_as(_u32p), names, logs.ctypes.data_as(_u32p), len(prep_names), words.ctypes.data_as(_u32p), words.size,
+                                     repr, log_blowup, num_queries, pow_bits, opt.ctypes.data_as(_u32p), 3, err, 256)
     return None if rc == 0 else (err.value.decode() or f"error {rc}")
 
 
@@ -715,8 +727,10 @@ class CudaProver:
         ch = Challenger(self.ctx)
         lib().bfgpu_pk_observe_into(pk._h, ch._h)
         shard = self.commit_record(rec)
-        buf = self.open_raw(pk, shard, ch.clone(), pow_witness)
-        shard.free()
+        try:
+            buf = self.open_raw(pk, shard, ch.clone(), pow_witness)
+        finally:  # a failing open must not keep the main LDEs alive until the garbage collector gets to them
+            shard.free()
         res = (buf, (lambda: self._parse(buf, pk, None))) if raw else self._parse(buf, pk, None)
         return res, rec
 
@@ -759,8 +773,10 @@ class CudaProver:
             ch = Challenger(self.ctx)
             lib().bfgpu_pk_observe_into(pk._h, ch._h)
             shard = self.commit_record(rec)
-            buf = self.open_raw(pk, shard, ch.clone())
-            shard.free()
+            try:
+                buf = self.open_raw(pk, shard, ch.clone())
+            finally:
+                shard.free()
             item = None
             yield buf, rec
             del buf, rec  # the record's page-locked buffer goes back to the context's pool for the next execution
@@ -788,14 +804,13 @@ class CudaProver:
         raw=True returns (serialised proof words, decoder) so that callers can time the prover without the Python decoding."""
         lib().bfgpu_pk_observe_into(pk._h, challenger._h)
         shard = self.commit(traces)
-        if raw:
-            buf = self.open_raw(pk, shard, challenger.clone(), pow_witness)
-            names, heights = list(shard.names), list(shard.heights)
+        try:
+            if raw:
+                buf = self.open_raw(pk, shard, challenger.clone(), pow_witness)
+                return buf, (lambda: self._parse(buf, pk, None))
+            return self.open(pk, shard, challenger.clone(), pow_witness)
+        finally:
             shard.free()
-            return buf, (lambda: self._parse(buf, pk, None))
-        proof = self.open(pk, shard, challenger.clone(), pow_witness)
-        shard.free()
-        return proof
 
     def _parse(self, buf, pk, shard):
         info = {n: (mw, pw, ew, lo) for n, mw, pw, ew, lo in self.chips}

@@ -101,6 +101,8 @@ struct bfgpu_ctx {
     std::unordered_map<void*, size_t> export_live;
     // allocation scopes (AllocScope): blocks taken by an entry point that has not yet handed them to a returned object
     std::vector<std::vector<void*>*> scopes;
+    // transcript options (bfgpu_set_transcript_option): the choices inside Plonky3 that cannot be confirmed offline (SURVEY.md P3 marks)
+    uint32_t opt[BFGPU_NUM_OPTS] = {1, 0, 0};
     // test hook (bfgpu_debug_fail_alloc): the n-th dalloc from now fails with BFGPU_ERR_OOM
     int64_t fail_alloc_in = -1;
 };
@@ -442,6 +444,11 @@ extern "C" int32_t bfgpu_set_fri_params(bfgpu_ctx* ctx, uint32_t log_blowup, uin
     ctx->log_blowup = log_blowup;
     ctx->num_queries = num_queries;
     ctx->pow_bits = pow_bits;
+    return BFGPU_OK;
+}
+extern "C" int32_t bfgpu_set_transcript_option(bfgpu_ctx* ctx, int32_t option, uint32_t value) {
+    if (!ctx || option < 0 || option >= BFGPU_NUM_OPTS || value > 1) return fail(ctx, BFGPU_ERR_INVALID, "bad transcript option %d = %u", option, value);
+    ctx->opt[option] = value;
     return BFGPU_OK;
 }
 extern "C" uint64_t bfgpu_launch_count(const bfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -1701,7 +1708,7 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
             for (auto& ys : mp.ys)
                 for (auto& y : ys) {
                     for (int k = 0; k < 4; k++) flat.push_back(out_word(ctx, y.c[k]));
-                    ch.observe_ext(y);
+                    if (ctx->opt[BFGPU_OPT_OBSERVE_OPENED_VALUES]) ch.observe_ext(y);
                 }
     const kb::Ext alpha = ch.sample_ext();
 
@@ -1819,6 +1826,7 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
                 ta.log_len = ilog2(len);
                 ta.nrounds = ta.log_len - log_blowup;
                 ta.tw = ctx->d_tw;
+                ta.rollin = (int)ctx->opt[BFGPU_OPT_FRI_ROLLIN];
                 ta.ch = d_ch;
                 ta.roots = d_roots + 8 * (size_t)round;
                 ta.vec[0] = folded;
@@ -1881,7 +1889,8 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
             TRY(dalloc(ctx, (void**)&next, nlen * 16));
             const uint32_t* add = nullptr;
             if (it != reduced.end() && (1ull << it->first) == nlen) add = it->second;
-            openk::k_fri_fold_dev<<<(unsigned)((nlen + 127) / 128), 128, 0, ctx->stream>>>(folded, next, add, log_nlen, d_betas + 4 * (size_t)round, ctx->d_tw);
+            openk::k_fri_fold_dev<<<(unsigned)((nlen + 127) / 128), 128, 0, ctx->stream>>>(folded, next, add, log_nlen, d_betas + 4 * (size_t)round, ctx->d_tw,
+                                                                                         (int)ctx->opt[BFGPU_OPT_FRI_ROLLIN]);
             LAUNCHED(ctx);
             CU(cudaGetLastError());
             if (add) {
@@ -1939,16 +1948,23 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
             // (2^bits candidates on average), the following ones are bigger
             const uint32_t mask = (1u << ctx->pow_bits) - 1;
             uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(4ull << ctx->pow_bits, 1u << 14), 1u << 22);
-            unsigned int best = 0xffffffffu;
-            for (uint64_t start = 0; start < kb::P && best == 0xffffffffu; start += batch, batch = std::min<uint64_t>(batch * 4, 1u << 24)) {
+            // BFGPU_OPT_POW_ORDER: 0 = the smallest witness (ascending batches), 1 = the largest one below p (descending batches).
+            // The reference's rayon `find_any` returns an arbitrary valid witness; both ends are deterministic.
+            const bool desc = ctx->opt[BFGPU_OPT_POW_ORDER] == 1;
+            const unsigned int none = desc ? 0u : 0xffffffffu;
+            unsigned int best = none;
+            for (uint64_t done = 0; done < kb::P && best == none; done += batch, batch = std::min<uint64_t>(batch * 4, 1u << 24)) {
                 TRY(upload_small(ctx, d_best, &best, 4));
-                uint32_t count = (uint32_t)std::min<uint64_t>(batch, kb::P - start);
-                openk::k_pow_grind<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_st, pos, mask, (uint32_t)start, count, d_best);
+                uint32_t count = (uint32_t)std::min<uint64_t>(batch, kb::P - done);
+                uint32_t start = desc ? (uint32_t)(kb::P - done - count) : (uint32_t)done;
+                openk::k_pow_grind<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_st, pos, mask, start, count, d_best, desc ? 1 : 0);
                 LAUNCHED(ctx);
                 CU(cudaGetLastError());
                 CU(cudaMemcpyAsync(&best, d_best, 4, cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cudaStreamSynchronize(ctx->stream));
             }
+            if (desc && best != none) best -= 1;  // the kernel stores w + 1
+            else if (desc) best = 0xffffffffu;
             dfree(ctx, d_st);
             dfree(ctx, d_best);
             if (best == 0xffffffffu) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "proof-of-work search failed"); }

@@ -204,8 +204,10 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
 }
 
 // ---- FRI fold: out[i] = (1/2 + b g^-br(i)) in[2i] + (1/2 - b g^-br(i)) in[2i+1] (+ add[i]),  b = beta/2 -----
+// rollin: how the reduced opening of the new height enters (BFGPU_OPT_FRI_ROLLIN): 0 = plain sum (Plonky3 of the pinned API era),
+// 1 = beta^2 * add[i] (the later upstream rule), beta being this round's folding challenge
 __device__ __forceinline__ void fri_fold_one(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h,
-                                             Ext half_beta, const uint32_t* __restrict__ tw, uint32_t i) {
+                                             Ext half_beta, const uint32_t* __restrict__ tw, uint32_t i, int rollin = 0) {
     // g = generator of order 2^(log_h+1); g^-j = w^(2^(log_h+1) - j)
     uint32_t j = kb::bitrev(i, log_h);
     uint32_t ginv = j ? root_pow(tw, log_h + 1, (1u << (log_h + 1)) - j) : kb::ONE;
@@ -216,7 +218,11 @@ __device__ __forceinline__ void fri_fold_one(const uint32_t* __restrict__ in, ui
     a.c[0] = kb::add(a.c[0], half);
     b.c[0] = kb::add(b.c[0], half);
     Ext o = kb::ext_add(kb::ext_mul(a, lo), kb::ext_mul(b, hi));
-    if (add) o = kb::ext_add(o, ld_ext(add + 4 * (uint64_t)i));
+    if (add) {
+        Ext r = ld_ext(add + 4 * (uint64_t)i);
+        if (rollin == 1) r = kb::ext_mul(kb::ext_sqr(kb::ext_add(half_beta, half_beta)), r);
+        o = kb::ext_add(o, r);
+    }
     st_ext(out + 4 * (uint64_t)i, o);
 }
 __global__ void k_fri_fold(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h /* out length */,
@@ -284,11 +290,11 @@ __global__ void __launch_bounds__(32) k_challenger_round(uint32_t* __restrict__ 
 }
 // fold with beta read from device memory (written by k_challenger_round)
 __global__ void k_fri_fold_dev(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h,
-                               const uint32_t* __restrict__ beta, const uint32_t* __restrict__ tw) {
+                               const uint32_t* __restrict__ beta, const uint32_t* __restrict__ tw, int rollin) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (1u << log_h)) return;
     const Ext half_beta = kb::ext_scale(ld_ext(beta), kb::halve(kb::ONE));
-    fri_fold_one(in, out, add, log_h, half_beta, tw, i);
+    fri_fold_one(in, out, add, log_h, half_beta, tw, i, rollin);
 }
 
 // ---- FRI tail: every commit-phase round whose input has at most 2^TAIL_MAX_LOG elements, in ONE single-CTA launch -----
@@ -302,6 +308,7 @@ constexpr int TAIL_MAX_LOG = 11, TAIL_THREADS = 1024, TAIL_MAX_ROUNDS = 11;
 struct FriTailArgs {
     uint32_t* vec[TAIL_MAX_ROUNDS + 1];              // vec[r]: input of round r, 2^(log_len - r) elements; vec[nrounds]: final vector
     const uint32_t* add[TAIL_MAX_ROUNDS];            // reduced opening added to the output of round r, or null
+    int rollin;                                      // BFGPU_OPT_FRI_ROLLIN
     uint32_t* layer[TAIL_MAX_ROUNDS][TAIL_MAX_LOG];  // layer[r][l]: 2^(log_len - r - 1 - l) digests, l = 0 .. log_len - r - 1
     uint32_t* roots;                                 // nrounds x 8
     uint32_t log_len, nrounds;
@@ -435,14 +442,14 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_fri_tail(FriTailArgs A) {
         __syncthreads();
         // ---- fold -------------------------------------------------------------------------------------------------------------
         const Ext half_beta = kb::ext_scale(Ext{{s_beta[0], s_beta[1], s_beta[2], s_beta[3]}}, kb::halve(kb::ONE));
-        for (uint32_t i = t; i < n; i += TAIL_THREADS) fri_fold_one(vin, A.vec[r + 1], A.add[r], log_n, half_beta, A.tw, i);
+        for (uint32_t i = t; i < n; i += TAIL_THREADS) fri_fold_one(vin, A.vec[r + 1], A.add[r], log_n, half_beta, A.tw, i, A.rollin);
         __syncthreads();  // the next round reads vec[r + 1] (same CTA: block-level visibility suffices)
     }
 }
 
-// ---- proof of work: smallest w in [start, start+count) with (permute(state | w at pos)[7] & mask) == 0 ------
+// ---- proof of work: smallest (descending: largest) w in [start, start+count) with (permute(state | w at pos)[7] & mask) == 0 ------
 __global__ void __launch_bounds__(128) k_pow_grind(const uint32_t* __restrict__ state16, uint32_t pos, uint32_t mask, uint32_t start, uint32_t count,
-                                                   unsigned int* __restrict__ best) {
+                                                   unsigned int* __restrict__ best, int descending) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     uint32_t w = start + i;  // canonical candidate
@@ -454,7 +461,10 @@ __global__ void __launch_bounds__(128) k_pow_grind(const uint32_t* __restrict__ 
     for (int k = 0; k < 8; k++)
         if ((uint32_t)k == pos) s[k] = wm;
     p2::permute(s);
-    if ((kb::from_mont(s[7]) & mask) == 0) atomicMin(best, w);
+    if ((kb::from_mont(s[7]) & mask) == 0) {
+        if (descending) atomicMax(best, w + 1);  // 0 = nothing found
+        else atomicMin(best, w);
+    }
 }
 
 // ---- query gathers: out[i] = *src[i] (optionally converted to canonical) -----------------------------------

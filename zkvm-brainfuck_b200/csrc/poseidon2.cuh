@@ -101,8 +101,13 @@ KB_D uint32_t mul_diag(uint32_t x, int i) {
 // (a Montgomery reduction by 2^k whose quotient digit is read off the low bits).  The Shoup product this replaces costs
 // IMAD.HI + 2 IMAD on the FMA-heavy pipe, the busy one in the hash kernels (profiles/r1_leaf_hash_final.md); this form is
 // AND + shift + one small multiply (or shift/subtract, P2_DIAG_SHIFT=2) and two modular add/subs on the ALU pipe.
+// MEASURED (round 2, gpurun_out/r2_c1_*): leaf hash 48.25 ms with this form against 46.74 ms with the Shoup products at 2^23 x 32
+// permutations, although the internal-round body drops from 66 to 47 FMA-pipe slots (cuobjdump).  tools/p2_bench.cu with 0..44 of the M4
+// additions pinned to the ALU pipe on top moves the result by +-1 % only (49.1 .. 50.0 clk/permutation/SM): the kernel sits at the
+// ~0.68 warp-instructions/clk/scheduler that mixed three-operand integer code issues on this part (same ceiling as the IMAD+VIADDMNMX
+// probes in profiles/r1_pipe_probe.txt), so moving work between the two pipes buys nothing; only fewer instructions would.  Off.
 #ifndef P2_DIAG_SHIFT
-#define P2_DIAG_SHIFT 1
+#define P2_DIAG_SHIFT 0
 #endif
 template <int K, bool NEG>
 KB_D uint32_t diag_pow2(uint32_t x, uint32_t sum) {

@@ -147,7 +147,8 @@ static std::string fmt(const char* f, ...) {
 
 // returns "" when the proof is accepted, else the reference's error name (+ detail)
 static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std::pair<int, unsigned>>& prep /* (chip index, log height), pk order */,
-                          const uint32_t* words, uint64_t n_words, bool monty, unsigned log_blowup, unsigned num_queries, unsigned pow_bits) {
+                          const uint32_t* words, uint64_t n_words, bool monty, unsigned log_blowup, unsigned num_queries, unsigned pow_bits,
+                          const uint32_t opt[BFGPU_NUM_OPTS]) {
     Reader rd{words, n_words, 0, monty};
     uint32_t vk_commit[8];
     for (int i = 0; i < 8; i++) {
@@ -217,7 +218,8 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
     for (auto& r : rounds)
         for (auto& m : r.mats)
             for (auto& v : m.values)
-                for (auto& e : v) ch.observe_ext(e);
+                for (auto& e : v)
+                    if (opt[BFGPU_OPT_OBSERVE_OPENED_VALUES]) ch.observe_ext(e);
     const Ext fri_alpha = ch.sample_ext();
     const uint32_t n_commit = rd.raw();
     if (!rd.ok || n_commit == 0 || n_commit > (unsigned)kb::TWO_ADICITY - log_blowup) return "InvalidProofShape";
@@ -290,7 +292,10 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
         for (uint32_t k = 0; k < n_commit; k++) {
             const unsigned lfh = log_max - 1 - k;
             if (it != ro.end() && it->first == lfh + 1) {
-                folded = kb::ext_add(folded, it->second);
+                // rolled in right after the fold of round k-1: plain, or scaled by that round's beta^2 (BFGPU_OPT_FRI_ROLLIN)
+                Ext r = it->second;
+                if (opt[BFGPU_OPT_FRI_ROLLIN] == 1 && k > 0) r = kb::ext_mul(kb::ext_sqr(betas[k - 1]), r);
+                folded = kb::ext_add(folded, r);
                 ++it;
             }
             Ext ev[2] = {folded, folded};
@@ -392,9 +397,9 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
 // vk = preprocessed commitment + (chip name, log height) of every preprocessed trace in proving-key order.
 // repr: representation of vk_commit and of the proof words (BFGPU_REPR_*).  Returns BFGPU_OK when the proof is accepted;
 // otherwise BFGPU_ERR_INVALID with the reference's error name in `err`.
-extern "C" int32_t bfgpu_verify_shard(const uint32_t vk_commit[8], const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep,
-                                      const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits,
-                                      char* err, uint64_t err_len) {
+extern "C" int32_t bfgpu_verify_shard_ex(const uint32_t vk_commit[8], const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep,
+                                         const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits,
+                                         const uint32_t* options, int32_t n_options, char* err, uint64_t err_len) {
     auto say = [&](const std::string& s) {
         if (err && err_len) snprintf(err, (size_t)err_len, "%s", s.c_str());
     };
@@ -411,7 +416,15 @@ extern "C" int32_t bfgpu_verify_shard(const uint32_t vk_commit[8], const char* c
         }
         prep.emplace_back(ci, prep_log_heights[i]);
     }
-    std::string e = verifier::verify(vk_commit, prep, proof, n_words, repr == BFGPU_REPR_MONTY, log_blowup, num_queries, pow_bits);
+    uint32_t opt[BFGPU_NUM_OPTS] = {1, 0, 0};
+    for (int32_t i = 0; options && i < n_options && i < BFGPU_NUM_OPTS; i++) opt[i] = options[i];
+    std::string e = verifier::verify(vk_commit, prep, proof, n_words, repr == BFGPU_REPR_MONTY, log_blowup, num_queries, pow_bits, opt);
     say(e);
     return e.empty() ? BFGPU_OK : BFGPU_ERR_INVALID;
+}
+extern "C" int32_t bfgpu_verify_shard(const uint32_t vk_commit[8], const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep,
+                                      const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits,
+                                      char* err, uint64_t err_len) {
+    return bfgpu_verify_shard_ex(vk_commit, prep_names, prep_log_heights, n_prep, proof, n_words, repr, log_blowup, num_queries, pow_bits, nullptr, 0, err,
+                                 err_len);
 }
