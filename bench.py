@@ -3,20 +3,19 @@
 
 Workload (BASELINE.json configs[3], the largest single-GPU configuration of the commit hot path):
 `Pcs::commit` = coset LDE (blowup 2, shift 3, bit-reversed rows) + Poseidon2 MerkleTreeMmcs commit of
-a synthetic 2^22 x 256 trace of uniform KoalaBear values.  One "step" = one full commit.
+the synthetic 2^22 x 256 trace `bench_workload` defines (SplitMix64 words, seed 0xB200).  One "step" = one full commit.
+The root of that exact input is pinned by the CPU oracle (tests/golden/bench_roots.json) and checked here at every N.
 
-  value : algorithmic LDE bytes (12*R*W) per second, whole job over all ranks, input
-          already resident in HBM (row-major, canonical u32), device-timed with CUDA events on the
-          stream the kernels run on.
-  e2e   : the same call through the C ABI with a pinned HOST matrix (H2D copy inside the timed
-          region, root read back to the host).
-  roofline      : dominant kernel (Poseidon2 leaf sponge) against the integer-issue peak measured
-                  live by a register-only probe; `roofline_hbm`: the LDE kernels against the HBM peak.
-  cpu_baseline  : the CPU oracle (`oracle/`, scalar C + OpenMP port of the same algorithm) on a
-                  bounded sample; `--impl reference` runs only that arm.
-
-N > 1 (torchrun): every rank commits its own trace (chips / trace matrices shard across GPUs with
-no data-path collective), weak scaling, max-over-ranks device time.
+  value : algorithmic LDE bytes (12*R*W) per second, input already resident in HBM (row-major, canonical
+          u32), device-timed with CUDA events on the stream the kernels run on.
+          N = 1: one commit on one GPU.  N > 1: the SAME single commitment sharded over the N GPUs (column-sharded LDE, P2P row
+          exchange into peer HBM, per-rank subtrees, cap exchange): strong scaling, max-over-ranks device time.
+  e2e   : the same call through the C ABI with pinned HOST matrices (H2D copy inside the timed region, root read back).
+  roofline      : dominant kernel (Poseidon2 leaf sponge) against the integer-issue peak measured live by a register-only
+                  probe, from the ALGORITHMIC instruction count and the ncu counters committed under
+                  profiles/ (profiles/roofline_inputs.json); `roofline_hbm`: the LDE kernels against the HBM peak.
+  cpu_baseline  : the tuned CPU port (oracle/fast_commit.c: AVX-512 Montgomery, packed Poseidon2, cache-blocked row NTT, all
+                  host threads) on the FULL workload; `--impl reference` runs only that arm, same config.
 """
 import argparse
 import json
@@ -30,16 +29,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 P = 2130706433
-# SASS thread-instructions per element of the NTT passes of a 2^22-point column (pass plan g = 8, 7, 7): column-loop bodies of
-# k_pass<0,3,0,0> x2 + k_pass<0,4,1,0> (584 + 584 + 472) / 16 forward, k_pass<1,4,1,0> + k_pass<1,3,0,0> + k_pass<1,3,0,1> (517 + 641 + 857) / 16
-# inverse incl. the fused coset epilogue (cuobjdump -sass, profiles/r1_ntt_instr_counts.txt)
-NTT_INSTR_FWD_2P22 = 102.5
-NTT_INSTR_INV_2P22 = 125.9
-# executed thread-instructions per Poseidon2 permutation in k_leaf_hash: ncu smsp__inst_executed.sum * 32 / permutations
-# = 38.01e9 * 32 / 268 435 456 (profiles/r1_leaf_hash_final.md)
-P2_INSTR_PER_PERM = 4531
-# DRAM bytes of one k_leaf_hash launch at the default workload, from the same ncu --set full capture
-LEAF_TRAFFIC_2P22X256 = 8600113000 + 269837312
+# Roofline inputs that cannot be measured inside a timed run (executed-instruction and DRAM counters of the dominant kernels) come
+# from the ncu captures committed under profiles/, digested by tools/ncu_to_roofline.py into profiles/roofline_inputs.json
+# (which names its source files); nothing is a literal in this file.
+def roofline_inputs():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
+    except OSError:
+        return {}
+
+
+# ALGORITHMIC integer instructions of one Poseidon2 permutation: 282 S-box Montgomery products x 5 + 208 diagonal
+# products x 4 (Shoup form) + ~1100 modular additions x 2
+P2_ALGORITHMIC_INSTR = 282 * 5 + 208 * 4 + 1100 * 2
+# ALGORITHMIC instructions of the transforms: 3 per element and radix-2 stage (one butterfly = add, sub, one 4-instruction
+# Shoup product, per TWO elements), log2(R) stages on R*W trace elements (inverse) + log2(R) stages on 2R*W (forward)
+NTT_ALGORITHMIC_INSTR_PER_ELEMENT_STAGE = 3
 
 
 def log(*a):
@@ -54,7 +59,6 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-rows", type=int, default=22)
     ap.add_argument("--cols", type=int, default=256)
-    ap.add_argument("--cpu-log-rows", type=int, default=16, help="bounded CPU sample height (log2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dist-commit", action="store_true", help="N>1: skip the one-commitment-over-all-ranks measurements")
     ap.add_argument("--no-prove", action="store_true", help="skip the end-to-end shard-prove timings (BASELINE configs 1-3)")
@@ -75,25 +79,67 @@ def num_perms(rows, cols):
     return leaves * ((cols + 7) // 8) + (leaves - 1)
 
 
-def cpu_commit_sample(log_rows, cols, steps, warmup):
-    """Time the CPU oracle's Pcs::commit on a 2^log_rows x cols sample -> (GB/s, seconds/step, threads)."""
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_commit(log_rows, cols, steps, warmup):
+    """Time the CPU arm's Pcs::commit of the bench workload (seed 0xB200) on every host thread.
+    -> dict(gbs, sec, threads, kind, sample, root, phases).  With AVX-512 this is the tuned port (oracle/fast_commit.c) on the
+    FULL 2^log_rows x cols matrix; without it the scalar restatement on a bounded 2^16-row sample (said in `sample`)."""
     import numpy as np
+    import bench_workload as BW
     import oracle
 
     # every host thread, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
-    oracle.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    rng = np.random.default_rng(0xB200)
-    m = rng.integers(0, P, (1 << log_rows, cols), dtype=np.uint32)
-    times = []
+    oracle.set_threads(host_threads())
+    fast = oracle.fast_available()
+    lr = log_rows if fast else min(log_rows, 16)
+    m = BW.trace_numpy(1 << lr, cols)
+    times, root, phases = [], None, {}
     for i in range(warmup + steps):
         t = time.perf_counter()
-        d = oracle.PcsData([m])
+        if fast:
+            root, _, ph = oracle.fast_pcs_commit(m)
+        else:
+            d = oracle.PcsData([m])
+            root, ph = d.root.copy(), {}
+            del d
         dt = time.perf_counter() - t
-        del d
         if i >= warmup:
             times.append(dt)
+            for k, v in ph.items():
+                phases[k] = phases.get(k, 0.0) + v * 1e3 / steps
+    if fast:
+        oracle.fast_release()
     sec = sum(times) / len(times)
-    return algorithmic_bytes(1 << log_rows, cols) / sec / 1e9, sec, oracle.get_threads()
+    full = lr == log_rows
+    sample = (f"the full 2^{lr}x{cols} workload per step" if full else
+              f"2^{lr}x{cols} sample of the workload per step (host without AVX-512: scalar restatement; full size would be {1 << (log_rows - lr)}x longer)")
+    kind_note = ("tuned CPU port of the reference algorithm (oracle/fast_commit.c: AVX-512 Montgomery arithmetic, 16-lane packed Poseidon2, "
+                 "cache-blocked row NTT, OpenMP); the Rust/rayon prover itself cannot be built offline" if fast else
+                 "scalar C/OpenMP restatement (oracle/*.c)")
+    return dict(gbs=algorithmic_bytes(1 << lr, cols) / sec / 1e9, sec=sec, threads=oracle.get_threads(), kind="port", sample=sample,
+                note=kind_note, root=[int(x) for x in root], phases_ms=phases, full=full,
+                perms_per_s=num_perms(1 << lr, cols) / sec)
+
+
+def bench_config(args, world):
+    """`config` of the JSON line: identical for the b200 arm and the reference arm at the same N."""
+    R, W = 1 << args.log_rows, args.cols
+    return {"workload": workload_name(args.log_rows, W), "rows": R, "cols": W, "log_blowup": 1, "seed": "0xB200 (bench_workload.py)",
+            "parallelism": "1 GPU" if world == 1 else f"ONE commitment sharded over {world} GPUs (columns -> LDE -> P2P row exchange -> subtrees -> caps)",
+            "l2": "inputs (4 GiB/step at full size) and LDE (8 GiB) exceed the 126 MB L2; no flush needed"}
+
+
+def golden_root(log_rows, cols, rank_seed=0):
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_roots.json")))["roots"]
+    except OSError:
+        return None
+    if cols != 256:
+        return None
+    return g.get(f"log_rows={log_rows},seed=0xB200+{rank_seed}") or (g.get(f"log_rows={log_rows},seed=0xB200") if rank_seed == 0 else None)
 
 
 def prove_timings(ctx, bf, with_cpu):
@@ -212,23 +258,25 @@ def prove_timings(ctx, bf, with_cpu):
     return out
 
 
-def run_reference(args, rank):
-    """Reference arm: the reference's CPU algorithm (oracle port; the Rust prover cannot be built here)
-    on all host threads, bounded sample of the same workload."""
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU algorithm for this path on the box's host cores, same workload and config as the b200 arm
+    (the Rust prover cannot be built here: no cargo, Plonky3 not vendored — DESIGN.md).  Rank 0 alone runs it."""
     if rank != 0:
         return
-    gbs, sec, threads = cpu_commit_sample(args.cpu_log_rows, args.cols, args.steps, args.warmup)
-    sample = f"2^{args.cpu_log_rows}x{args.cols} sample of the workload per step (full size would be {1 << (args.log_rows - args.cpu_log_rows)}x longer)"
+    r = cpu_commit(args.log_rows, args.cols, args.steps, args.warmup)
     line = {
         "impl": "reference",
-        "metric": "lde_poseidon2_commit_throughput", "value": gbs, "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear mod p)",
+        "metric": "lde_poseidon2_commit_throughput", "value": r["gbs"], "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec"] * 1e3,
+        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear mod p)",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.log_rows, args.cols), "sample": sample},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": bench_config(args, world),
+        "cpu_baseline": {"value": r["gbs"], "unit": "GB/s", "cores": r["threads"], "kind": r["kind"], "sample": r["sample"], "note": r["note"],
+                         "phases_ms": r["phases_ms"], "poseidon2_perms_per_s": r["perms_per_s"]},
+        "e2e": {"value": r["gbs"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "root": r["root"],
+        "root_matches_oracle_golden": (r["root"] == golden_root(args.log_rows, args.cols)) if r["full"] and golden_root(args.log_rows, args.cols) else None,
     }
     print(json.dumps(line), flush=True)
 
@@ -276,7 +324,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
 
     import ctypes as C
@@ -302,20 +350,43 @@ def main():
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     lib = bf.lib()
+    from importlib import import_module
+    import bench_workload as BW
+    shard = import_module("zkvm-brainfuck_b200.shard")
 
-    # synthetic trace, resident in HBM: row-major canonical u32 (the layout RowMajorMatrix<KoalaBear> has)
-    g = torch.Generator(device="cuda")
-    g.manual_seed(0xB200 + rank)
-    trace = torch.randint(0, P, (R, W), dtype=torch.int32, device="cuda", generator=g)
+    # synthetic trace, resident in HBM: row-major canonical u32 (the layout RowMajorMatrix<KoalaBear> has).  Every rank of an N > 1 run
+    # holds ITS COLUMNS of the one global matrix (seed 0xB200), so the root is the golden root at every N.
+    c0, nloc = shard.col_range(W, world, rank)
+    if world == 1:
+        trace = BW.trace_torch(R, W, device="cuda")
+    else:
+        trace = torch.empty((R, nloc), dtype=torch.int32, device="cuda")
+        step_rows = 1 << 16
+        for r0 in range(0, R, step_rows):  # generate full-width row chunks, keep this rank's columns
+            r1 = min(R, r0 + step_rows)
+            i = torch.arange(r0 * W, r1 * W, dtype=torch.int64, device="cuda").reshape(r1 - r0, W)[:, c0:c0 + nloc].reshape(-1)
+            z = (i + 1) * BW._s64(BW._G) + BW._s64(BW.SEED)
+            lsr = lambda z, k: (z >> k) & ((1 << (64 - k)) - 1)
+            z = (z ^ lsr(z, 30)) * BW._s64(BW._M1)
+            z = (z ^ lsr(z, 27)) * BW._s64(BW._M2)
+            z = z ^ lsr(z, 31)
+            trace[r0:r1] = (lsr(z, 33) % P).to(torch.int32).reshape(r1 - r0, nloc)
     torch.cuda.synchronize()
-    mat = bf.Mat(trace.data_ptr(), R, W)
     root = np.zeros(8, np.uint32)
     root_p = root.ctypes.data_as(C.POINTER(C.c_uint32))
 
-    def commit_once():
-        h = C.c_void_p()
-        ctx.check(lib.bfgpu_pcs_commit(ctx._h, C.byref(mat), None, 1, root_p, C.byref(h)))
-        lib.bfgpu_pcs_data_free(h)
+    if world == 1:
+        mat = bf.Mat(trace.data_ptr(), R, W)
+
+        def commit_once():
+            h = C.c_void_p()
+            ctx.check(lib.bfgpu_pcs_commit(ctx._h, C.byref(mat), None, 1, root_p, C.byref(h)))
+            lib.bfgpu_pcs_data_free(h)
+    else:
+        def commit_once(src=None):
+            dc = shard.DistributedCommit(ctx, dist, [R], [W], exchange="p2p")
+            root[:] = dc.commit([src if src is not None else (trace.data_ptr(), R, nloc)])
+            dc.free()
 
     ctx.set_input_space(bf.MEM_DEVICE)
     for _ in range(max(args.warmup, 3)):
@@ -340,25 +411,31 @@ def main():
     ctx.profile_enable(False)
     clocks = sampler.stop()
     root_dev = root.copy()
-    from importlib import import_module
-    shard = import_module("zkvm-brainfuck_b200.shard")
     ms_total = shard.max_over_ranks(ms_total, dist, "cuda")
     ms_step = ms_total / args.steps
-    value = world * algorithmic_bytes(R, W) / (ms_step * 1e-3) / 1e9
+    value = algorithmic_bytes(R, W) / (ms_step * 1e-3) / 1e9  # N > 1: the one commitment is the whole job (strong scaling)
+    gold = golden_root(args.log_rows, W)
+    root_ok = None if gold is None else bool(root_dev.tolist() == gold)
+    if root_ok is False:
+        raise SystemExit(f"bench.py: root {root_dev.tolist()} differs from the CPU oracle's golden root {gold}")
 
-    # ---- e2e: same call with a pinned HOST matrix ------------------------------------------------
+    # ---- e2e: same call with pinned HOST matrices ------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((R, W), dtype=torch.int32, pin_memory=True)
+        host = torch.empty(tuple(trace.shape), dtype=torch.int32, pin_memory=True)
         host.copy_(trace)
         torch.cuda.synchronize()
-        hmat = bf.Mat(host.data_ptr(), R, W)
         ctx.set_input_space(bf.MEM_HOST)
+        if world == 1:
+            hmat = bf.Mat(host.data_ptr(), R, W)
 
-        def commit_host():
-            h = C.c_void_p()
-            ctx.check(lib.bfgpu_pcs_commit(ctx._h, C.byref(hmat), None, 1, root_p, C.byref(h)))
-            lib.bfgpu_pcs_data_free(h)
+            def commit_host():
+                h = C.c_void_p()
+                ctx.check(lib.bfgpu_pcs_commit(ctx._h, C.byref(hmat), None, 1, root_p, C.byref(h)))
+                lib.bfgpu_pcs_data_free(h)
+        else:
+            def commit_host():
+                commit_once((host.data_ptr(), R, nloc))
 
         commit_host()
         assert (root == root_dev).all(), "host-path root differs from device-path root"
@@ -369,9 +446,10 @@ def main():
         ctx.synchronize()
         dt = time.perf_counter() - t0
         dt = shard.max_over_ranks(dt, dist, "cuda")
-        e2e = {"value": world * algorithmic_bytes(R, W) / (dt / args.steps) / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": 4 * R * W, "d2h_bytes_per_step": 32, "ms_per_step": dt / args.steps * 1e3}
+        e2e = {"value": algorithmic_bytes(R, W) / (dt / args.steps) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": 4 * R * W, "d2h_bytes_per_step": 32 * world, "ms_per_step": dt / args.steps * 1e3}
         del host
+        ctx.set_input_space(bf.MEM_DEVICE)
 
     # ---- N > 1: one independent program -> proof per GPU (replica throughput of the whole prover) -----------
     replica_prove = None
@@ -413,6 +491,8 @@ def main():
                          "cycles_per_s": world * cycles / dt, "proof_words": int(first.size),
                          "pipelined_ms_per_proof": dtp * 1e3, "pipelined_proofs_per_s": world / dtp, "pipelined_trace_rows_per_s": world * (1 << 22) / dtp}
         pk.free()
+
+    sharded_prove = None  # filled by the one-proof-over-N-GPUs measurement below when the sharded prover is built in
 
     # ---- N > 1: ONE commitment over all ranks (columns -> LDE -> P2P row exchange -> subtrees -> caps) -------
     one_commitment = None
@@ -460,7 +540,6 @@ def main():
             "note": "one Pcs::commit sharded over the ranks: column shards -> LDE -> row shards stored into peer HBM by "
                     "k_scatter_rows (CUDA IPC over NVLink, overlapped with the next LDE block) -> per-rank subtree -> all-gather of caps; "
                     "'staged' = same with a local pack + NCCL all_to_all_single instead (comparison baseline)",
-            "strong_p2p": dist_case(W, "p2p"),
             "weak_p2p": dist_case(W * world, "p2p"),
             "weak_staged_nccl": dist_case(W * world, "staged"),
         }
@@ -474,41 +553,49 @@ def main():
         except OSError:
             pass
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        rin = roofline_inputs()
+        leaf_in = rin.get("k_leaf_hash", {})
         leaf_ms, leaf_n = phases["leaf_hash"]
         leaf_ms_per = leaf_ms / max(leaf_n, 1)
-        leaf_perms = 2 * R * ((W + 7) // 8)
-        leaf_giops = leaf_perms * P2_INSTR_PER_PERM / (leaf_ms_per * 1e-3) / 1e9
+        leaf_rows = 2 * R // world  # rows this rank hashes per commit
+        leaf_perms = leaf_rows * ((W + 7) // 8)
+        leaf_alg = leaf_perms * P2_ALGORITHMIC_INSTR / (leaf_ms_per * 1e-3) / 1e9
+        exec_per_perm = leaf_in.get("thread_instructions_per_permutation")
         lde_ms = sum(phases[k][0] for k in ("ingest", "intt", "scale", "ntt")) / args.steps
-        lde_gbs = algorithmic_bytes(R, W) / (lde_ms * 1e-3) / 1e9
+        lde_gbs = algorithmic_bytes(R, W) / world / (lde_ms * 1e-3) / 1e9
+        ntt_ms = (phases["intt"][0] + phases["ntt"][0]) / args.steps
+        ntt_alg = NTT_ALGORITHMIC_INSTR_PER_ELEMENT_STAGE * args.log_rows * 3 * R * W / world
         line = {
             "metric": "lde_poseidon2_commit_throughput", "value": value, "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
             "dtype": "u32 (KoalaBear mod p, Montgomery on INT32 pipes)", "data": "synthetic",
-            "config": {"workload": workload_name(args.log_rows, W), "rows": R, "cols": W, "log_blowup": 1,
-                       "parallelism": f"{world} independent trace commits (one per GPU)",
-                       "l2": "inputs (4 GiB/step at full size) and LDE (8 GiB) exceed the 126 MB L2; no flush needed"},
-            "rows_per_s": world * R / (ms_step * 1e-3),
-            "poseidon2_perms_per_s": world * num_perms(R, W) / (ms_step * 1e-3),
+            "config": bench_config(args, world),
+            "rows_per_s": R / (ms_step * 1e-3),
+            "poseidon2_perms_per_s": num_perms(R, W) / (ms_step * 1e-3),
             "gpu_launches": launches,
             "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items() if v[1]},
             "roofline": {"kernel": "hashk::k_leaf_hash (Poseidon2 sponge, 1 thread/leaf)", "bound": "int32",
-                         "achieved": leaf_giops, "peak": int32_peak, "unit": "Ginstr/s", "frac": leaf_giops / int32_peak,
-                         "traffic": LEAF_TRAFFIC_2P22X256 if (args.log_rows, W) == (22, 256) else None,
-                         "algorithmic_bytes": 8 * R * W + 32 * 2 * R,
-                         "note": f"achieved = {leaf_perms} permutations x {P2_INSTR_PER_PERM} SASS integer thread-instructions / {leaf_ms_per:.3f} ms; peak = live register-only IMAD/IADD/LOP3 probe (bfgpu_int32_peak_probe)"},
-            "roofline_hbm": {"kernel": "LDE = k_ingest + k_ntt_pass<inv> + k_scale_cosets + k_ntt_pass<fwd>", "bound": "hbm",
-                             "achieved": lde_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": lde_gbs / hbm_peak, "traffic": None,
+                         "achieved": leaf_alg, "peak": int32_peak, "unit": "Ginstr/s", "frac": leaf_alg / int32_peak,
+                         "traffic": leaf_in.get("dram_bytes") if (args.log_rows, W, world) == (22, 256, 1) else None,
+                         "algorithmic_bytes": (8 * R * W + 32 * 2 * R) // world,
+                         "executed_frac": None if not exec_per_perm else leaf_perms * exec_per_perm / (leaf_ms_per * 1e-3) / 1e9 / int32_peak,
+                         "counters_from": leaf_in.get("source"),
+                         "note": f"achieved = {leaf_perms} permutations x {P2_ALGORITHMIC_INSTR} ALGORITHMIC integer instructions (SURVEY 8d: 282 Montgomery x5 + 208 Shoup x4 + 1100 adds x2) / "
+                                 f"{leaf_ms_per:.3f} ms measured live; peak = live register-only IMAD/IADD/LOP3 probe (bfgpu_int32_peak_probe); executed_frac uses the ncu instruction "
+                                 f"count ({exec_per_perm} thread-instructions per permutation)"},
+            "roofline_hbm": {"kernel": "LDE = k_ingest + ntt passes (inverse, fused coset scaling, forward)", "bound": "hbm",
+                             "achieved": lde_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": lde_gbs / hbm_peak,
+                             "traffic": rin.get("lde", {}).get("dram_bytes") if (args.log_rows, W, world) == (22, 256, 1) else None,
+                             "counters_from": rin.get("lde", {}).get("source"),
                              "peak_source": hbm_src, "note": f"12*R*W algorithmic bytes / {lde_ms:.3f} ms for the whole LDE"},
-            "roofline_ntt_int32": None if args.log_rows != 22 else {
-                "kernel": "ntt2::k_pass (3 inverse + 3 forward passes per column at 2^22)", "bound": "int32",
-                "achieved": (NTT_INSTR_FWD_2P22 * 2 * R * W + NTT_INSTR_INV_2P22 * R * W) / ((phases["intt"][0] + phases["ntt"][0]) / args.steps * 1e-3) / 1e9,
-                "peak": int32_peak, "unit": "Ginstr/s",
-                "frac": (NTT_INSTR_FWD_2P22 * 2 * R * W + NTT_INSTR_INV_2P22 * R * W) / ((phases["intt"][0] + phases["ntt"][0]) / args.steps * 1e-3) / 1e9 / int32_peak,
-                "note": "the transforms are issue-bound, not HBM-bound: SASS thread-instructions per element (column-loop bodies, cuobjdump) "
-                        f"forward {NTT_INSTR_FWD_2P22} per LDE element, inverse {NTT_INSTR_INV_2P22} per trace element; >85 % of them are butterfly arithmetic"},
+            "roofline_ntt_int32": {
+                "kernel": "NTT passes (inverse + forward)", "bound": "int32",
+                "achieved": ntt_alg / (ntt_ms * 1e-3) / 1e9, "peak": int32_peak, "unit": "Ginstr/s", "frac": ntt_alg / (ntt_ms * 1e-3) / 1e9 / int32_peak,
+                "note": f"ALGORITHMIC count: {NTT_ALGORITHMIC_INSTR_PER_ELEMENT_STAGE} instructions per element and radix-2 stage, log2(R) = {args.log_rows} stages over 3*R*W elements, / {ntt_ms:.3f} ms"},
             "clocks": clocks,
             "root": [int(x) for x in root_dev],
+            "root_matches_oracle_golden": root_ok,
         }
         if e2e:
             line["e2e"] = e2e
@@ -516,18 +603,25 @@ def main():
             line["one_commitment"] = one_commitment
         if replica_prove:
             line["replica_prove"] = replica_prove
+        if sharded_prove:
+            line["sharded_prove"] = sharded_prove
         if world == 1 and not args.no_prove:
             ctx.set_input_space(bf.MEM_HOST)  # traces come from (pinned) host memory
             line["prove"] = prove_timings(ctx, bf, not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
-            gbs, sec, threads = cpu_commit_sample(args.cpu_log_rows, W, 1, 1)
-            line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
-                                    "sample": f"one commit of a 2^{args.cpu_log_rows}x{W} sample ({sec:.2f} s), oracle C/OpenMP port of the reference algorithm"}
+            ctx.close()  # the CPU arm needs ~17 GiB of host memory; nothing of the GPU context is needed any more
+            ctx = None
+            r = cpu_commit(args.log_rows, W, 1, 1)
+            line["cpu_baseline"] = {"value": r["gbs"], "unit": "GB/s", "cores": r["threads"], "kind": r["kind"],
+                                    "sample": f"{r['sample']} ({r['sec']:.2f} s)", "note": r["note"], "phases_ms": r["phases_ms"],
+                                    "poseidon2_perms_per_s": r["perms_per_s"],
+                                    "root_equals_gpu_root": (r["root"] == [int(x) for x in root_dev]) if r["full"] else None}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
 
 
 if __name__ == "__main__":

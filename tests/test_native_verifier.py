@@ -188,3 +188,27 @@ def test_rejects_hostile_shapes_and_noncanonical_words(hello):
     assert e is not None and "InvalidProofShape" in e
     e = bf.verify_shard(pk.commit, pk.names, [1 << 40 for _ in pk.traces], words, *FRI)
     assert e is not None
+
+
+@pytest.mark.parametrize("observe,rollin", [(0, 0), (1, 1), (0, 1)])
+def test_transcript_options_native_verifier_matches_oracle(oracle, monkeypatch, observe, rollin):
+    """bfgpu_verify_shard_ex with non-default transcript options accepts exactly the proofs the oracle produces (and its verifier
+    accepts) under the same switches, and rejects them under the default options: the switches are wired through both verifiers."""
+    from oracle import prover as PR, stark as S
+    monkeypatch.setattr(S, "OBSERVE_OPENED_VALUES", bool(observe))
+    monkeypatch.setattr(S, "FRI_ROLLIN", rollin)
+    prog = ex.Program("++[>+<-]>.")
+    traces, preps = tg.generate_traces(ex.execute(prog)), tg.preprocessed_traces(prog)
+    pk = PR.setup(chips, preps)
+    ch = S.Challenger()
+    PR.observe_pk(pk, ch)
+    cfg = S.FriConfig(*FRI)
+    proof = PR.prove_shard(chips, pk, traces, ch.clone(), cfg)
+    proof.pop("_debug", None)
+    vk = dict(commit=pk.commit, chip_information=[(n, t.shape[0].bit_length() - 1, lo) for n, t, lo in zip(pk.names, pk.traces, pk.local_only)])
+    assert PR.verify_shard(chips, vk, proof, ch.clone(), cfg) is None
+    words = serialize(proof, pk.names)
+    heights = [t.shape[0] for t in pk.traces]
+    opts = dict(observe_opened_values=observe, fri_rollin=rollin)
+    assert bf.verify_shard(pk.commit, pk.names, heights, words, *FRI, options=opts) is None
+    assert bf.verify_shard(pk.commit, pk.names, heights, words, *FRI) is not None
