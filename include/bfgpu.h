@@ -306,6 +306,26 @@ int32_t bfgpu_shard_num_traces(const bfgpu_shard* shard);
 int32_t bfgpu_shard_trace_info(const bfgpu_shard* shard, int32_t i, const char** name, uint64_t* rows, uint64_t* cols);
 int32_t bfgpu_shard_get_trace(const bfgpu_shard* shard, int32_t i, uint32_t* out);
 
+/* ---- ONE shard proof over several GPUs (one process / context per GPU) ---------------------------------------- */
+/* `MachineProver::prove` (crates/stark/src/prover.rs:560-582: commit + open, :209-553) by `world` ranks.  The three commitments go
+ * through the sharded commitment above; the LogUp traces are replicated; the quotient is evaluated on each rank's LDE rows (the
+ * "next" row read from the peer that holds it, the result stored straight into the rank that owns that quotient column); opened
+ * values, reduced openings and FRI folds are row-local with one small exchange per step; queries are answered by the owner of the
+ * leaf (csrc/dist_prove.cuh).  The proof is word for word the one bfgpu_machine_open produces on one GPU, returned on EVERY rank.
+ * The caller supplies the control plane: an all-gather of equal-sized byte strings between host buffers (recv = world * bytes, rank
+ * order) and a barrier — ~30 small all-gathers and ~8 barriers per proof (torch.distributed in the Python mirror, MPI / NCCL in a
+ * Rust shim).  Callbacks return 0 on success.  Every rank passes the same proving key, the same record (or the same full set of
+ * main traces) and a challenger in the same state (pk observed). */
+typedef struct {
+    void* user;
+    int32_t (*all_gather)(void* user, const void* send, void* recv, uint64_t bytes_per_rank);
+    int32_t (*barrier)(void* user);
+} bfgpu_comm;
+int32_t bfgpu_dist_prove_record(bfgpu_ctx* ctx, const bfgpu_comm* comm, uint32_t rank, uint32_t world, const bfgpu_pk* pk, const bfgpu_record* rec,
+                                bfgpu_challenger* ch, int64_t fixed_pow_witness, bfgpu_shard_proof** out);
+int32_t bfgpu_dist_prove(bfgpu_ctx* ctx, const bfgpu_comm* comm, uint32_t rank, uint32_t world, const bfgpu_pk* pk, const char* const* names,
+                         const bfgpu_mat* traces, int32_t n, bfgpu_challenger* ch, int64_t fixed_pow_witness, bfgpu_shard_proof** out);
+
 /* ---- native verifier ---------------------------------------------------------------- */
 /* `Verifier::verify_shard` (crates/stark/src/verifier.rs:27-216) on the serialisation of bfgpu_machine_open: replays the
  * transcript, verifies the PCS opening (input Merkle openings, reduced openings, FRI fold chain, proof of work), checks

@@ -105,6 +105,9 @@ ABI = {
     "bfgpu_dist_commit_open_batch": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "bfgpu_dist_commit_rows_per_rank": (C.c_uint64, [C.c_void_p]),
     "bfgpu_dist_commit_free": (None, [C.c_void_p]),
+    "bfgpu_dist_prove_record": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "bfgpu_dist_prove": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(Mat), C.c_int32, C.c_void_p,
+                                     C.c_int64, C.POINTER(C.c_void_p)]),
     "bfgpu_challenger_create": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bfgpu_challenger_clone": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bfgpu_challenger_free": (None, [C.c_void_p]),

@@ -1560,6 +1560,194 @@ struct ExtKey {
     bool operator<(const ExtKey& o) const { return log_h != o.log_h ? log_h < o.log_h : z < o.z; }
 };
 
+// Proof of work of the FRI argument (`challenger.grind(bits)`): the witness (canonical) that makes the next sample_bits zero; the
+// transcript `ch` observes it.  fixed >= 0 reuses a known witness (pinning against a reference run).
+static int32_t pow_grind(bfgpu_ctx* ctx, bfgpu_challenger& ch, int64_t fixed_pow_witness, uint32_t* witness_out) {
+    Phase ph(ctx, BFGPU_PHASE_POW);
+    if (fixed_pow_witness >= 0) {
+        *witness_out = (uint32_t)fixed_pow_witness;
+    } else {
+        uint32_t st[16];
+        memcpy(st, ch.state, sizeof st);
+        for (size_t i = 0; i < ch.input.size(); i++) st[i] = ch.input[i];
+        uint32_t pos = (uint32_t)ch.input.size();
+        uint32_t* d_st = nullptr;
+        unsigned int* d_best = nullptr;
+        TRY(dalloc(ctx, (void**)&d_st, 64));
+        TRY(dalloc(ctx, (void**)&d_best, 4));
+        TRY(upload_small(ctx, d_st, st, 64));
+        // batches in increasing order keep "the smallest witness"; the first one covers 4x the expected search length
+        // (2^bits candidates on average), the following ones are bigger
+        const uint32_t mask = (1u << ctx->pow_bits) - 1;
+        uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(4ull << ctx->pow_bits, 1u << 14), 1u << 22);
+        // BFGPU_OPT_POW_ORDER: 0 = the smallest witness (ascending batches), 1 = the largest one below p (descending batches).
+        // The reference's rayon `find_any` returns an arbitrary valid witness; both ends are deterministic.
+        const bool desc = ctx->opt[BFGPU_OPT_POW_ORDER] == 1;
+        const unsigned int none = desc ? 0u : 0xffffffffu;
+        unsigned int best = none;
+        for (uint64_t done = 0; done < kb::P && best == none; done += batch, batch = std::min<uint64_t>(batch * 4, 1u << 24)) {
+            TRY(upload_small(ctx, d_best, &best, 4));
+            uint32_t count = (uint32_t)std::min<uint64_t>(batch, kb::P - done);
+            uint32_t start = desc ? (uint32_t)(kb::P - done - count) : (uint32_t)done;
+            openk::k_pow_grind<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_st, pos, mask, start, count, d_best, desc ? 1 : 0);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(&best, d_best, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        if (desc && best != none) best -= 1;  // the kernel stores w + 1
+        else if (desc) best = 0xffffffffu;
+        dfree(ctx, d_st);
+        dfree(ctx, d_best);
+        if (best == 0xffffffffu) { return fail(ctx, BFGPU_ERR_STATE, "proof-of-work search failed"); }
+        *witness_out = best;
+    }
+    if (!ch.check_witness(ctx->pow_bits, kb::to_mont(*witness_out))) { return fail(ctx, BFGPU_ERR_STATE, "invalid proof-of-work witness %u", *witness_out); }
+    return BFGPU_OK;
+}
+
+// One committed FRI layer: the folded vector it commits to (pairs of extension elements = rows of 8 words) and its Merkle tree.
+struct FriLayer {
+    uint32_t* vec;  // folded input of this layer: len ext elements = len/2 rows of 8 words
+    uint64_t len;
+    bfgpu_tree* tree;
+};
+// FRI commit phase on ONE device from the folded vector `folded` (len extension elements, consumed) down to the final constant:
+// commit, observe the root, sample beta, fold, roll in the reduced openings of `reduced` (log height -> ext vector, tallest first,
+// entries consumed and set to null) whose length matches.  Appends to layers / commits; the caller releases them.
+// (The single-GPU Pcs::open runs all of it here; the sharded prover enters with the vector it gathered below its threshold.)
+static int32_t fri_commit_phase(bfgpu_ctx* ctx, bfgpu_challenger& ch, uint32_t* folded, uint64_t len,
+                                std::map<unsigned, uint32_t*, std::greater<unsigned>>& reduced, std::vector<FriLayer>& layers,
+                                std::vector<std::array<uint32_t, 8>>& commits, uint32_t final_poly[4]) {
+    const unsigned log_blowup = ctx->log_blowup;
+    using Layer = FriLayer;
+    (void)sizeof(Layer);
+    Phase ph(ctx, BFGPU_PHASE_FRI);
+    auto it = reduced.begin();
+    while (it != reduced.end() && (it->second == nullptr || (1ull << it->first) >= len)) ++it;
+    // The challenger rides along on the device for the whole commit phase (openk::k_challenger_round, k_fri_tail): rounds
+    // are enqueued back to back with no host round trip; all roots come back in ONE copy and the host challenger replays them.
+    Scratch fs(ctx);
+    uint32_t *d_ch = nullptr, *d_roots = nullptr, *d_betas = nullptr;
+    const uint32_t total_rounds = ilog2(len) - log_blowup;
+    TRY(fs.alloc((void**)&d_ch, 32 * 4));
+    TRY(fs.alloc((void**)&d_roots, (size_t)std::max(total_rounds, 1u) * 32));
+    TRY(fs.alloc((void**)&d_betas, (size_t)std::max(total_rounds, 1u) * 16));
+    {
+        uint32_t h[32] = {0};
+        memcpy(h, ch.state, 64);
+        for (size_t k = 0; k < ch.input.size(); k++) h[16 + k] = ch.input[k];
+        h[24] = (uint32_t)ch.input.size();
+        TRY(upload_small(ctx, d_ch, h, sizeof h));
+    }
+    uint32_t round = 0;
+    while (len > (1ull << log_blowup)) {
+        if (ctx->fri_tail && len <= (1ull << openk::TAIL_MAX_LOG) && ilog2(len) - log_blowup <= (unsigned)openk::TAIL_MAX_ROUNDS) {
+            // ---- all remaining rounds in one single-CTA launch (openk::k_fri_tail) ----
+            openk::FriTailArgs ta;
+            memset(&ta, 0, sizeof ta);
+            ta.log_len = ilog2(len);
+            ta.nrounds = ta.log_len - log_blowup;
+            ta.tw = ctx->d_tw;
+            ta.rollin = (int)ctx->opt[BFGPU_OPT_FRI_ROLLIN];
+            ta.ch = d_ch;
+            ta.roots = d_roots + 8 * (size_t)round;
+            ta.vec[0] = folded;
+            int32_t rc = BFGPU_OK;
+            for (uint32_t r = 0; r < ta.nrounds && rc == BFGPU_OK; r++) {
+                const uint64_t nleaves = len >> (r + 1);
+                bfgpu_tree* t = new bfgpu_tree();
+                t->ctx = ctx;
+                DMat leaves;
+                leaves.d = ta.vec[r];
+                leaves.rows = nleaves;
+                leaves.cols = 8;
+                leaves.rs = 8;
+                t->mats.push_back(leaves);
+                t->log_max = ilog2(nleaves);
+                layers.push_back({ta.vec[r], len >> r, t});
+                for (unsigned l = 0; l <= t->log_max && rc == BFGPU_OK; l++) {
+                    uint32_t* lay = nullptr;
+                    rc = dalloc(ctx, (void**)&lay, (nleaves >> l) * 32);
+                    t->layers.push_back(lay);
+                    t->layer_len.push_back(nleaves >> l);
+                    ta.layer[r][l] = lay;
+                }
+                if (rc == BFGPU_OK) rc = dalloc(ctx, (void**)&ta.vec[r + 1], nleaves * 16);
+                if (it != reduced.end() && (1ull << it->first) == nleaves) {
+                    ta.add[r] = it->second;
+                    ++it;
+                }
+            }
+            if (rc != BFGPU_OK) { return rc; }
+            openk::k_fri_tail<<<1, openk::TAIL_THREADS, 0, ctx->stream>>>(ta);
+            LAUNCHED(ctx);
+            CU(cudaGetLastError());
+            for (uint32_t r = 0; r < ta.nrounds; r++)  // the reduced openings consumed by the tail (stream order keeps them alive)
+                if (ta.add[r])
+                    for (auto& kv : reduced)
+                        if (kv.second == ta.add[r]) {
+                            dfree(ctx, kv.second);
+                            kv.second = nullptr;
+                        }
+            round += ta.nrounds;
+            folded = ta.vec[ta.nrounds];
+            len = 1ull << log_blowup;
+            break;
+        }
+        DMat leaves;
+        leaves.d = folded;
+        leaves.rows = len / 2;
+        leaves.cols = 8;
+        leaves.rs = 8;
+        bfgpu_tree* t = nullptr;
+        int32_t rc = build_tree(ctx, {leaves}, false, &t);
+        layers.push_back({folded, len, t});
+        if (rc != BFGPU_OK) { return rc; }
+        openk::k_challenger_round<<<1, 32, 0, ctx->stream>>>(d_ch, t->layers.back(), d_betas + 4 * (size_t)round, d_roots + 8 * (size_t)round);
+        LAUNCHED(ctx);
+        uint64_t nlen = len / 2;
+        unsigned log_nlen = ilog2(nlen);
+        uint32_t* next = nullptr;
+        TRY(dalloc(ctx, (void**)&next, nlen * 16));
+        const uint32_t* add = nullptr;
+        if (it != reduced.end() && (1ull << it->first) == nlen) add = it->second;
+        openk::k_fri_fold_dev<<<(unsigned)((nlen + 127) / 128), 128, 0, ctx->stream>>>(folded, next, add, log_nlen, d_betas + 4 * (size_t)round, ctx->d_tw,
+                                                                                     (int)ctx->opt[BFGPU_OPT_FRI_ROLLIN], 0, (uint32_t)nlen);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        if (add) {
+            dfree(ctx, it->second);
+            it->second = nullptr;
+            ++it;
+        }
+        folded = next;
+        len = nlen;
+        round++;
+    }
+    std::vector<uint32_t> fin(len * 4);
+    {   // one copy for every root of the phase (and the final vector); the host transcript catches up
+        std::vector<uint32_t> roots((size_t)round * 8);
+        if (round) CU(cudaMemcpyAsync(roots.data(), d_roots, roots.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(fin.data(), folded, len * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t r = 0; r < round; r++) {
+            std::array<uint32_t, 8> root;
+            memcpy(root.data(), &roots[8 * r], 32);
+            ch.observe_slice(root.data(), 8);
+            commits.push_back(root);
+            (void)ch.sample_ext();
+        }
+    }
+    if (it != reduced.end()) { return fail(ctx, BFGPU_ERR_STATE, "FRI inputs left over after the commit phase"); }
+    dfree(ctx, folded);
+    for (uint64_t i = 1; i < len; i++)
+        if (memcmp(&fin[0], &fin[4 * i], 16)) { return fail(ctx, BFGPU_ERR_STATE, "FRI final layer is not constant: a committed matrix is not low-degree"); }
+    memcpy(final_poly, fin.data(), 16);
+    ch.observe_slice(final_poly, 4);
+    return BFGPU_OK;
+}
+
 static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int32_t n_rounds, bfgpu_challenger* chh,
                                   int64_t fixed_pow_witness, bfgpu_opening** out);
 extern "C" int32_t bfgpu_pcs_open(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int32_t n_rounds, bfgpu_challenger* chh,
@@ -1612,7 +1800,7 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
                 uint32_t* d = nullptr;
                 TRY(dalloc(ctx, (void**)&d, (size_t)16 << log_h));
                 uint32_t h = 1u << log_h;
-                openk::k_bary_weights<<<(h + 255) / 256, 256, 0, ctx->stream>>>(d, log_h, gen, z, ctx->d_tw);
+                openk::k_bary_weights<<<(h + 255) / 256, 256, 0, ctx->stream>>>(d, log_h, gen, z, ctx->d_tw, 0, h);
                 LAUNCHED(ctx);
                 CU(cudaGetLastError());
                 it = wcache.emplace(key, d).first;
@@ -1738,6 +1926,7 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
                 openk::RoMat rm;
                 memset(&rm, 0, sizeof rm);
                 rm.d = mp.m->d;
+                rm.stride = mp.m->rows;
                 rm.width = mp.m->cols;
                 if (mp.pts.size() > 2) return fail(ctx, BFGPU_ERR_INVALID, "more than two opening points per matrix are not supported");
                 rm.npoints = (uint32_t)mp.pts.size();
@@ -1768,7 +1957,7 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
             TRY(upload_small(ctx, d_m, g.mats.data(), g.mats.size() * sizeof(openk::RoMat)));
             TRY(upload_small(ctx, d_z, g.pts.data(), g.pts.size() * 16));
             openk::k_reduce_openings<<<((1u << lh) + 127) / 128, 128, 0, ctx->stream>>>(d_m, (uint32_t)g.mats.size(), d_z, (uint32_t)g.pts.size(), d_apow, lh,
-                                                                                         gen, ctx->d_tw, ro);
+                                                                                         gen, ctx->d_tw, ro, 0, 1u << lh);
             LAUNCHED(ctx);
             CU(cudaGetLastError());
             dfree(ctx, d_m);
@@ -1779,11 +1968,7 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
     }
 
     // ---- (iii) FRI commit phase ------------------------------------------------------------------------------
-    struct Layer {
-        uint32_t* vec;  // folded input of this layer: len ext elements = len/2 rows of 8 words
-        uint64_t len;
-        bfgpu_tree* tree;
-    };
+    using Layer = FriLayer;
     std::vector<Layer> layers;
     auto release_layers = [&]() {
         for (auto& L : layers) {
@@ -1795,133 +1980,11 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
     uint32_t final_poly[4];
     const unsigned log_max_height = reduced.begin()->first;
     {
-        Phase ph(ctx, BFGPU_PHASE_FRI);
-        auto it = reduced.begin();
-        uint32_t* folded = it->second;
-        uint64_t len = 1ull << it->first;
-        it->second = nullptr;
-        ++it;
+        uint32_t* folded = reduced.begin()->second;
+        reduced.begin()->second = nullptr;
         std::vector<std::array<uint32_t, 8>> commits;
-        // The challenger rides along on the device for the whole commit phase (openk::k_challenger_round, k_fri_tail): rounds
-        // are enqueued back to back with no host round trip; all roots come back in ONE copy and the host challenger replays them.
-        Scratch fs(ctx);
-        uint32_t *d_ch = nullptr, *d_roots = nullptr, *d_betas = nullptr;
-        const uint32_t total_rounds = ilog2(len) - log_blowup;
-        TRY(fs.alloc((void**)&d_ch, 32 * 4));
-        TRY(fs.alloc((void**)&d_roots, (size_t)std::max(total_rounds, 1u) * 32));
-        TRY(fs.alloc((void**)&d_betas, (size_t)std::max(total_rounds, 1u) * 16));
-        {
-            uint32_t h[32] = {0};
-            memcpy(h, ch.state, 64);
-            for (size_t k = 0; k < ch.input.size(); k++) h[16 + k] = ch.input[k];
-            h[24] = (uint32_t)ch.input.size();
-            TRY(upload_small(ctx, d_ch, h, sizeof h));
-        }
-        uint32_t round = 0;
-        while (len > (1ull << log_blowup)) {
-            if (ctx->fri_tail && len <= (1ull << openk::TAIL_MAX_LOG) && ilog2(len) - log_blowup <= (unsigned)openk::TAIL_MAX_ROUNDS) {
-                // ---- all remaining rounds in one single-CTA launch (openk::k_fri_tail) ----
-                openk::FriTailArgs ta;
-                memset(&ta, 0, sizeof ta);
-                ta.log_len = ilog2(len);
-                ta.nrounds = ta.log_len - log_blowup;
-                ta.tw = ctx->d_tw;
-                ta.rollin = (int)ctx->opt[BFGPU_OPT_FRI_ROLLIN];
-                ta.ch = d_ch;
-                ta.roots = d_roots + 8 * (size_t)round;
-                ta.vec[0] = folded;
-                int32_t rc = BFGPU_OK;
-                for (uint32_t r = 0; r < ta.nrounds && rc == BFGPU_OK; r++) {
-                    const uint64_t nleaves = len >> (r + 1);
-                    bfgpu_tree* t = new bfgpu_tree();
-                    t->ctx = ctx;
-                    DMat leaves;
-                    leaves.d = ta.vec[r];
-                    leaves.rows = nleaves;
-                    leaves.cols = 8;
-                    leaves.rs = 8;
-                    t->mats.push_back(leaves);
-                    t->log_max = ilog2(nleaves);
-                    layers.push_back({ta.vec[r], len >> r, t});
-                    for (unsigned l = 0; l <= t->log_max && rc == BFGPU_OK; l++) {
-                        uint32_t* lay = nullptr;
-                        rc = dalloc(ctx, (void**)&lay, (nleaves >> l) * 32);
-                        t->layers.push_back(lay);
-                        t->layer_len.push_back(nleaves >> l);
-                        ta.layer[r][l] = lay;
-                    }
-                    if (rc == BFGPU_OK) rc = dalloc(ctx, (void**)&ta.vec[r + 1], nleaves * 16);
-                    if (it != reduced.end() && (1ull << it->first) == nleaves) {
-                        ta.add[r] = it->second;
-                        ++it;
-                    }
-                }
-                if (rc != BFGPU_OK) { release_layers(); return rc; }
-                openk::k_fri_tail<<<1, openk::TAIL_THREADS, 0, ctx->stream>>>(ta);
-                LAUNCHED(ctx);
-                CU(cudaGetLastError());
-                for (uint32_t r = 0; r < ta.nrounds; r++)  // the reduced openings consumed by the tail (stream order keeps them alive)
-                    if (ta.add[r])
-                        for (auto& kv : reduced)
-                            if (kv.second == ta.add[r]) {
-                                dfree(ctx, kv.second);
-                                kv.second = nullptr;
-                            }
-                round += ta.nrounds;
-                folded = ta.vec[ta.nrounds];
-                len = 1ull << log_blowup;
-                break;
-            }
-            DMat leaves;
-            leaves.d = folded;
-            leaves.rows = len / 2;
-            leaves.cols = 8;
-            leaves.rs = 8;
-            bfgpu_tree* t = nullptr;
-            int32_t rc = build_tree(ctx, {leaves}, false, &t);
-            layers.push_back({folded, len, t});
-            if (rc != BFGPU_OK) { release_layers(); return rc; }
-            openk::k_challenger_round<<<1, 32, 0, ctx->stream>>>(d_ch, t->layers.back(), d_betas + 4 * (size_t)round, d_roots + 8 * (size_t)round);
-            LAUNCHED(ctx);
-            uint64_t nlen = len / 2;
-            unsigned log_nlen = ilog2(nlen);
-            uint32_t* next = nullptr;
-            TRY(dalloc(ctx, (void**)&next, nlen * 16));
-            const uint32_t* add = nullptr;
-            if (it != reduced.end() && (1ull << it->first) == nlen) add = it->second;
-            openk::k_fri_fold_dev<<<(unsigned)((nlen + 127) / 128), 128, 0, ctx->stream>>>(folded, next, add, log_nlen, d_betas + 4 * (size_t)round, ctx->d_tw,
-                                                                                         (int)ctx->opt[BFGPU_OPT_FRI_ROLLIN]);
-            LAUNCHED(ctx);
-            CU(cudaGetLastError());
-            if (add) {
-                dfree(ctx, it->second);
-                it->second = nullptr;
-                ++it;
-            }
-            folded = next;
-            len = nlen;
-            round++;
-        }
-        std::vector<uint32_t> fin(len * 4);
-        {   // one copy for every root of the phase (and the final vector); the host transcript catches up
-            std::vector<uint32_t> roots((size_t)round * 8);
-            if (round) CU(cudaMemcpyAsync(roots.data(), d_roots, roots.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaMemcpyAsync(fin.data(), folded, len * 16, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            for (uint32_t r = 0; r < round; r++) {
-                std::array<uint32_t, 8> root;
-                memcpy(root.data(), &roots[8 * r], 32);
-                ch.observe_slice(root.data(), 8);
-                commits.push_back(root);
-                (void)ch.sample_ext();
-            }
-        }
-        if (it != reduced.end()) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "FRI inputs left over after the commit phase"); }
-        dfree(ctx, folded);
-        for (uint64_t i = 1; i < len; i++)
-            if (memcmp(&fin[0], &fin[4 * i], 16)) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "FRI final layer is not constant: a committed matrix is not low-degree"); }
-        memcpy(final_poly, fin.data(), 16);
-        ch.observe_slice(final_poly, 4);
+        int32_t rc = fri_commit_phase(ctx, ch, folded, 1ull << log_max_height, reduced, layers, commits, final_poly);
+        if (rc != BFGPU_OK) { release_layers(); return rc; }
         flat.push_back((uint32_t)commits.size());
         for (auto& c : commits)
             for (int k = 0; k < 8; k++) flat.push_back(out_word(ctx, c[k]));
@@ -1931,46 +1994,8 @@ static int32_t pcs_open_impl(bfgpu_ctx* ctx, const bfgpu_open_round* rounds, int
     // ---- (iv) proof of work ----------------------------------------------------------------------------------
     uint32_t witness = 0;
     {
-        Phase ph(ctx, BFGPU_PHASE_POW);
-        if (fixed_pow_witness >= 0) {
-            witness = (uint32_t)fixed_pow_witness;
-        } else {
-            uint32_t st[16];
-            memcpy(st, ch.state, sizeof st);
-            for (size_t i = 0; i < ch.input.size(); i++) st[i] = ch.input[i];
-            uint32_t pos = (uint32_t)ch.input.size();
-            uint32_t* d_st = nullptr;
-            unsigned int* d_best = nullptr;
-            TRY(dalloc(ctx, (void**)&d_st, 64));
-            TRY(dalloc(ctx, (void**)&d_best, 4));
-            TRY(upload_small(ctx, d_st, st, 64));
-            // batches in increasing order keep "the smallest witness"; the first one covers 4x the expected search length
-            // (2^bits candidates on average), the following ones are bigger
-            const uint32_t mask = (1u << ctx->pow_bits) - 1;
-            uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(4ull << ctx->pow_bits, 1u << 14), 1u << 22);
-            // BFGPU_OPT_POW_ORDER: 0 = the smallest witness (ascending batches), 1 = the largest one below p (descending batches).
-            // The reference's rayon `find_any` returns an arbitrary valid witness; both ends are deterministic.
-            const bool desc = ctx->opt[BFGPU_OPT_POW_ORDER] == 1;
-            const unsigned int none = desc ? 0u : 0xffffffffu;
-            unsigned int best = none;
-            for (uint64_t done = 0; done < kb::P && best == none; done += batch, batch = std::min<uint64_t>(batch * 4, 1u << 24)) {
-                TRY(upload_small(ctx, d_best, &best, 4));
-                uint32_t count = (uint32_t)std::min<uint64_t>(batch, kb::P - done);
-                uint32_t start = desc ? (uint32_t)(kb::P - done - count) : (uint32_t)done;
-                openk::k_pow_grind<<<(count + 127) / 128, 128, 0, ctx->stream>>>(d_st, pos, mask, start, count, d_best, desc ? 1 : 0);
-                LAUNCHED(ctx);
-                CU(cudaGetLastError());
-                CU(cudaMemcpyAsync(&best, d_best, 4, cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaStreamSynchronize(ctx->stream));
-            }
-            if (desc && best != none) best -= 1;  // the kernel stores w + 1
-            else if (desc) best = 0xffffffffu;
-            dfree(ctx, d_st);
-            dfree(ctx, d_best);
-            if (best == 0xffffffffu) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "proof-of-work search failed"); }
-            witness = best;
-        }
-        if (!ch.check_witness(ctx->pow_bits, kb::to_mont(witness))) { release_layers(); return fail(ctx, BFGPU_ERR_STATE, "invalid proof-of-work witness %u", witness); }
+        int32_t rc = pow_grind(ctx, ch, fixed_pow_witness, &witness);
+        if (rc != BFGPU_OK) { release_layers(); return rc; }
         flat.push_back(witness);
     }
 
@@ -2219,6 +2244,46 @@ static int32_t commit_bitrev_device(bfgpu_ctx* ctx, std::vector<DMat>& coefs, co
     return BFGPU_OK;
 }
 
+// LogUp permutation traces of every chip (prover.rs:280-296 -> permutation.rs:75-148): perm[i] = n x 4*perm_w base columns in the
+// prover's layout; the cumulative sums (last running totals) are parked at d_csums[4 i ..] for ONE later copy.
+static int32_t perm_traces(bfgpu_ctx* ctx, const bfgpu_pk* pk, const std::vector<int>& pk_idx, const std::vector<int>& chips, const std::vector<DMat>& traces,
+                           const air::Challenges& chal, std::vector<DMat>* perm_out, uint32_t* d_csums) {
+    std::vector<DMat>& perm = *perm_out;
+    const size_t nchips = chips.size();
+    Phase ph(ctx, BFGPU_PHASE_PERM);
+    for (size_t i = 0; i < nchips; i++) {
+        const air::ChipInfo& ci = air::CHIPS[chips[i]];
+        const DMat& main = traces[i];
+        uint64_t n = main.rows;
+        unsigned log_n = ilog2(n);
+        perm[i].rows = n;
+        perm[i].cols = 4 * ci.perm_w;
+        TRY(dalloc(ctx, (void**)&perm[i].d, n * perm[i].cols * 4));
+        uint32_t* rowsum = nullptr;
+        TRY(dalloc(ctx, (void**)&rowsum, n * 16));
+        const uint32_t* prep = pk_idx[i] >= 0 ? pk->traces[pk_idx[i]].d : nullptr;
+#define BF_PERM_CASE(C) \
+    case C: air::k_perm_rows<C><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(C, main.d, prep, log_n, chal, ci.perm_w, perm[i].d, rowsum); break;
+        switch (chips[i]) {
+            BF_PERM_CASE(0) BF_PERM_CASE(1) BF_PERM_CASE(2) BF_PERM_CASE(3) BF_PERM_CASE(4) BF_PERM_CASE(5) BF_PERM_CASE(6) BF_PERM_CASE(7)
+        }
+#undef BF_PERM_CASE
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        TRY(scan_ext(ctx, rowsum, n));
+        air::k_scan_fixup<<<(unsigned)((n + air::SCAN_THREADS - 1) / air::SCAN_THREADS), air::SCAN_THREADS, 0, ctx->stream>>>(
+            (const uint4*)rowsum, n, nullptr, log_n, perm[i].d + (uint64_t)4 * (ci.perm_w - 1) * n);
+        LAUNCHED(ctx);
+        CU(cudaGetLastError());
+        // cumulative sum = last running total: parked on the device, fetched with ONE copy after the permutation commit
+        // (a device->host copy into pageable memory blocks the host: eight of them plus a synchronisation cost more than
+        // the kernels of a small proof)
+        CU(cudaMemcpyAsync(d_csums + 4 * i, rowsum + 4 * (n - 1), 16, cudaMemcpyDeviceToDevice, ctx->stream));
+        dfree(ctx, rowsum);  // stream-ordered reuse: the copy above is enqueued before any later writer
+    }
+    return BFGPU_OK;
+}
+
 // CpuProver::open (prover.rs:242-553)
 static int32_t machine_open_impl(bfgpu_ctx* ctx, const bfgpu_pk* pk, const bfgpu_shard* sd, bfgpu_challenger* chh, int64_t fixed_pow_witness,
                                       bfgpu_shard_proof** out);
@@ -2261,39 +2326,7 @@ static int32_t machine_open_impl(bfgpu_ctx* ctx, const bfgpu_pk* pk, const bfgpu
     Scratch csum_scratch(ctx);
     uint32_t* d_csums = nullptr;
     TRY(csum_scratch.alloc((void**)&d_csums, nchips * 16));
-    {
-        Phase ph(ctx, BFGPU_PHASE_PERM);
-        for (size_t i = 0; i < nchips; i++) {
-            const air::ChipInfo& ci = air::CHIPS[sd->chip[i]];
-            const DMat& main = sd->traces[i];
-            uint64_t n = main.rows;
-            unsigned log_n = ilog2(n);
-            perm[i].rows = n;
-            perm[i].cols = 4 * ci.perm_w;
-            TRY(dalloc(ctx, (void**)&perm[i].d, n * perm[i].cols * 4));
-            uint32_t* rowsum = nullptr;
-            TRY(dalloc(ctx, (void**)&rowsum, n * 16));
-            const uint32_t* prep = pk_idx[i] >= 0 ? pk->traces[pk_idx[i]].d : nullptr;
-#define BF_PERM_CASE(C) \
-    case C: air::k_perm_rows<C><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(C, main.d, prep, log_n, chal, ci.perm_w, perm[i].d, rowsum); break;
-            switch (sd->chip[i]) {
-                BF_PERM_CASE(0) BF_PERM_CASE(1) BF_PERM_CASE(2) BF_PERM_CASE(3) BF_PERM_CASE(4) BF_PERM_CASE(5) BF_PERM_CASE(6) BF_PERM_CASE(7)
-            }
-#undef BF_PERM_CASE
-            LAUNCHED(ctx);
-            CU(cudaGetLastError());
-            TRY(scan_ext(ctx, rowsum, n));
-            air::k_scan_fixup<<<(unsigned)((n + air::SCAN_THREADS - 1) / air::SCAN_THREADS), air::SCAN_THREADS, 0, ctx->stream>>>(
-                (const uint4*)rowsum, n, nullptr, log_n, perm[i].d + (uint64_t)4 * (ci.perm_w - 1) * n);
-            LAUNCHED(ctx);
-            CU(cudaGetLastError());
-            // cumulative sum = last running total: parked on the device, fetched with ONE copy after the permutation commit
-            // (a device->host copy into pageable memory blocks the host: eight of them plus a synchronisation cost more than
-            // the kernels of a small proof)
-            CU(cudaMemcpyAsync(d_csums + 4 * i, rowsum + 4 * (n - 1), 16, cudaMemcpyDeviceToDevice, ctx->stream));
-            dfree(ctx, rowsum);  // stream-ordered reuse: the copy above is enqueued before any later writer
-        }
-    }
+    TRY(perm_traces(ctx, pk, pk_idx, sd->chip, sd->traces, chal, &perm, d_csums));
     bfgpu_pcs_data* perm_data = nullptr;
     uint32_t perm_root[8];
     {
@@ -2454,6 +2487,11 @@ extern "C" int32_t bfgpu_machine_chip_info(int32_t i, const char** name, int32_t
 // native executor + device-side trace generation
 // =====================================================================================================
 #include "tracegen.cuh"
+
+// =====================================================================================================
+// one shard proof over several GPUs
+// =====================================================================================================
+#include "dist_prove.cuh"
 
 // =====================================================================================================
 // native verifier (host only)

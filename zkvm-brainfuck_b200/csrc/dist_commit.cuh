@@ -70,10 +70,26 @@ struct bfgpu_dist_commit {
     std::vector<std::vector<uint32_t>> top;  // top[0] = caps (world digests) ... top.back() = root; Montgomery
 };
 
-static inline void dist_col_range(uint32_t total, uint32_t world, uint32_t r, uint32_t* c0, uint32_t* n) {
-    uint32_t a = (uint32_t)((uint64_t)total * r / world), b = (uint32_t)((uint64_t)total * (r + 1) / world);
+// Columns of matrix `mat_index` that rank r extends: the even split [W*q/G, W*(q+1)/G) taken at position q = (r + mat_index) mod G, so
+// that commitments of many NARROW matrices (the sixteen 4-column quotient chunks over 8 ranks) spread over all ranks instead of
+// landing on the same few.
+static inline void dist_col_range(uint32_t total, uint32_t world, uint32_t r, uint32_t mat_index, uint32_t* c0, uint32_t* n) {
+    const uint32_t q = (r + mat_index) % world;
+    uint32_t a = (uint32_t)((uint64_t)total * q / world), b = (uint32_t)((uint64_t)total * (q + 1) / world);
     *c0 = a;
     *n = b - a;
+}
+// rank owning column c of matrix mat_index, and that rank's first column
+static inline uint32_t dist_col_owner(uint32_t total, uint32_t world, uint32_t mat_index, uint32_t c, uint32_t* owner_col0) {
+    for (uint32_t r = 0; r < world; r++) {
+        uint32_t c0, n;
+        dist_col_range(total, world, r, mat_index, &c0, &n);
+        if (c >= c0 && c < c0 + n) {
+            if (owner_col0) *owner_col0 = c0;
+            return r;
+        }
+    }
+    return 0;
 }
 
 extern "C" int32_t bfgpu_dist_commit_begin(bfgpu_ctx* ctx, uint32_t rank, uint32_t world, const uint64_t* rows, const uint32_t* total_cols, int32_t n,
@@ -96,7 +112,7 @@ extern "C" int32_t bfgpu_dist_commit_begin(bfgpu_ctx* ctx, uint32_t rank, uint32
         if (m.lde_rows < world) return fail(ctx, BFGPU_ERR_INVALID, "matrix %d: LDE height %llu is below the world size %u", i, (unsigned long long)m.lde_rows, world);
         m.rpg = m.lde_rows / world;
         m.total_cols = total_cols[i];
-        dist_col_range(m.total_cols, world, rank, &m.col0, &m.ncols);
+        dist_col_range(m.total_cols, world, rank, (uint32_t)i, &m.col0, &m.ncols);
         m.recv_off = dc->recv_words;
         dc->recv_words += m.rpg * m.total_cols;
         m.send_off = dc->block_words;
@@ -118,9 +134,10 @@ extern "C" uint32_t bfgpu_dist_commit_local_cols(const bfgpu_dist_commit* dc, in
 extern "C" uint64_t bfgpu_dist_commit_block_words(const bfgpu_dist_commit* dc, uint32_t src) {
     if (!dc || src >= dc->world) return 0;
     uint64_t w = 0;
-    for (auto& m : dc->mats) {
+    for (size_t i = 0; i < dc->mats.size(); i++) {
+        const auto& m = dc->mats[i];
         uint32_t c0, nc;
-        dist_col_range(m.total_cols, dc->world, src, &c0, &nc);
+        dist_col_range(m.total_cols, dc->world, src, (uint32_t)i, &c0, &nc);
         w += m.rpg * nc;
     }
     return w;
@@ -203,22 +220,14 @@ static int32_t dist_scatter(bfgpu_dist_commit* dc, const bfgpu_dist_commit::Mat&
     return BFGPU_OK;
 }
 
-// Coset LDE of this rank's columns of every matrix (local[i]: rows[i] x local_cols(i), row-major, in the context's
-// input space; data may be null where the rank owns no column) and the exchange.  Asynchronous: returns once
-// everything is enqueued.  Before bfgpu_dist_commit_finish every rank must have synchronised its context and the
-// ranks must have passed a barrier (P2P mode) or completed the all-to-all + _unpack (staged mode).
 constexpr uint32_t DIST_CHUNK_COLS = 64;
-static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts);
-extern "C" int32_t bfgpu_dist_commit_lde(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts) {
-    AllocScope scope(dc ? dc->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
-    return scope.ok(dist_commit_lde_impl(dc, local, domain_shifts));
-}
-static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts) {
-    if (!dc || !local) return BFGPU_ERR_INVALID;
+// LDE + exchange of this rank's columns of every matrix, from coefficient-side inputs already on the device in the prover's layout
+// (column-major, Montgomery, bit-reversed rows; coefs[i] = the rank's ncols(i) columns, TRANSFORMED IN PLACE: pass a copy to keep them).
+// shift_mont[i]: LDE coset shift of matrix i.  Asynchronous, same completion protocol as bfgpu_dist_commit_lde.
+static int32_t dist_lde_coefs(bfgpu_dist_commit* dc, const std::vector<DMat>& coefs, const std::vector<uint32_t>& shift_mont) {
     bfgpu_ctx* ctx = dc->ctx;
     if (dc->lde_done) return fail(ctx, BFGPU_ERR_STATE, "LDE already done");
     if (!dc->staging && dc->peer_recv.empty()) return fail(ctx, BFGPU_ERR_STATE, "neither peers nor a staging buffer set");
-    const uint32_t gen = kb::to_mont(kb::GEN);
     struct Pending { uint32_t* buf; cudaEvent_t done; };
     std::vector<Pending> pending;
     auto retire = [&](size_t keep) -> int32_t {  // compute stream waits for old scatters, then their blocks return to the cache
@@ -234,23 +243,11 @@ static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* loca
     for (size_t i = 0; i < dc->mats.size() && rc == BFGPU_OK; i++) {
         const auto& m = dc->mats[i];
         if (m.ncols == 0) continue;
-        if (local[i].rows != m.rows || local[i].cols != m.ncols) {
-            rc = fail(ctx, BFGPU_ERR_INVALID, "matrix %zu: expected this rank's %llu x %u column slice, got %llu x %llu", i, (unsigned long long)m.rows, m.ncols,
-                      (unsigned long long)local[i].rows, (unsigned long long)local[i].cols);
+        const DMat& coef = coefs[i];
+        if (coef.rows != m.rows || coef.cols != m.ncols || !coef.d) {
+            rc = fail(ctx, BFGPU_ERR_INVALID, "matrix %zu: expected this rank's %llu x %u column slice", i, (unsigned long long)m.rows, m.ncols);
             break;
         }
-        if ((rc = check_mat(ctx, &local[i], true)) != BFGPU_OK) break;
-        uint32_t shift = gen;
-        if (domain_shifts) {
-            uint32_t ds = ctx->repr == BFGPU_REPR_CANONICAL ? kb::to_mont(domain_shifts[i] % kb::P) : domain_shifts[i];
-            if (ds == 0) {
-                rc = fail(ctx, BFGPU_ERR_INVALID, "zero domain shift");
-                break;
-            }
-            shift = kb::mul(gen, kb::inv(ds));
-        }
-        DMat coef;
-        if ((rc = ingest(ctx, local[i], /*bitrev=*/true, &coef)) != BFGPU_OK) break;
         // at least ~4 blocks per matrix so that only the last quarter of the exchange is exposed (16..64 columns each)
         const uint32_t chunk = std::min(DIST_CHUNK_COLS, std::max(16u, ((m.ncols + 3) / 4 + 7) / 8 * 8));
         for (uint32_t c = 0; c < m.ncols && rc == BFGPU_OK; c += chunk) {
@@ -259,7 +256,7 @@ static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* loca
             DMat slice = coef, lde;
             slice.d = coef.d + (uint64_t)c * coef.rows;
             slice.cols = nc;
-            if ((rc = lde_from_bitrev(ctx, slice, ctx->log_blowup, shift, &lde, /*consume=*/false)) != BFGPU_OK) break;
+            if ((rc = lde_from_bitrev(ctx, slice, ctx->log_blowup, shift_mont[i], &lde, /*consume=*/false)) != BFGPU_OK) break;
             Phase ph(ctx, BFGPU_PHASE_EXCHANGE);
             cudaEvent_t ready, done;
             cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
@@ -271,14 +268,55 @@ static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* loca
             cudaEventRecord(done, ctx->copy_stream);
             pending.push_back({lde.d, done});
         }
-        // the coefficient matrix was transformed in place slice by slice; all work on it is in compute-stream order
-        dfree(ctx, coef.d);
     }
     int32_t rc2 = retire(0);
     if (rc != BFGPU_OK) return rc;
     TRY(rc2);
     dc->lde_done = true;
     return BFGPU_OK;
+}
+
+// Coset LDE of this rank's columns of every matrix (local[i]: rows[i] x local_cols(i), row-major, in the context's
+// input space; data may be null where the rank owns no column) and the exchange.  Asynchronous: returns once
+// everything is enqueued.  Before bfgpu_dist_commit_finish every rank must have synchronised its context and the
+// ranks must have passed a barrier (P2P mode) or completed the all-to-all + _unpack (staged mode).
+static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts);
+extern "C" int32_t bfgpu_dist_commit_lde(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts) {
+    AllocScope scope(dc ? dc->ctx : nullptr);  // blocks taken by a failing call go back to the cache (see AllocScope)
+    return scope.ok(dist_commit_lde_impl(dc, local, domain_shifts));
+}
+static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* local, const uint32_t* domain_shifts) {
+    if (!dc || !local) return BFGPU_ERR_INVALID;
+    bfgpu_ctx* ctx = dc->ctx;
+    if (dc->lde_done) return fail(ctx, BFGPU_ERR_STATE, "LDE already done");
+    if (!dc->staging && dc->peer_recv.empty()) return fail(ctx, BFGPU_ERR_STATE, "neither peers nor a staging buffer set");
+    const uint32_t gen = kb::to_mont(kb::GEN);
+    std::vector<DMat> coefs(dc->mats.size());
+    std::vector<uint32_t> shifts(dc->mats.size(), gen);
+    int32_t rc = BFGPU_OK;
+    for (size_t i = 0; i < dc->mats.size() && rc == BFGPU_OK; i++) {
+        const auto& m = dc->mats[i];
+        if (m.ncols == 0) continue;
+        if (local[i].rows != m.rows || local[i].cols != m.ncols) {
+            rc = fail(ctx, BFGPU_ERR_INVALID, "matrix %zu: expected this rank's %llu x %u column slice, got %llu x %llu", i, (unsigned long long)m.rows, m.ncols,
+                      (unsigned long long)local[i].rows, (unsigned long long)local[i].cols);
+            break;
+        }
+        if ((rc = check_mat(ctx, &local[i], true)) != BFGPU_OK) break;
+        if (domain_shifts) {
+            uint32_t ds = ctx->repr == BFGPU_REPR_CANONICAL ? kb::to_mont(domain_shifts[i] % kb::P) : domain_shifts[i];
+            if (ds == 0) {
+                rc = fail(ctx, BFGPU_ERR_INVALID, "zero domain shift");
+                break;
+            }
+            shifts[i] = kb::mul(gen, kb::inv(ds));
+        }
+        rc = ingest(ctx, local[i], /*bitrev=*/true, &coefs[i]);
+    }
+    if (rc == BFGPU_OK) rc = dist_lde_coefs(dc, coefs, shifts);
+    // the coefficient matrices were transformed in place slice by slice; all work on them is in compute-stream order
+    for (DMat& c : coefs) dfree(ctx, c.d);
+    return rc;
 }
 
 // staged mode: dev_recv = [source rank][matrix][source's columns][own rows]  ->  the receive matrices
@@ -293,9 +331,10 @@ static int32_t dist_commit_unpack_impl(bfgpu_dist_commit* dc, const uint32_t* de
     Phase ph(ctx, BFGPU_PHASE_EXCHANGE);
     uint64_t off = 0;
     for (uint32_t s = 0; s < dc->world; s++)
-        for (auto& m : dc->mats) {
+        for (size_t i = 0; i < dc->mats.size(); i++) {
+            const auto& m = dc->mats[i];
             uint32_t c0, nc;
-            dist_col_range(m.total_cols, dc->world, s, &c0, &nc);
+            dist_col_range(m.total_cols, dc->world, s, (uint32_t)i, &c0, &nc);
             if (!nc) continue;
             CU(cudaMemcpyAsync(dc->recv + m.recv_off + (uint64_t)c0 * m.rpg, dev_recv + off, m.rpg * nc * 4, cudaMemcpyDeviceToDevice, ctx->stream));
             off += m.rpg * nc;

@@ -190,4 +190,81 @@ __global__ void __launch_bounds__(128, BFGPU_QUOT_MINBLOCKS) k_quotient(Quotient
     o[3 * n] = acc.c[3];
 }
 
+
+// ---- quotient over ROW SHARDS (one proof over several GPUs, dist_prove.cuh) ----------------------------------------------------
+// The committed LDEs of a sharded commitment live as row shards: rank r holds stored rows [r * rpg, (r + 1) * rpg) of every matrix,
+// column-major with rpg words per column, and every rank has all shards mapped (CUDA IPC over NVLink).  A thread handles one LOCAL
+// stored row; its "next" row (natural index + 2) sits at a fixed stored offset that usually belongs to another rank and is read
+// straight out of that peer's HBM.  The preprocessed LDE is replicated (full height on every rank).  Each quotient word goes to the
+// rank that owns that COLUMN of the quotient-chunk matrix (column-sharded LDE of the next commitment): out_col[chunk][k] points into
+// the owner's coefficient buffer, so the row -> column exchange of the quotient commit is the kernel's own store.
+constexpr int AIR_MAX_WORLD = 16;
+struct ShardedLde {
+    const uint32_t* shard[AIR_MAX_WORLD];  // shard r of this matrix (null when the chip has no such trace)
+};
+struct QuotientShardArgs {
+    int chip;
+    ShardedLde main, perm;
+    const uint32_t* prep;  // full preprocessed LDE (2^(log_n + lqd) rows) or null
+    unsigned log_n, lqd, log_rpg;
+    uint32_t rank;
+    uint32_t shift, g_inv, zh[2], zh_inv[2];
+    const kb::Ext* apow;
+    const uint32_t* tw;
+    uint32_t* out_col[2][4];  // [chunk][extension coefficient]: column of 2^log_n words on the owning rank
+};
+struct ShardLoader {
+    const uint32_t *m0, *m1, *p0, *p1, *q0, *q1;  // row pointers (column 0) of the local / next row in main, prep, perm
+    uint64_t ms, ps;                               // words between columns: shard height (main, perm), full height (prep)
+    __device__ __forceinline__ uint32_t main0(int c) const { return m0[(uint64_t)c * ms]; }
+    __device__ __forceinline__ uint32_t main1(int c) const { return m1[(uint64_t)c * ms]; }
+    __device__ __forceinline__ uint32_t prep0(int c) const { return p0[(uint64_t)c * ps]; }
+    __device__ __forceinline__ uint32_t prep1(int c) const { return p1[(uint64_t)c * ps]; }
+    __device__ __forceinline__ kb::Ext perm0(int j) const {
+        const uint32_t* p = q0 + (uint64_t)(4 * j) * ms;
+        return kb::Ext{{p[0], p[ms], p[2 * ms], p[3 * ms]}};
+    }
+    __device__ __forceinline__ kb::Ext perm1(int j) const {
+        const uint32_t* p = q1 + (uint64_t)(4 * j) * ms;
+        return kb::Ext{{p[0], p[ms], p[2 * ms], p[3 * ms]}};
+    }
+};
+template <int CHIP>
+__global__ void __launch_bounds__(128, BFGPU_QUOT_MINBLOCKS) k_quotient_shard(QuotientShardArgs A, Challenges ch) {
+    const unsigned L = A.log_n + A.lqd;
+    const uint64_t N = 1ull << L, n = 1ull << A.log_n, rpg = 1ull << A.log_rpg;
+    const uint64_t tl = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (tl >= rpg) return;
+    const uint64_t t = ((uint64_t)A.rank << A.log_rpg) + tl;  // global stored row
+    const uint32_t i = kb::bitrev((uint32_t)t, L);
+    const uint32_t inext = (i + (1u << A.lqd)) & (uint32_t)(N - 1);
+    const uint64_t tn = kb::bitrev(inext, L);
+    const uint32_t rn = (uint32_t)(tn >> A.log_rpg);
+    const uint64_t tnl = tn & (rpg - 1);
+    ShardLoader ld;
+    ld.ms = rpg;
+    ld.ps = N;
+    ld.m0 = A.main.shard[A.rank] + tl;
+    ld.m1 = A.main.shard[rn] + tnl;
+    ld.q0 = A.perm.shard[A.rank] + tl;
+    ld.q1 = A.perm.shard[rn] + tnl;
+    ld.p0 = A.prep ? A.prep + t : nullptr;
+    ld.p1 = A.prep ? A.prep + tn : nullptr;
+    const uint32_t x = kb::mul(A.shift, root_pow_(A.tw, L, i));
+    const uint32_t zh = A.zh[i & ((1u << A.lqd) - 1)], zh_inv = A.zh_inv[i & ((1u << A.lqd) - 1)];
+    Selectors sel;
+    const uint32_t d_first = kb::sub(x, kb::ONE), d_last = kb::sub(x, A.g_inv);
+    const uint32_t ip = kb::mul(zh, kb::inv(kb::mul(d_first, d_last)));
+    sel.is_first = kb::mul(ip, d_last);
+    sel.is_last = kb::mul(ip, d_first);
+    sel.is_trans = d_last;
+    kb::Ext acc = kb::ext_zero();
+    air_constraints(CHIP, ld, sel, ch, A.apow, acc);
+    acc = kb::ext_scale(acc, zh_inv);
+    const uint32_t c = (uint32_t)(t >> A.log_n);
+    const uint64_t pos = t & (n - 1);
+#pragma unroll
+    for (int k = 0; k < 4; k++) A.out_col[c][k][pos] = acc.c[k];
+}
+
 }  // namespace air

@@ -31,13 +31,16 @@ __device__ __forceinline__ uint32_t root_pow(const uint32_t* __restrict__ tw, un
 
 // ---- barycentric weights: w[r] = g^{br(r)} / (z - s g^{br(r)}),  r < h = 2^log_h ---------------------
 // (rows of the low coset of a stored LDE are in bit-reversed order; s = coset shift, Montgomery)
-__global__ void k_bary_weights(uint32_t* __restrict__ w, unsigned log_h, uint32_t shift, Ext z, const uint32_t* __restrict__ tw) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= (1u << log_h)) return;
+// rows [r0, r0 + count) of the coset only (w[0] = weight of row r0): a rank of the sharded prover evaluates over its own row shard
+__global__ void k_bary_weights(uint32_t* __restrict__ w, unsigned log_h, uint32_t shift, Ext z, const uint32_t* __restrict__ tw, uint32_t r0,
+                               uint32_t count) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const uint32_t r = r0 + k;
     uint32_t g = root_pow(tw, log_h, kb::bitrev(r, log_h));
     Ext d = z;
     d.c[0] = kb::sub(d.c[0], kb::mul(shift, g));
-    st_ext(w + 4 * (uint64_t)r, kb::ext_scale(kb::ext_inv(d), g));
+    st_ext(w + 4 * (uint64_t)k, kb::ext_scale(kb::ext_inv(d), g));
 }
 
 // partial[(c * nchunks + chunk) * NP + t] = sum over the chunk's rows of col_c[r] * w_t[r]
@@ -145,7 +148,8 @@ __global__ void k_bary_finish(const uint32_t* __restrict__ partial, uint32_t* __
 #endif
 constexpr int RO_UNROLL = BFGPU_RO_UNROLL;  // column loads in flight per thread in k_reduce_openings
 struct RoMat {
-    const uint32_t* d;  // column-major LDE, `rows` rows
+    const uint32_t* d;  // column-major LDE: first row handled by the launch (a row shard points at its first local row)
+    uint64_t stride;    // words between columns (the height of the buffer `d` points into)
     uint32_t width;
     uint32_t npoints;    // 1 or 2
     uint32_t pt[2];      // index into the group's point list
@@ -155,10 +159,12 @@ struct RoMat {
 // ro[r] = sum_{mat, point} aoff * (yred - sum_k alpha^k M[r][k]) / (z_point - x_r),  x_r = shift * w_H^{br(r)}
 __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict__ mats, uint32_t nmats, const uint32_t* __restrict__ zs /* npts x 4 */,
                                                          uint32_t npts, const uint32_t* __restrict__ apow /* ext alpha^k */, unsigned log_h,
-                                                         uint32_t shift, const uint32_t* __restrict__ tw, uint32_t* __restrict__ ro) {
+                                                         uint32_t shift, const uint32_t* __restrict__ tw, uint32_t* __restrict__ ro, uint32_t r0,
+                                                         uint32_t count) {
+    // rows [r0, r0 + count) of the height-2^log_h group; matrices, ro and the thread index are relative to r0 (row shard of a rank)
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= (1u << log_h)) return;
-    uint32_t x = kb::mul(shift, root_pow(tw, log_h, kb::bitrev(r, log_h)));
+    if (r >= count) return;
+    uint32_t x = kb::mul(shift, root_pow(tw, log_h, kb::bitrev(r0 + r, log_h)));
     // 1 / (z_t - x) for the (at most four) opening points of this height: Montgomery's trick, ONE extension inversion per row
     // (an inversion is ~1 200 instructions, an extension product ~140; the two inversions were 60 % of this kernel)
     Ext inv[4], pre[4];
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
         const uint32_t* col = M.d + r;
 #pragma unroll RO_UNROLL
         for (uint32_t k = 0; k < M.width; k++) {
-            uint32_t v = col[(uint64_t)k << log_h];
+            uint32_t v = col[(uint64_t)k * M.stride];
             Ext a = ld_ext(apow + 4 * k);
             kb::mac(a0, a.c[0], v);
             kb::mac(a1, a.c[1], v);
@@ -206,10 +212,11 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
 // ---- FRI fold: out[i] = (1/2 + b g^-br(i)) in[2i] + (1/2 - b g^-br(i)) in[2i+1] (+ add[i]),  b = beta/2 -----
 // rollin: how the reduced opening of the new height enters (BFGPU_OPT_FRI_ROLLIN): 0 = plain sum (Plonky3 of the pinned API era),
 // 1 = beta^2 * add[i] (the later upstream rule), beta being this round's folding challenge
+// i0: global index of element 0 of in/out/add (a rank of the sharded prover folds its contiguous slice of the vector)
 __device__ __forceinline__ void fri_fold_one(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h,
-                                             Ext half_beta, const uint32_t* __restrict__ tw, uint32_t i, int rollin = 0) {
+                                             Ext half_beta, const uint32_t* __restrict__ tw, uint32_t i, int rollin = 0, uint32_t i0 = 0) {
     // g = generator of order 2^(log_h+1); g^-j = w^(2^(log_h+1) - j)
-    uint32_t j = kb::bitrev(i, log_h);
+    uint32_t j = kb::bitrev(i0 + i, log_h);
     uint32_t ginv = j ? root_pow(tw, log_h + 1, (1u << (log_h + 1)) - j) : kb::ONE;
     Ext lo = ld_ext(in + 8 * (uint64_t)i), hi = ld_ext(in + 8 * (uint64_t)i + 4);
     Ext pw = kb::ext_scale(half_beta, ginv);
@@ -225,11 +232,12 @@ __device__ __forceinline__ void fri_fold_one(const uint32_t* __restrict__ in, ui
     }
     st_ext(out + 4 * (uint64_t)i, o);
 }
+// host-supplied beta, elements [i0, i0 + count) of the output (sharded prover: the challenger runs on the host between the rounds)
 __global__ void k_fri_fold(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h /* out length */,
-                           Ext half_beta, const uint32_t* __restrict__ tw) {
+                           Ext half_beta, const uint32_t* __restrict__ tw, int rollin, uint32_t i0, uint32_t count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (1u << log_h)) return;
-    fri_fold_one(in, out, add, log_h, half_beta, tw, i);
+    if (i >= count) return;
+    fri_fold_one(in, out, add, log_h, half_beta, tw, i, rollin, i0);
 }
 
 // ---- Fiat-Shamir on the device for the rounds that are too big for the tail kernel --------------------------------------------
@@ -290,11 +298,11 @@ __global__ void __launch_bounds__(32) k_challenger_round(uint32_t* __restrict__ 
 }
 // fold with beta read from device memory (written by k_challenger_round)
 __global__ void k_fri_fold_dev(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ add, unsigned log_h,
-                               const uint32_t* __restrict__ beta, const uint32_t* __restrict__ tw, int rollin) {
+                               const uint32_t* __restrict__ beta, const uint32_t* __restrict__ tw, int rollin, uint32_t i0, uint32_t count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (1u << log_h)) return;
+    if (i >= count) return;
     const Ext half_beta = kb::ext_scale(ld_ext(beta), kb::halve(kb::ONE));
-    fri_fold_one(in, out, add, log_h, half_beta, tw, i, rollin);
+    fri_fold_one(in, out, add, log_h, half_beta, tw, i, rollin, i0);
 }
 
 // ---- FRI tail: every commit-phase round whose input has at most 2^TAIL_MAX_LOG elements, in ONE single-CTA launch -----

@@ -538,9 +538,10 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
     AllocScope scope(ctx);  // blocks taken by a failing call go back to the cache (see AllocScope)
     return scope.ok(machine_commit_record_impl(ctx, rec, root, out));
 }
-static int32_t machine_commit_record_impl(bfgpu_ctx* ctx, const bfgpu_record* rec, uint32_t root[8], bfgpu_shard** out) {
-    if (!ctx || !rec || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
-    *out = nullptr;
+// Every included chip's main trace generated on the device from the execution record, in the prover's layout (column-major, Montgomery,
+// bit-reversed rows), sorted by (height desc, name) as `MachineProver::commit` orders them (prover.rs:214).  The caller owns the blocks.
+static int32_t record_traces(bfgpu_ctx* ctx, const bfgpu_record* rec, std::vector<std::string>* out_names, std::vector<int>* out_chip,
+                             std::vector<DMat>* out_traces) {
     const uint32_t n = (uint32_t)rec->n_cycles, n_instr = (uint32_t)rec->ops.size(), n_cells = (uint32_t)(rec->mem_events.size() / 5);
     if (n == 0) return fail(ctx, BFGPU_ERR_INVALID, "empty execution");
     // The Cpu trace is padded to a power of two with no minimum (utils/mod.rs:25-53): one cycle gives a ONE-row trace whose
@@ -651,7 +652,6 @@ static int32_t machine_commit_record_impl(bfgpu_ctx* ctx, const bfgpu_record* re
         for (DMat& t : traces) dfree(ctx, t.d);
         return rc;
     }
-    // ---- commit: sort by (height desc, name) (prover.rs:214), LDE a scratch copy of every trace, Merkle tree ----
     const size_t nt = traces.size();
     std::vector<size_t> order(nt);
     for (size_t k = 0; k < nt; k++) order[k] = k;
@@ -659,15 +659,31 @@ static int32_t machine_commit_record_impl(bfgpu_ctx* ctx, const bfgpu_record* re
         if (traces[a].rows != traces[b].rows) return traces[a].rows > traces[b].rows;
         return names[a] < names[b];
     });
+    for (size_t k = 0; k < nt; k++) {
+        out_names->push_back(names[order[k]]);
+        out_chip->push_back(chip_index(names[order[k]].c_str()));
+        out_traces->push_back(traces[order[k]]);
+    }
+    return BFGPU_OK;
+}
+
+static int32_t machine_commit_record_impl(bfgpu_ctx* ctx, const bfgpu_record* rec, uint32_t root[8], bfgpu_shard** out) {
+    if (!ctx || !rec || !root || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    // ---- commit: traces sorted by (height desc, name) (prover.rs:214), LDE a scratch copy of every trace, Merkle tree ----
     auto* sd = new bfgpu_shard();
     sd->ctx = ctx;
+    int32_t rc = record_traces(ctx, rec, &sd->names, &sd->chip, &sd->traces);
+    if (rc != BFGPU_OK) {
+        delete sd;
+        return rc;
+    }
+    std::vector<DMat>& traces = sd->traces;
+    const size_t nt = traces.size();
     std::vector<DMat> coefs(nt);
     std::vector<uint32_t> shifts(nt, kb::to_mont(kb::GEN));
     for (size_t k = 0; k < nt && rc == BFGPU_OK; k++) {
-        const DMat& t = traces[order[k]];
-        sd->names.push_back(names[order[k]]);
-        sd->chip.push_back(chip_index(names[order[k]].c_str()));
-        sd->traces.push_back(t);
+        const DMat& t = traces[k];
         coefs[k] = t;
         coefs[k].d = nullptr;
         rc = dalloc(ctx, (void**)&coefs[k].d, t.rows * t.cols * 4);

@@ -1,9 +1,10 @@
-"""Multi-GPU sharding of the proving hot path: one process per GPU, no data-path collective.
+"""Multi-GPU sharding of the proving hot path: one process per GPU.
 
-Trace matrices (chips) and whole proofs are independent units: every rank commits / proves the units the
-plan assigns to it and only 8-word roots (and timing scalars) cross ranks, through `torch.distributed`
-(NCCL on the GPU box, gloo in the CPU tests).  Sharding ONE commitment by rows (column shards -> row shards
-all-to-all, then an all-gather of subtree caps) is designed in DESIGN.md §7 but not built in round 1.
+Three levels: independent units (`plan_units`: whole traces / proofs per rank, no data-path exchange), ONE commitment over
+all ranks (`DistributedCommit`: column-sharded LDE, P2P row exchange into peer HBM, per-rank subtrees, cap tree) and ONE
+shard proof over all ranks (`DistributedProver`, csrc/dist_prove.cuh).  `torch.distributed` carries only the control
+plane (IPC handles, caps, partial sums, proof pieces, barriers): NCCL or gloo for the tensors of bench.py, a gloo group for
+the small host-side exchanges of the sharded prover.
 """
 import numpy as np
 
@@ -49,7 +50,8 @@ def max_over_ranks(value, dist=None, device=None):
 
 # ---- one commitment over several GPUs -----------------------------------------------------------------------------
 def col_range(total_cols, world_size, rank):
-    """Columns [c0, c0 + n) of a `total_cols`-wide matrix that `rank` extends (same rule as dist_commit.cuh)."""
+    """Columns [c0, c0 + n) of a `total_cols`-wide matrix that `rank` extends when it is matrix 0 of a commitment (matrix i uses
+    position (rank + i) mod world: `DistributedCommit.local_cols`; same rule as dist_commit.cuh)."""
     a, b = total_cols * rank // world_size, total_cols * (rank + 1) // world_size
     return a, b - a
 
@@ -100,7 +102,10 @@ class DistributedCommit:
         self._send = self._recv = None
 
     def local_cols(self, i):
-        return col_range(int(self.total_cols[i]), self.world, self.rank)
+        """(first column, count) of matrix i this rank extends: the even split taken at position (rank + i) mod world (dist_commit.cuh)"""
+        c0 = self._C.c_uint32()
+        n = self._lib.bfgpu_dist_commit_local_cols(self._h, int(i), self._C.byref(c0))
+        return int(c0.value), int(n)
 
     def commit(self, local_mats, domain_shifts=None):
         """local_mats[i]: this rank's rows[i] x local_cols(i) slice — numpy array (host input space) or a
@@ -185,3 +190,81 @@ class DistributedCommit:
             self.free()
         except Exception:  # interpreter shutdown: module globals may already be gone
             pass
+
+
+# ---- one shard proof over several GPUs -----------------------------------------------------------------------------------
+class DistributedProver:
+    """`MachineProver::prove` (crates/stark/src/prover.rs:560-582) of ONE shard by all ranks of a process group
+    (csrc/dist_prove.cuh): every rank calls with the same proving key / record / challenger state and receives the same
+    serialised proof, word for word the single-GPU one.  The library's control plane (bfgpu_comm: all-gather of small host
+    buffers + barrier) is served by a gloo group created next to the caller's group."""
+
+    def __init__(self, ctx, dist, group=None):
+        import ctypes as C
+        from . import lib
+        self._C, self._lib, self.ctx, self.dist = C, lib(), ctx, dist
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        backend = str(dist.get_backend(group))
+        # host-side exchanges: gloo.  (new_group is collective: every rank of the default group constructs its DistributedProver)
+        self._cpu_group = group if "gloo" in backend and "nccl" not in backend else dist.new_group(backend="gloo")
+        self.calls = {"all_gather": 0, "barrier": 0, "bytes": 0}
+        AG = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+        BR = C.CFUNCTYPE(C.c_int32, C.c_void_p)
+
+        def all_gather(_user, send, recv, nbytes):
+            try:
+                import torch
+                n = int(nbytes)
+                src = torch.frombuffer((C.c_uint8 * n).from_address(send), dtype=torch.uint8)
+                dst = torch.frombuffer((C.c_uint8 * (n * self.world)).from_address(recv), dtype=torch.uint8)
+                self.dist.all_gather(list(dst.view(self.world, n).unbind(0)), src, group=self._cpu_group)
+                self.calls["all_gather"] += 1
+                self.calls["bytes"] += n
+                return 0
+            except Exception:  # never unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        def barrier(_user):
+            try:
+                self.dist.barrier(group=self._cpu_group)
+                self.calls["barrier"] += 1
+                return 0
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        class Comm(C.Structure):
+            _fields_ = [("user", C.c_void_p), ("all_gather", AG), ("barrier", BR)]
+
+        self._cb = (AG(all_gather), BR(barrier))  # keep the thunks alive
+        self._comm = Comm(None, self._cb[0], self._cb[1])
+
+    def _finish(self, h):
+        C, L = self._C, self._lib
+        size = L.bfgpu_shard_proof_size(h)
+        buf = np.zeros(size, np.uint32)
+        self.ctx.check(L.bfgpu_shard_proof_read(h, buf.ctypes.data_as(C.c_void_p)))
+        L.bfgpu_shard_proof_free(h)
+        return buf
+
+    def prove_record(self, pk, rec, challenger, pow_witness=None):
+        """proof words from an execution record (`bf.Record`): device-side trace generation replicated, the rest sharded"""
+        C = self._C
+        h = C.c_void_p()
+        self.ctx.check(self._lib.bfgpu_dist_prove_record(self.ctx._h, C.byref(self._comm), self.rank, self.world, pk._h, rec._h, challenger._h,
+                                                          -1 if pow_witness is None else int(pow_witness), C.byref(h)))
+        return self._finish(h)
+
+    def prove(self, pk, traces, challenger, pow_witness=None):
+        """proof words from host traces {chip name: main trace} (every rank passes all of them)"""
+        from . import _named_mats
+        C = self._C
+        named = list(traces.items())
+        cn, arr, keep = _named_mats(named)
+        h = C.c_void_p()
+        self.ctx.check(self._lib.bfgpu_dist_prove(self.ctx._h, C.byref(self._comm), self.rank, self.world, pk._h, cn, arr, len(named), challenger._h,
+                                                   -1 if pow_witness is None else int(pow_witness), C.byref(h)))
+        return self._finish(h)
