@@ -492,7 +492,66 @@ def main():
                          "pipelined_ms_per_proof": dtp * 1e3, "pipelined_proofs_per_s": world / dtp, "pipelined_trace_rows_per_s": world * (1 << 22) / dtp}
         pk.free()
 
-    sharded_prove = None  # filled by the one-proof-over-N-GPUs measurement below when the sharded prover is built in
+    # ---- N > 1: ONE shard proof over all ranks (BASELINE configs 3 and 5; csrc/dist_prove.cuh) --------------------------------------
+    sharded_prove = None
+    if dist is not None and not args.no_prove:
+        ctx.set_input_space(bf.MEM_HOST)
+        prover = bf.CudaProver(ctx)
+        dp = shard.DistributedProver(ctx, dist)
+        sharded_prove = {"note": "ONE proof by all ranks: sharded commitments, replicated LogUp traces, row-sharded quotient (P2P next-row reads, "
+                                 "column-owner stores), sharded openings / FRI rounds, owner-answered queries; the proof is word for word the single-GPU proof"}
+        for name, code in (("loop 2^20 Cpu rows (config 3)", "-[>-[>+>+>+<<<-]<-]"), ("loop 2^22 Cpu rows (north-star size)", "++++++++[>-[>-[>+>+<<-]<-]<-]")):
+            rec = prover.execute(code)
+            pk = prover.setup_record(rec)
+
+            def once(program=False):
+                r = prover.execute(code) if program else rec
+                ch = bf.Challenger(ctx)
+                lib.bfgpu_pk_observe_into(pk._h, ch._h)
+                w = dp.prove_record(pk, r, ch.clone())
+                if program:
+                    r.free()
+                return w
+
+            words = once()
+            calls0 = dict(dp.calls)
+            once()
+            calls = {k: dp.calls[k] - calls0[k] for k in calls0}
+            times, ptimes = [], []
+            for _ in range(max(args.steps, 3)):
+                barrier()
+                t0 = time.perf_counter()
+                once()
+                ctx.synchronize()
+                times.append(shard.max_over_ranks(time.perf_counter() - t0, dist, "cuda") * 1e3)
+            for _ in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                once(program=True)
+                ctx.synchronize()
+                ptimes.append(shard.max_over_ranks(time.perf_counter() - t0, dist, "cuda") * 1e3)
+            # one more with the per-phase device timers (this rank)
+            ctx.profile_enable(True)
+            once()
+            ph = {k: v[0] for k, v in ctx.profile_read().items() if v[0] or v[1]}
+            ctx.profile_enable(False)
+            # reference: the same proof on ONE GPU (this rank alone), and the native verifier's verdict
+            single = None
+            if rank == 0:
+                ch = bf.Challenger(ctx)
+                lib.bfgpu_pk_observe_into(pk._h, ch._h)
+                sh = prover.commit_record(rec)
+                ref = prover.open_raw(pk, sh, ch.clone())
+                sh.free()
+                single = {"identical_to_single_gpu_proof": bool(ref.shape == words.shape and (ref == words).all()),
+                          "native_verifier": bf.verify_shard(pk.commit, pk.names, pk.heights, words) or "accepted"}
+            barrier()
+            sharded_prove[name] = {"cycles": rec.cycles, "proof_words": int(words.size), "prove_ms": min(times), "prove_ms_median": statistics.median(times),
+                                   "program_to_proof_ms": min(ptimes), "trace_rows_per_s": float(1 << (20 if "2^20" in name else 22)) / (min(times) * 1e-3),
+                                   "control_plane_calls_per_proof": calls, "phases_ms_rank0": ph, **(single or {})}
+            pk.free()
+            rec.free()
+        ctx.set_input_space(bf.MEM_DEVICE)
 
     # ---- N > 1: ONE commitment over all ranks (columns -> LDE -> P2P row exchange -> subtrees -> caps) -------
     one_commitment = None
