@@ -29,8 +29,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, fri, from_traces, q):
+def _worker(rank, world, port, case, fri, from_traces, q, gather_log=None):
     try:
+        if gather_log is not None:  # force sharded FRI rounds on small proofs
+            os.environ["BFGPU_DIST_FRI_GATHER_LOG"] = str(gather_log)
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
         dist.init_process_group("gloo", rank=rank, world_size=world)
         dev = rank % torch.cuda.device_count()
@@ -78,11 +80,11 @@ def _worker(rank, world, port, case, fri, from_traces, q):
         q.put((rank, traceback.format_exc() + repr(e), None))
 
 
-def _run(world, case, fri=(1, 12, 6), from_traces=False):
+def _run(world, case, fri=(1, 12, 6), from_traces=False, gather_log=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, fri, from_traces, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, fri, from_traces, q, gather_log)) for r in range(world)]
     for p in procs:
         p.start()
     res = []
@@ -108,6 +110,14 @@ def test_sharded_proof_is_the_single_gpu_proof(world, case):
         assert r["got"] == r["words"], (rank, r)
         assert all(r["same"]), f"rank {rank}: sharded proof differs from the single-GPU proof (first differing word {r['first_diff']})"
         assert r["verdict"] is None, r["verdict"]
+
+
+@pytest.mark.parametrize("world,case,gather_log", [(2, "tiny", 6), (4, "fibo", 8), (8, "fibo", 10), (4, "loop18", 13)])
+def test_sharded_fri_rounds_above_the_gather_point(world, case, gather_log):
+    """the default gather point (2^20 elements) leaves small proofs without a sharded FRI round: lower it so that the per-round subtree +
+    cap exchange + sharded fold + owner-answered layer openings run on the test programs too"""
+    for rank, _, r in _run(world, case, gather_log=gather_log):
+        assert all(r["same"]) and r["verdict"] is None, (rank, r)
 
 
 def test_sharded_proof_full_parameters_from_host_traces():

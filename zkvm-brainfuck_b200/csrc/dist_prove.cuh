@@ -12,8 +12,8 @@
 //                                              row from the peer that holds it (P2P load) and stores each quotient word into the
 //                                              coefficient buffer of the rank that owns that COLUMN of the quotient commitment
 //   opened values                              row-sharded barycentric partial sums over the whole LDE coset + one small all-gather
-//   reduced openings, FRI folds                row-local on the row shards; per round a subtree + cap exchange; below 2^13 elements the
-//                                              vector is gathered and every rank finishes the commit phase redundantly
+//   reduced openings, FRI folds                row-local on the row shards; per round a subtree + cap exchange; at 2^20 elements the
+//                                              vector is all-gathered by peer copies and every rank finishes the commit phase alone
 //   queries                                    answered by the rank owning the leaf; one all-gather assembles the proof on every rank
 //
 // Only the data path touches peer HBM.  The control plane (64-byte IPC handles, 32-byte caps, partial sums, proof pieces, barriers)
@@ -21,6 +21,9 @@
 // host all-gathers and ~8 barriers per proof.  The Fiat-Shamir challenger is replicated: every rank observes the same roots and
 // samples the same challenges.
 #pragma once
+
+// global length (log2) at which the FRI vector stops being sharded ($BFGPU_DIST_FRI_GATHER_LOG overrides, tests use 13): above it every round costs a subtree + a cap exchange through the
+// host communicator, below it one device finishes alone; measured with the threshold at 2^13 the ~10 sharded rounds cost 8.5 ms at 8 ranks
 
 namespace distp {
 
@@ -65,6 +68,29 @@ static void cap_tree(const uint32_t* caps, uint32_t world, std::vector<std::vect
 }
 
 }  // namespace distp
+
+// map the exported buffers of all ranks from their 64-byte IPC handles (handles[r] at stride `stride`); mine = this rank's own pointer
+static int32_t dist_map_peers(bfgpu_ctx* ctx, const uint8_t* handles, size_t stride, uint32_t rank, uint32_t world, void* mine, std::vector<uint32_t*>* out) {
+    out->assign(world, nullptr);
+    for (uint32_t r = 0; r < world; r++) {
+        if (r == rank) {
+            (*out)[r] = (uint32_t*)mine;
+            continue;
+        }
+        std::array<uint8_t, 64> key;
+        memcpy(key.data(), handles + stride * r, 64);
+        auto it = ctx->ipc_open.find(key);
+        if (it == ctx->ipc_open.end()) {
+            cudaIpcMemHandle_t hh;
+            memcpy(&hh, key.data(), 64);
+            void* p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, hh, cudaIpcMemLazyEnablePeerAccess));
+            it = ctx->ipc_open.emplace(key, p).first;
+        }
+        (*out)[r] = (uint32_t*)it->second;
+    }
+    return BFGPU_OK;
+}
 
 #define COMM(call)                                                                                           \
     do {                                                                                                     \
@@ -128,10 +154,11 @@ static int32_t dist_prove_core(bfgpu_ctx* ctx, const bfgpu_comm* comm, uint32_t 
     struct DcGuard {
         bfgpu_dist_commit* dc[3] = {nullptr, nullptr, nullptr};
         bfgpu_ctx* ctx = nullptr;
-        uint32_t* qcol = nullptr;
+        uint32_t *qcol = nullptr, *gbuf = nullptr;
         ~DcGuard() {
             for (auto* d : dc) bfgpu_dist_commit_free(d);
             if (qcol) dfree_export(ctx, qcol);
+            if (gbuf) dfree_export(ctx, gbuf);
         }
     } G;
     G.ctx = ctx;
@@ -159,37 +186,31 @@ static int32_t dist_prove_core(bfgpu_ctx* ctx, const bfgpu_comm* comm, uint32_t 
     };
     const uint64_t qcol_words = qcol_offset(rank, 2 * nchips);
     TRY(dalloc_export(ctx, (void**)&G.qcol, std::max<uint64_t>(qcol_words, 1) * 4));
-    std::vector<uint32_t*> qcol_peer(world, nullptr);
+    // FRI gather buffer: below `gather_at` elements the folded vector and the reduced openings still to come are all-gathered by
+    // plain peer copies into this buffer on every rank (less than 2 * gather_at extension elements in total)
+    unsigned log_tallest = 0;
+    for (size_t i = 0; i < nchips; i++) log_tallest = std::max(log_tallest, ilog2(rows_main[i]) + 1);
+    for (const DMat& m : pk->data->ldes) log_tallest = std::max(log_tallest, ilog2(m.rows));
+    const uint64_t gather_at = std::min<uint64_t>(1ull << log_tallest, std::max<uint64_t>(1ull << ctx->dist_fri_gather_log, 4ull * world));
+    TRY(dalloc_export(ctx, (void**)&G.gbuf, 2 * gather_at * 16));
+    std::vector<uint32_t*> qcol_peer, gbuf_peer;
     {
-        uint8_t mine[4 * 64];
+        uint8_t mine[5 * 64];
         for (int k = 0; k < 3; k++) TRY(bfgpu_dist_commit_recv_handle(G.dc[k], mine + 64 * k));
         cudaIpcMemHandle_t h;
         CU(cudaIpcGetMemHandle(&h, G.qcol));
         memcpy(mine + 192, &h, 64);
-        std::vector<uint8_t> all((size_t)world * 256);
-        COMM(comm->all_gather(comm->user, mine, all.data(), 256));
+        CU(cudaIpcGetMemHandle(&h, G.gbuf));
+        memcpy(mine + 256, &h, 64);
+        std::vector<uint8_t> all((size_t)world * 320);
+        COMM(comm->all_gather(comm->user, mine, all.data(), 320));
         std::vector<uint8_t> per(world * 64);
         for (int k = 0; k < 3; k++) {
-            for (uint32_t r = 0; r < world; r++) memcpy(&per[64 * r], &all[256 * r + 64 * k], 64);
+            for (uint32_t r = 0; r < world; r++) memcpy(&per[64 * r], &all[320 * r + 64 * k], 64);
             TRY(bfgpu_dist_commit_set_peers(G.dc[k], per.data()));
         }
-        for (uint32_t r = 0; r < world; r++) {
-            if (r == rank) {
-                qcol_peer[r] = G.qcol;
-                continue;
-            }
-            std::array<uint8_t, 64> key;
-            memcpy(key.data(), &all[256 * r + 192], 64);
-            auto it = ctx->ipc_open.find(key);
-            if (it == ctx->ipc_open.end()) {
-                cudaIpcMemHandle_t hh;
-                memcpy(&hh, key.data(), 64);
-                void* p = nullptr;
-                CU(cudaIpcOpenMemHandle(&p, hh, cudaIpcMemLazyEnablePeerAccess));
-                it = ctx->ipc_open.emplace(key, p).first;
-            }
-            qcol_peer[r] = (uint32_t*)it->second;
-        }
+        TRY(dist_map_peers(ctx, all.data() + 192, 320, rank, world, G.qcol, &qcol_peer));
+        TRY(dist_map_peers(ctx, all.data() + 256, 320, rank, world, G.gbuf, &gbuf_peer));
     }
     // nobody may still be reading these exported buffers for a previous proof (they are recycled through the exported pool)
     COMM(comm->barrier(comm->user));
@@ -561,7 +582,6 @@ static int32_t dist_prove_core(bfgpu_ctx* ctx, const bfgpu_comm* comm, uint32_t 
     uint32_t final_poly[4];
     {
         Phase ph(ctx, BFGPU_PHASE_FRI);
-        const uint64_t gather_at = std::max<uint64_t>(1ull << 13, 4ull * world);  // global length at which the vector is gathered
         auto it = reduced.begin();
         uint32_t* folded = it->second;  // local slice
         uint64_t len = 1ull << it->first;
@@ -612,31 +632,34 @@ static int32_t dist_prove_core(bfgpu_ctx* ctx, const bfgpu_comm* comm, uint32_t 
             folded = next;
             len = nlen;
         }
-        // gather the folded vector and the reduced openings still to come: every rank finishes the commit phase on the whole vector
+        // gather the folded vector and the reduced openings still to come: every rank stores its slice into the gather buffer of every
+        // rank (peer copies over NVLink), one barrier, and every rank finishes the commit phase on the whole vector
+        uint64_t goff = 0;  // words
         auto gather_vec = [&](uint32_t* local, uint64_t glen, uint32_t** full) -> int32_t {
             const uint64_t ll = glen / world;
-            std::vector<uint32_t> mine(ll * 4), all(glen * 4);
-            CU(cudaMemcpyAsync(mine.data(), local, ll * 16, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            COMM(comm->all_gather(comm->user, mine.data(), all.data(), ll * 16));
-            TRY(dalloc(ctx, (void**)full, glen * 16));
-            CU(cudaMemcpyAsync(*full, all.data(), glen * 16, cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));  // `all` dies with this scope
+            if (goff + glen * 4 > 2 * gather_at * 4) return fail(ctx, BFGPU_ERR_STATE, "internal: FRI gather buffer too small");
+            for (uint32_t r = 0; r < world; r++) {
+                const uint32_t dst = (rank + 1 + r) % world;  // senders start at different receivers
+                CU(cudaMemcpyAsync(gbuf_peer[dst] + goff + (uint64_t)rank * ll * 4, local, ll * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            *full = G.gbuf + goff;
+            goff += glen * 4;
             return BFGPU_OK;
         };
         uint32_t* full = nullptr;
         TRY(gather_vec(folded, len, &full));
+        std::vector<std::pair<unsigned, uint32_t*>> gathered;
+        for (auto jt = it; jt != reduced.end(); ++jt) {
+            uint32_t* f = nullptr;
+            TRY(gather_vec(jt->second, 1ull << jt->first, &f));
+            gathered.push_back({jt->first, f});
+        }
+        TRY(dist_sync_barrier(ctx, comm));  // every slice has landed in this rank's buffer
         dfree(ctx, folded);
         folded = nullptr;
-        for (; it != reduced.end(); ++it) {
-            uint32_t* f = nullptr;
-            int32_t rc = gather_vec(it->second, 1ull << it->first, &f);
-            if (rc != BFGPU_OK) {
-                dfree(ctx, full);
-                return rc;
-            }
-            dfree(ctx, it->second);
-            it->second = f;
+        for (auto& g : gathered) {
+            dfree(ctx, reduced[g.first]);
+            reduced[g.first] = g.second;  // lives in the exported gather buffer: dfree() ignores blocks it does not own
         }
         TRY(fri_commit_phase(ctx, ch, full, len, reduced, layers, commits, final_poly));
     }
@@ -800,7 +823,32 @@ extern "C" int32_t bfgpu_dist_prove_record(bfgpu_ctx* ctx, const bfgpu_comm* com
     std::vector<std::string> names;
     std::vector<int> chips;
     std::vector<DMat> traces;
-    int32_t rc = record_traces(ctx, rec, &names, &chips, &traces);
+    // the 16-byte cycle records (67 MB at 4.2 M cycles): every rank uploads 1/world of them and stores its slice into all peers
+    // (8 ranks pulling the whole record over PCIe at once took 2.9 ms)
+    struct RecGuard {
+        bfgpu_ctx* ctx;
+        uint32_t* buf = nullptr;
+        ~RecGuard() { if (buf) dfree_export(ctx, buf); }
+    } recg{ctx};
+    const uint64_t nrec = rec->n_cycles + 1;
+    if (world > 1 && nrec >= 64 * (uint64_t)world && is_pow2(world) && rank < world) {
+        Phase ph(ctx, BFGPU_PHASE_H2D);
+        TRY(dalloc_export(ctx, (void**)&recg.buf, nrec * 16));
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, recg.buf));
+        std::vector<uint8_t> all((size_t)world * 64);
+        COMM(comm->all_gather(comm->user, &h, all.data(), 64));
+        std::vector<uint32_t*> peer;
+        TRY(dist_map_peers(ctx, all.data(), 64, rank, world, recg.buf, &peer));
+        const uint64_t lo = nrec * rank / world, hi = nrec * (rank + 1) / world;
+        CU(cudaMemcpyAsync(recg.buf + lo * 4, (const uint32_t*)rec->cycles + lo * 4, (hi - lo) * 16, cudaMemcpyHostToDevice, ctx->stream));
+        for (uint32_t r = 1; r < world; r++) {
+            const uint32_t dst = (rank + r) % world;
+            CU(cudaMemcpyAsync(peer[dst] + lo * 4, recg.buf + lo * 4, (hi - lo) * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        TRY(dist_sync_barrier(ctx, comm));
+    }
+    int32_t rc = record_traces(ctx, rec, &names, &chips, &traces, (const uint4*)recg.buf);
     if (rc != BFGPU_OK) return rc;
     auto* proof = new bfgpu_shard_proof();
     rc = dist_prove_core(ctx, comm, rank, world, pk, names, chips, traces, box(chh)->ch, fixed_pow_witness, &proof->flat);

@@ -540,8 +540,10 @@ extern "C" int32_t bfgpu_machine_commit_record(bfgpu_ctx* ctx, const bfgpu_recor
 }
 // Every included chip's main trace generated on the device from the execution record, in the prover's layout (column-major, Montgomery,
 // bit-reversed rows), sorted by (height desc, name) as `MachineProver::commit` orders them (prover.rs:214).  The caller owns the blocks.
+// d_cyc_in: the (cycles + 1) 16-byte cycle records already on the device (sharded prover: every rank uploads a slice and the ranks
+// exchange them over NVLink), or null to copy them from the record's page-locked host buffer here.
 static int32_t record_traces(bfgpu_ctx* ctx, const bfgpu_record* rec, std::vector<std::string>* out_names, std::vector<int>* out_chip,
-                             std::vector<DMat>* out_traces) {
+                             std::vector<DMat>* out_traces, const uint4* d_cyc_in = nullptr) {
     const uint32_t n = (uint32_t)rec->n_cycles, n_instr = (uint32_t)rec->ops.size(), n_cells = (uint32_t)(rec->mem_events.size() / 5);
     if (n == 0) return fail(ctx, BFGPU_ERR_INVALID, "empty execution");
     // The Cpu trace is padded to a power of two with no minimum (utils/mod.rs:25-53): one cycle gives a ONE-row trace whose
@@ -556,12 +558,13 @@ static int32_t record_traces(bfgpu_ctx* ctx, const bfgpu_record* rec, std::vecto
     unsigned int* d_hist = nullptr;
     {
         Phase ph(ctx, BFGPU_PHASE_H2D);
-        TRY(scratch.alloc((void**)&d_cyc, (size_t)(n + 1) * 16));
+        if (d_cyc_in) d_cyc = const_cast<uint4*>(d_cyc_in);
+        else TRY(scratch.alloc((void**)&d_cyc, (size_t)(n + 1) * 16));
         TRY(scratch.alloc((void**)&d_ops, n_instr));
         TRY(scratch.alloc((void**)&d_args, (size_t)n_instr * 4));
         TRY(scratch.alloc((void**)&d_counts, (size_t)n_instr * 4));
         TRY(scratch.alloc((void**)&d_mem, std::max<size_t>(rec->mem_events.size(), 1) * 4));
-        CU(cudaMemcpyAsync(d_cyc, rec->cycles, (size_t)(n + 1) * 16, cudaMemcpyHostToDevice, ctx->stream));
+        if (!d_cyc_in) CU(cudaMemcpyAsync(d_cyc, rec->cycles, (size_t)(n + 1) * 16, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(d_ops, rec->ops.data(), n_instr, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(d_args, rec->args.data(), (size_t)n_instr * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(d_counts, rec->prog_counts.data(), (size_t)n_instr * 4, cudaMemcpyHostToDevice, ctx->stream));
