@@ -341,6 +341,16 @@ int32_t bfgpu_verify_shard_ex(const uint32_t vk_commit[8], const char* const* pr
                               const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries,
                               uint32_t pow_bits, const uint32_t* options, int32_t n_options, char* err, uint64_t err_len);
 
+/* Canonical proof serialiser: the bytes `bincode::serialize(&MachineProof { shard_proof })` writes for this proof
+ * (crates/stark/src/types.rs:32-73,116-119; bincode 1.x defaults) — what the reference's `proofSize` counts
+ * (crates/core/machine/src/utils/prove.rs:47-56) and what a Rust caller can `bincode::deserialize` into a `MachineProof`.  Host code
+ * only.  field_repr: 1 = field elements as Montgomery words (p3-monty-31's serde form, P3), 0 = canonical residues.  `chip_ordering`
+ * is written in chip order (the reference iterates a randomly seeded hashbrown map: its byte ORDER differs per process, the byte COUNT
+ * does not).  out == NULL returns only *out_len. */
+int32_t bfgpu_shard_proof_to_bincode(const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep, const uint32_t* proof,
+                                     uint64_t n_words, int repr, uint32_t log_blowup, int field_repr, uint8_t* out, uint64_t out_cap,
+                                     uint64_t* out_len, char* err, uint64_t err_len);
+
 #ifdef __cplusplus
 }
 #endif

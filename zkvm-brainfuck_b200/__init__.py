@@ -92,6 +92,8 @@ ABI = {
                            C.c_char_p, C.c_uint64]),
     "bfgpu_verify_shard_ex": (C.c_int32, [_u32p, C.POINTER(C.c_char_p), _u32p, C.c_int32, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                               _u32p, C.c_int32, C.c_char_p, C.c_uint64]),
+    "bfgpu_shard_proof_to_bincode": (C.c_int32, [C.POINTER(C.c_char_p), _u32p, C.c_int32, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.c_void_p,
+                                                  C.c_uint64, _u64p, C.c_char_p, C.c_uint64]),
     "bfgpu_dist_commit_begin": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u32p, C.c_int32, C.POINTER(C.c_void_p)]),
     "bfgpu_dist_commit_local_cols": (C.c_uint32, [C.c_void_p, C.c_int32, _u32p]),
     "bfgpu_dist_commit_recv_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),
@@ -590,6 +592,26 @@ def verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1,
     rc = lib().bfgpu_verify_shard_ex(com.ctypes.data_as(_u32p), names, logs.ctypes.data_as(_u32p), len(prep_names), words.ctypes.data_as(_u32p), words.size,
                                      repr, log_blowup, num_queries, pow_bits, opt.ctypes.data_as(_u32p), 3, err, 256)
     return None if rc == 0 else (err.value.decode() or f"error {rc}")
+
+
+def proof_to_bincode(prep_names, prep_heights, proof_words, log_blowup=1, repr=REPR_CANONICAL, field_repr=1):
+    """`bincode::serialize(&MachineProof { shard_proof })` (crates/core/machine/src/utils/prove.rs:47) of a serialised proof: the bytes a
+    Rust caller deserialises, `len()` of which is the reference's `proofSize`.  field_repr 1 = Montgomery words (p3-monty-31 serde), 0 =
+    canonical.  Needs no GPU."""
+    words = _u32(proof_words)
+    names = (C.c_char_p * len(prep_names))(*[n.encode() for n in prep_names])
+    logs = _u32([int(h).bit_length() - 1 for h in prep_heights])
+    err = C.create_string_buffer(256)
+    n = C.c_uint64()
+    args = (names, logs.ctypes.data_as(_u32p), len(prep_names), words.ctypes.data_as(_u32p), words.size, repr, log_blowup, field_repr)
+    rc = lib().bfgpu_shard_proof_to_bincode(*args, None, 0, C.byref(n), err, 256)
+    if rc != 0:
+        raise BfGpuError(f"bfgpu_shard_proof_to_bincode: {err.value.decode()}")
+    out = np.zeros(n.value, np.uint8)
+    rc = lib().bfgpu_shard_proof_to_bincode(*args, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n), err, 256)
+    if rc != 0:
+        raise BfGpuError(f"bfgpu_shard_proof_to_bincode: {err.value.decode()}")
+    return out.tobytes()
 
 
 class Record:

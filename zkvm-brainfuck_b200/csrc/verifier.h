@@ -428,3 +428,188 @@ extern "C" int32_t bfgpu_verify_shard(const uint32_t vk_commit[8], const char* c
     return bfgpu_verify_shard_ex(vk_commit, prep_names, prep_log_heights, n_prep, proof, n_words, repr, log_blowup, num_queries, pow_bits, nullptr, 0, err,
                                  err_len);
 }
+
+// ---- canonical proof serialiser: the bytes `bincode::serialize(&MachineProof)` writes ------------------------------
+// The reference measures `proofSize` as the length of `bincode::serialize(&proof)` (crates/core/machine/src/utils/prove.rs:47-56) over
+// `MachineProof { shard_proof: ShardProof { commitment, opened_values, opening_proof, chip_ordering } }` (crates/stark/src/types.rs:32-73,
+// 116-119).  bincode 1.x defaults: little endian, fixed-width integers, u64 for usize / lengths, arrays without a length prefix,
+// strings as u64 length + bytes, maps as u64 count + (key, value) pairs.  Plonky3 types inside (P3: restated from the published
+// v0.1.0 sources): Hash<F, W, 8> = [W; 8]; BinomialExtensionField = [F; 4]; FriProof { commit_phase_commits, query_proofs, final_poly,
+// pow_witness }; QueryProof { input_proof: Vec<BatchOpening { opened_values: Vec<Vec<F>>, opening_proof: Vec<[F; 8]> }>,
+// commit_phase_openings: Vec<CommitPhaseProofStep { sibling_value, opening_proof: Vec<[F; 8]> }> }.  A field element is one u32:
+// field_repr 1 writes the Montgomery word (p3-monty-31 serialises `self.value` "in monty form"), 0 the canonical residue.
+// `chip_ordering` is a hashbrown map whose iteration order is random per process in the reference: here it is
+// written in chip order, which makes the encoding canonical; the byte COUNT does not depend on the order.
+namespace verifier {
+struct ByteSink {
+    uint8_t* out;
+    uint64_t cap, len = 0;
+    void put(const void* p, size_t n) {
+        if (out && len + n <= cap) memcpy(out + len, p, n);
+        len += n;
+    }
+    void u64(uint64_t v) { put(&v, 8); }  // little-endian hosts only (x86-64 / aarch64 LE)
+    void u32(uint32_t v) { put(&v, 4); }
+};
+static std::string to_bincode(const std::vector<std::pair<int, unsigned>>& prep, const uint32_t* words, uint64_t n_words, bool monty, unsigned log_blowup,
+                              int field_repr, ByteSink& sink) {
+    Reader rd{words, n_words, 0, monty};
+    auto fe = [&](uint32_t mont) { sink.u32(field_repr == 1 ? mont : kb::from_mont(mont)); };
+    auto ext = [&](const Ext& e) { for (int k = 0; k < 4; k++) fe(e.c[k]); };
+    uint32_t commits[3][8];
+    for (auto& c : commits) rd.digest(c);
+    const uint32_t n = rd.raw();
+    if (!rd.ok || n == 0 || n > (uint32_t)air::NUM_CHIPS) return "ChipOpeningLengthMismatch";
+    struct ChipOpen { int chip; unsigned log_degree; Ext csum; };
+    std::vector<ChipOpen> chips(n);
+    std::map<int, size_t> where;
+    for (auto& c : chips) {
+        c.chip = (int)rd.raw();
+        c.log_degree = rd.raw();
+        c.csum = rd.ext();
+        if (!rd.ok || c.chip < 0 || c.chip >= air::NUM_CHIPS || c.log_degree > (unsigned)kb::TWO_ADICITY || where.count(c.chip)) return "InvalidProofShape";
+        where[c.chip] = &c - chips.data();
+    }
+    for (auto& pr : prep)
+        if (!where.count(pr.first)) return "InvalidProofShape: preprocessed chip missing from the proof";
+    // opened values in serialisation order: preprocessed (pk order), then main, permutation, quotient per chip
+    auto read_vals = [&](uint32_t width, bool both, std::vector<Ext>* local, std::vector<Ext>* next) {
+        local->resize(width);
+        for (auto& e : *local) e = rd.ext();
+        next->assign(width, kb::ext_zero());  // local-only chips: `next` is a vector of zeros of the same width (prover.rs:485-487)
+        if (both)
+            for (auto& e : *next) e = rd.ext();
+    };
+    std::vector<std::vector<Ext>> pl(n), pn(n), ml(n), mn(n), ql(n), qn(n);
+    std::vector<std::vector<std::vector<Ext>>> quot(n);
+    for (auto& pr : prep) {
+        size_t i = where[pr.first];
+        read_vals((uint32_t)air::CHIPS[pr.first].prep_w, !air::CHIPS[pr.first].local_only, &pl[i], &pn[i]);
+    }
+    for (size_t i = 0; i < n; i++) read_vals((uint32_t)air::CHIPS[chips[i].chip].main_w, !air::CHIPS[chips[i].chip].local_only, &ml[i], &mn[i]);
+    for (size_t i = 0; i < n; i++) read_vals(4u * (uint32_t)air::CHIPS[chips[i].chip].perm_w, true, &ql[i], &qn[i]);
+    for (size_t i = 0; i < n; i++)
+        for (int d = 0; d < (1 << air::CHIPS[chips[i].chip].log_quotient_degree); d++) {
+            std::vector<Ext> v(4);
+            for (auto& e : v) e = rd.ext();
+            quot[i].push_back(v);
+        }
+    if (!rd.ok) return "InvalidProofShape: truncated opened values";
+    // ---- MachineProof.shard_proof.commitment
+    for (auto& c : commits)
+        for (int k = 0; k < 8; k++) fe(c[k]);
+    // ---- opened_values: ShardOpenedValues { chips: Vec<ChipOpenedValues> }
+    auto vec_ext = [&](const std::vector<Ext>& v) {
+        sink.u64(v.size());
+        for (auto& e : v) ext(e);
+    };
+    sink.u64(n);
+    for (size_t i = 0; i < n; i++) {
+        vec_ext(pl[i]); vec_ext(pn[i]);   // preprocessed { local, next } (empty vectors for chips without a preprocessed trace)
+        vec_ext(ml[i]); vec_ext(mn[i]);   // main
+        vec_ext(ql[i]); vec_ext(qn[i]);   // permutation
+        sink.u64(quot[i].size());          // quotient: Vec<Vec<Challenge>>
+        for (auto& v : quot[i]) vec_ext(v);
+        ext(chips[i].csum);
+        sink.u64(chips[i].log_degree);
+    }
+    // ---- opening_proof: FriProof
+    const uint32_t n_commit = rd.raw();
+    if (!rd.ok || n_commit == 0 || n_commit > (unsigned)kb::TWO_ADICITY) return "InvalidProofShape";
+    sink.u64(n_commit);
+    for (uint32_t k = 0; k < n_commit; k++) {
+        uint32_t d[8];
+        rd.digest(d);
+        for (int j = 0; j < 8; j++) fe(d[j]);
+    }
+    const Ext final_poly = rd.ext();
+    const uint32_t pow_witness = rd.raw();  // canonical in the flat layout
+    const uint32_t nq = rd.raw();
+    if (!rd.ok || pow_witness >= kb::P) return "InvalidProofShape";
+    const unsigned log_max = n_commit + log_blowup;
+    // round shapes: [preprocessed (pk order), main, permutation, quotient]
+    struct Shape { std::vector<std::pair<unsigned, uint32_t>> mats; };  // (log LDE height, width)
+    Shape rounds[4];
+    for (auto& pr : prep) rounds[0].mats.push_back({pr.second + log_blowup, (uint32_t)air::CHIPS[pr.first].prep_w});
+    for (auto& c : chips) {
+        const auto& info = air::CHIPS[c.chip];
+        rounds[1].mats.push_back({c.log_degree + log_blowup, (uint32_t)info.main_w});
+        rounds[2].mats.push_back({c.log_degree + log_blowup, 4u * (uint32_t)info.perm_w});
+        for (int d = 0; d < (1 << info.log_quotient_degree); d++) rounds[3].mats.push_back({c.log_degree + log_blowup, 4u});
+    }
+    sink.u64(nq);
+    for (uint32_t q = 0; q < nq; q++) {
+        (void)rd.raw();  // the query index is not part of QueryProof: the verifier re-derives it from the transcript
+        sink.u64(4);      // input_proof: one BatchOpening per commitment round
+        for (auto& r : rounds) {
+            unsigned lmax = 0;
+            sink.u64(r.mats.size());
+            for (auto& m : r.mats) {
+                lmax = std::max(lmax, m.first);
+                sink.u64(m.second);
+                for (uint32_t c = 0; c < m.second; c++) fe(rd.fe());
+            }
+            if (lmax > log_max) return "InvalidProofShape: matrix taller than the FRI domain";
+            sink.u64(lmax);
+            for (unsigned l = 0; l < lmax; l++) {
+                uint32_t d[8];
+                rd.digest(d);
+                for (int j = 0; j < 8; j++) fe(d[j]);
+            }
+        }
+        sink.u64(n_commit);  // commit_phase_openings
+        for (uint32_t k = 0; k < n_commit; k++) {
+            ext(rd.ext());
+            const unsigned lfh = log_max - 1 - k;
+            sink.u64(lfh);
+            for (unsigned l = 0; l < lfh; l++) {
+                uint32_t d[8];
+                rd.digest(d);
+                for (int j = 0; j < 8; j++) fe(d[j]);
+            }
+        }
+        if (!rd.ok) return "InvalidProofShape: truncated query";
+    }
+    ext(final_poly);
+    fe(kb::to_mont(pow_witness));
+    if (rd.pos != rd.n) return "InvalidProofShape: trailing words";
+    // ---- chip_ordering: HashMap<String, usize>, written in chip order
+    sink.u64(n);
+    for (size_t i = 0; i < n; i++) {
+        const char* name = air::CHIPS[chips[i].chip].name;
+        sink.u64(strlen(name));
+        sink.put(name, strlen(name));
+        sink.u64(i);
+    }
+    return "";
+}
+}  // namespace verifier
+
+// out == NULL: only the length (the reference's `proofSize`).  Returns BFGPU_ERR_INVALID with a message in err for malformed input,
+// BFGPU_ERR_STATE when out_cap is too small (out_len still holds the needed size).
+extern "C" int32_t bfgpu_shard_proof_to_bincode(const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep, const uint32_t* proof,
+                                                uint64_t n_words, int repr, uint32_t log_blowup, int field_repr, uint8_t* out, uint64_t out_cap,
+                                                uint64_t* out_len, char* err, uint64_t err_len) {
+    auto say = [&](const std::string& s) {
+        if (err && err_len) snprintf(err, (size_t)err_len, "%s", s.c_str());
+    };
+    if (!proof || !out_len || n_prep < 0 || (n_prep && (!prep_names || !prep_log_heights))) {
+        say("null argument");
+        return BFGPU_ERR_INVALID;
+    }
+    std::vector<std::pair<int, unsigned>> prep;
+    for (int i = 0; i < n_prep; i++) {
+        int ci = chip_index(prep_names[i]);
+        if (ci < 0) {
+            say(std::string("unknown chip ") + prep_names[i]);
+            return BFGPU_ERR_INVALID;
+        }
+        prep.emplace_back(ci, prep_log_heights[i]);
+    }
+    verifier::ByteSink sink{out, out_cap};
+    std::string e = verifier::to_bincode(prep, proof, n_words, repr == BFGPU_REPR_MONTY, log_blowup, field_repr, sink);
+    say(e);
+    if (!e.empty()) return BFGPU_ERR_INVALID;
+    *out_len = sink.len;
+    return (out && sink.len > out_cap) ? BFGPU_ERR_STATE : BFGPU_OK;
+}
