@@ -278,6 +278,21 @@ uint64_t bfgpu_shard_proof_size(const bfgpu_shard_proof* p);
 int32_t bfgpu_shard_proof_read(const bfgpu_shard_proof* p, uint32_t* out);
 void bfgpu_shard_proof_free(bfgpu_shard_proof* p);
 
+/* ---- plug point #2: the steps of CpuProver::open for an integration at the Plonky3 trait level ------------------------- */
+/* Pcs::get_evaluations_on_domain (prover.rs:365-373) as a device view: pointer and layout of the committed LDE (column-major,
+ * col_stride words between columns, rows bit-reversed, Montgomery words) — the LDE never leaves HBM. */
+int32_t bfgpu_pcs_lde_device(const bfgpu_pcs_data* data, int32_t idx, const uint32_t** dev, uint64_t* rows, uint64_t* cols, uint64_t* col_stride);
+/* Chip::generate_permutation_trace (chip.rs:117-136 -> permutation.rs:75-148) of one chip: perm_out = rows x 4*perm_ext_width words,
+ * row-major, natural row order (the flattened matrix prover.rs:318-328 commits); challenges = LogUp alpha then beta (4 words each);
+ * prep may be NULL for chips without a preprocessed trace. */
+int32_t bfgpu_logup_perm_trace(bfgpu_ctx* ctx, const char* chip, const bfgpu_mat* main, const bfgpu_mat* prep, const uint32_t challenges[8],
+                               uint32_t* perm_out, uint32_t cum_sum[4]);
+/* quotient_values (quotient.rs:18-165) of one chip, read from the committed (device-resident) LDEs: out = 2 * trace_rows extension
+ * elements (4 words each) over the quotient domain in natural order.  prep_data may be NULL (prep_idx -1). */
+int32_t bfgpu_quotient_values(bfgpu_ctx* ctx, const char* chip, const bfgpu_pcs_data* prep_data, int32_t prep_idx, const bfgpu_pcs_data* main_data,
+                              int32_t main_idx, const bfgpu_pcs_data* perm_data, int32_t perm_idx, const uint32_t alpha[4],
+                              const uint32_t perm_challenges[8], const uint32_t cum_sum[4], uint32_t* out);
+
 /* ---- executor + device-side trace generation -------------------------------------- */
 /* `Program::from` + `Executor::run` (crates/core/executor/src/program.rs:22-44, executor.rs:71-79,106-325) as one
  * native pass that emits a 16-byte record per cycle; the eight `MachineAir::generate_trace` implementations and

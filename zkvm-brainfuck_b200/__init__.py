@@ -75,6 +75,10 @@ ABI = {
     "bfgpu_pcs_get_evaluations": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int, C.c_void_p]),
     "bfgpu_pcs_tree": (C.c_void_p, [C.c_void_p]),
     "bfgpu_pcs_data_free": (None, [C.c_void_p]),
+    "bfgpu_pcs_lde_device": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), _u64p, _u64p, _u64p]),
+    "bfgpu_logup_perm_trace": (C.c_int32, [C.c_void_p, C.c_char_p, C.POINTER(Mat), C.POINTER(Mat), _u32p, C.c_void_p, _u32p]),
+    "bfgpu_quotient_values": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, _u32p, _u32p, _u32p,
+                                           C.c_void_p]),
     "bfgpu_execute": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bfgpu_record_error": (C.c_char_p, [C.c_void_p]),
     "bfgpu_record_info": (C.c_int32, [C.c_void_p, _u64p]),
@@ -540,6 +544,35 @@ class TwoAdicFriPcs:
         out = np.zeros((r, c), np.uint32)
         self.ctx.check(lib().bfgpu_pcs_get_evaluations(data._h, idx, 1 if bit_reversed_rows else 0, _ptr(out)))
         return out
+
+
+def generate_permutation_trace(ctx, chip, main, prep, alpha, beta):
+    """`Chip::generate_permutation_trace` (chip.rs:117-136): -> (LogUp trace (rows, 4 * perm_width) uint32, cumulative sum (4,))."""
+    info = {c[0]: c for c in machine_chips()}[chip]
+    m = _u32(main)
+    cm = Mat(m.ctypes.data, m.shape[0], m.shape[1])
+    pm = None
+    if prep is not None and np.size(prep):
+        pa = _u32(prep)
+        pm = Mat(pa.ctypes.data, pa.shape[0], pa.shape[1])
+    ch = _u32(np.concatenate([np.asarray(alpha, np.uint64), np.asarray(beta, np.uint64)]))
+    out = np.zeros((m.shape[0], 4 * info[3]), np.uint32)
+    cs = np.zeros(4, np.uint32)
+    ctx.check(lib().bfgpu_logup_perm_trace(ctx._h, chip.encode(), C.byref(cm), C.byref(pm) if pm is not None else None, ch.ctypes.data_as(_u32p),
+                                           _ptr(out), cs.ctypes.data_as(_u32p)))
+    return out, cs
+
+
+def quotient_values(ctx, chip, prep_data, prep_idx, main_data, main_idx, perm_data, perm_idx, alpha, perm_challenges, cum_sum):
+    """`quotient_values` (quotient.rs:18-165) from committed `PcsProverData` handles -> (2 * rows, 4) uint32, natural order."""
+    rows = main_data.dims[main_idx][0]
+    out = np.zeros((rows, 4), np.uint32)
+    a = _u32(np.asarray(alpha, np.uint64))
+    pc = _u32(np.concatenate([np.asarray(x, np.uint64) for x in perm_challenges]))
+    cs = _u32(np.asarray(cum_sum, np.uint64))
+    ctx.check(lib().bfgpu_quotient_values(ctx._h, chip.encode(), prep_data._h if prep_data is not None else None, prep_idx, main_data._h, main_idx,
+                                          perm_data._h, perm_idx, a.ctypes.data_as(_u32p), pc.ctypes.data_as(_u32p), cs.ctypes.data_as(_u32p), _ptr(out)))
+    return out
 
 
 def machine_chips():

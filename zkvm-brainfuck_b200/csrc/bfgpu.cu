@@ -2480,6 +2480,166 @@ extern "C" int32_t bfgpu_machine_chip_info(int32_t i, const char** name, int32_t
     return BFGPU_OK;
 }
 
+// ---- plug point #2: the pieces of CpuProver::open a Plonky3-trait-level integration calls one by one -------------
+// Pcs::get_evaluations_on_domain as a DEVICE VIEW (prover.rs:365-373): the committed LDE stays in HBM; the caller gets the pointer
+// and the layout (column-major, `col_stride` words between columns, rows in bit-reversed order, Montgomery words).
+extern "C" int32_t bfgpu_pcs_lde_device(const bfgpu_pcs_data* d, int32_t idx, const uint32_t** dev, uint64_t* rows, uint64_t* cols, uint64_t* col_stride) {
+    if (!d || idx < 0 || (size_t)idx >= d->ldes.size() || !dev) return BFGPU_ERR_INVALID;
+    const DMat& m = d->ldes[idx];
+    *dev = m.d;
+    if (rows) *rows = m.rows;
+    if (cols) *cols = m.cols;
+    if (col_stride) *col_stride = m.col_stride();
+    return BFGPU_OK;
+}
+
+// Chip::generate_permutation_trace (chip.rs:117-136 -> permutation.rs:75-148) for ONE chip: main (and preprocessed) trace in, the
+// LogUp trace (rows x 4*perm_width base columns, row-major, natural rows: the flattened form prover.rs:318-328 commits) and the
+// cumulative sum out.  challenges = alpha (4 words) then beta (4 words).
+static int32_t logup_perm_trace_impl(bfgpu_ctx* ctx, const char* chip, const bfgpu_mat* main, const bfgpu_mat* prep, const uint32_t challenges[8],
+                                     uint32_t* perm_out, uint32_t cum_sum[4]);
+extern "C" int32_t bfgpu_logup_perm_trace(bfgpu_ctx* ctx, const char* chip, const bfgpu_mat* main, const bfgpu_mat* prep, const uint32_t challenges[8],
+                                          uint32_t* perm_out, uint32_t cum_sum[4]) {
+    AllocScope scope(ctx);
+    return scope.ok(logup_perm_trace_impl(ctx, chip, main, prep, challenges, perm_out, cum_sum));
+}
+static int32_t logup_perm_trace_impl(bfgpu_ctx* ctx, const char* chip, const bfgpu_mat* main, const bfgpu_mat* prep, const uint32_t challenges[8],
+                                     uint32_t* perm_out, uint32_t cum_sum[4]) {
+    if (!ctx || !chip || !main || !challenges || !perm_out || !cum_sum) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    const int ci = chip_index(chip);
+    if (ci < 0) return fail(ctx, BFGPU_ERR_INVALID, "unknown chip '%s'", chip);
+    const air::ChipInfo& info = air::CHIPS[ci];
+    TRY(check_mat(ctx, main, true));
+    if (main->cols != (uint64_t)info.main_w) return fail(ctx, BFGPU_ERR_INVALID, "chip %s: main trace width %llu, expected %d", chip, (unsigned long long)main->cols, info.main_w);
+    if (info.prep_w) {
+        if (!prep) return fail(ctx, BFGPU_ERR_INVALID, "chip %s needs its preprocessed trace", chip);
+        TRY(check_mat(ctx, prep, true));
+        if (prep->cols != (uint64_t)info.prep_w || prep->rows != main->rows) return fail(ctx, BFGPU_ERR_INVALID, "chip %s: bad preprocessed trace shape", chip);
+    }
+    if (info.perm_w == 0) return fail(ctx, BFGPU_ERR_INVALID, "chip %s has no lookups", chip);
+    Scratch sc(ctx);
+    bfgpu_pk tmp;  // carrier for perm_traces(): just the preprocessed trace
+    tmp.ctx = ctx;
+    std::vector<DMat> mains(1), perm(1);
+    TRY(ingest(ctx, *main, /*bitrev=*/true, &mains[0]));
+    sc.bufs.push_back(mains[0].d);
+    std::vector<int> pk_idx(1, -1);
+    if (info.prep_w) {
+        DMat p;
+        TRY(ingest(ctx, *prep, /*bitrev=*/true, &p));
+        sc.bufs.push_back(p.d);
+        tmp.traces.push_back(p);
+        pk_idx[0] = 0;
+    }
+    air::Challenges chal;
+    for (int k = 0; k < 4; k++) chal.alpha.c[k] = in_word(ctx, challenges[k]);
+    kb::Ext beta;
+    for (int k = 0; k < 4; k++) beta.c[k] = in_word(ctx, challenges[4 + k]);
+    chal.beta_pow[0] = kb::ext_one();
+    for (int k = 1; k < 8; k++) chal.beta_pow[k] = kb::ext_mul(chal.beta_pow[k - 1], beta);
+    chal.cumulative_sum = kb::ext_zero();
+    uint32_t* d_csum = nullptr;
+    TRY(sc.alloc((void**)&d_csum, 16));
+    TRY(perm_traces(ctx, &tmp, pk_idx, {ci}, mains, chal, &perm, d_csum));
+    sc.bufs.push_back(perm[0].d);
+    uint32_t cs[4];
+    CU(cudaMemcpyAsync(cs, d_csum, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(egress(ctx, perm[0], /*bitrev=*/true, perm_out));  // synchronises
+    for (int k = 0; k < 4; k++) cum_sum[k] = out_word(ctx, cs[k]);
+    return BFGPU_OK;
+}
+
+// quotient_values (quotient.rs:18-165) for ONE chip from the COMMITTED LDEs (device resident: nothing is copied back to evaluate):
+// out = 2^(log_n + 1) extension elements (4 words each), the quotient values over the quotient domain in NATURAL order, exactly the
+// Vec<Challenge> the reference then flattens and splits (prover.rs:391-402).  prep_data / prep_idx: -1 / NULL for chips without a
+// preprocessed trace.  alpha: constraint-folding challenge; perm_challenges: LogUp alpha, beta; cum_sum: the chip's cumulative sum.
+static int32_t quotient_values_impl(bfgpu_ctx* ctx, const char* chip, const bfgpu_pcs_data* prep_data, int32_t prep_idx, const bfgpu_pcs_data* main_data,
+                                    int32_t main_idx, const bfgpu_pcs_data* perm_data, int32_t perm_idx, const uint32_t alpha_in[4],
+                                    const uint32_t perm_challenges[8], const uint32_t cum_sum[4], uint32_t* out);
+extern "C" int32_t bfgpu_quotient_values(bfgpu_ctx* ctx, const char* chip, const bfgpu_pcs_data* prep_data, int32_t prep_idx, const bfgpu_pcs_data* main_data,
+                                         int32_t main_idx, const bfgpu_pcs_data* perm_data, int32_t perm_idx, const uint32_t alpha_in[4],
+                                         const uint32_t perm_challenges[8], const uint32_t cum_sum[4], uint32_t* out) {
+    AllocScope scope(ctx);
+    return scope.ok(quotient_values_impl(ctx, chip, prep_data, prep_idx, main_data, main_idx, perm_data, perm_idx, alpha_in, perm_challenges, cum_sum, out));
+}
+static int32_t quotient_values_impl(bfgpu_ctx* ctx, const char* chip, const bfgpu_pcs_data* prep_data, int32_t prep_idx, const bfgpu_pcs_data* main_data,
+                                    int32_t main_idx, const bfgpu_pcs_data* perm_data, int32_t perm_idx, const uint32_t alpha_in[4],
+                                    const uint32_t perm_challenges[8], const uint32_t cum_sum[4], uint32_t* out) {
+    if (!ctx || !chip || !main_data || !perm_data || !alpha_in || !perm_challenges || !cum_sum || !out) return fail(ctx, BFGPU_ERR_INVALID, "null argument");
+    const int ci = chip_index(chip);
+    if (ci < 0) return fail(ctx, BFGPU_ERR_INVALID, "unknown chip '%s'", chip);
+    const air::ChipInfo& info = air::CHIPS[ci];
+    if (ctx->log_blowup != 1 || info.log_quotient_degree != 1) return fail(ctx, BFGPU_ERR_INVALID, "quotient degree / blow-up other than 2 is not supported");
+    if (main_idx < 0 || (size_t)main_idx >= main_data->ldes.size() || perm_idx < 0 || (size_t)perm_idx >= perm_data->ldes.size())
+        return fail(ctx, BFGPU_ERR_INVALID, "bad matrix index");
+    const DMat& lm = main_data->ldes[main_idx];
+    const DMat& lp = perm_data->ldes[perm_idx];
+    if (lm.cols != (uint32_t)info.main_w || lp.cols != 4u * (uint32_t)info.perm_w || lp.rows != lm.rows)
+        return fail(ctx, BFGPU_ERR_INVALID, "chip %s: committed matrices have the wrong shape", chip);
+    const uint32_t* prep = nullptr;
+    if (info.prep_w) {
+        if (!prep_data || prep_idx < 0 || (size_t)prep_idx >= prep_data->ldes.size()) return fail(ctx, BFGPU_ERR_INVALID, "chip %s needs its preprocessed commitment", chip);
+        const DMat& lq = prep_data->ldes[prep_idx];
+        if (lq.cols != (uint32_t)info.prep_w || lq.rows != lm.rows) return fail(ctx, BFGPU_ERR_INVALID, "chip %s: preprocessed LDE has the wrong shape", chip);
+        prep = lq.d;
+    }
+    const uint64_t N = lm.rows, n = N / 2;
+    const unsigned log_n = ilog2(n);
+    const uint32_t gen = kb::to_mont(kb::GEN);
+    kb::Ext alpha;
+    for (int k = 0; k < 4; k++) alpha.c[k] = in_word(ctx, alpha_in[k]);
+    air::Challenges chal;
+    for (int k = 0; k < 4; k++) chal.alpha.c[k] = in_word(ctx, perm_challenges[k]);
+    kb::Ext beta;
+    for (int k = 0; k < 4; k++) beta.c[k] = in_word(ctx, perm_challenges[4 + k]);
+    chal.beta_pow[0] = kb::ext_one();
+    for (int k = 1; k < 8; k++) chal.beta_pow[k] = kb::ext_mul(chal.beta_pow[k - 1], beta);
+    for (int k = 0; k < 4; k++) chal.cumulative_sum.c[k] = in_word(ctx, cum_sum[k]);
+    Phase ph(ctx, BFGPU_PHASE_QUOTIENT);
+    Scratch sc(ctx);
+    std::vector<kb::Ext> apow(air::MAX_CONSTRAINTS);
+    apow[0] = kb::ext_one();
+    for (int k = 1; k < air::MAX_CONSTRAINTS; k++) apow[k] = kb::ext_mul(apow[k - 1], alpha);
+    kb::Ext* d_apow = nullptr;
+    uint32_t* q = nullptr;
+    TRY(sc.alloc((void**)&d_apow, apow.size() * sizeof(kb::Ext)));
+    TRY(sc.alloc((void**)&q, N * 16));
+    TRY(upload_small(ctx, d_apow, apow.data(), apow.size() * sizeof(kb::Ext)));
+    air::QuotientArgs qa;
+    qa.chip = ci;
+    qa.main = lm.d;
+    qa.prep = prep;
+    qa.perm = lp.d;
+    qa.log_n = log_n;
+    qa.lqd = 1;
+    qa.shift = gen;
+    qa.g_inv = kb::inv(kb::two_adic_generator(log_n));
+    uint32_t sn = kb::pow(gen, n);
+    qa.zh[0] = kb::sub(sn, kb::ONE);
+    qa.zh[1] = kb::sub(kb::neg(sn), kb::ONE);
+    qa.zh_inv[0] = kb::inv(qa.zh[0]);
+    qa.zh_inv[1] = kb::inv(qa.zh[1]);
+    qa.apow = d_apow;
+    qa.tw = ctx->d_tw;
+    qa.out = q;
+#define BF_QUOT_CASE(C) \
+    case C: air::k_quotient<C><<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(qa, chal); break;
+    switch (ci) { BF_QUOT_CASE(0) BF_QUOT_CASE(1) BF_QUOT_CASE(2) BF_QUOT_CASE(3) BF_QUOT_CASE(4) BF_QUOT_CASE(5) BF_QUOT_CASE(6) BF_QUOT_CASE(7) }
+#undef BF_QUOT_CASE
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    // the kernel leaves the two chunk matrices (chunk c = natural index mod 2, column-major, rows bit-reversed): put the values back in
+    // natural order of the quotient domain for the caller
+    std::vector<uint32_t> h(N * 4);
+    CU(cudaMemcpyAsync(h.data(), q, N * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < N; i++) {
+        const uint64_t c = i & 1, pos = kb::bitrev((uint32_t)(i >> 1), log_n);
+        for (int k = 0; k < 4; k++) out[4 * i + k] = out_word(ctx, h[(c * 4 + (uint64_t)k) * n + pos]);
+    }
+    return BFGPU_OK;
+}
+
 // =====================================================================================================
 // one commitment over several GPUs
 // =====================================================================================================
