@@ -548,7 +548,7 @@ class TwoAdicFriPcs:
 
 def generate_permutation_trace(ctx, chip, main, prep, alpha, beta):
     """`Chip::generate_permutation_trace` (chip.rs:117-136): -> (LogUp trace (rows, 4 * perm_width) uint32, cumulative sum (4,))."""
-    info = {c[0]: c for c in machine_chips()}[chip]
+    info = {c[0]: c for c in machine_chips()}.get(chip, (chip, 0, 0, 1, False))  # unknown names are reported by the library
     m = _u32(main)
     cm = Mat(m.ctypes.data, m.shape[0], m.shape[1])
     pm = None
