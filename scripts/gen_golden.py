@@ -34,6 +34,13 @@ def seeded(seed, rows, cols):
 
 
 def main():
+    if len(sys.argv) == 3 and sys.argv[1] == "--inputs-only":
+        # the seeded input matrices of the LDE / commitment vectors, for integration/dump_vectors.rs (numpy's generator is not
+        # reproducible from Rust): BFGPU_GOLDEN_INPUTS=<this file> cargo test ...
+        json.dump({"seed1_64x3": seeded(1, 64, 3).tolist(), "seed2_1024x31": seeded(2, 1 << 10, 31).tolist(), "seed3_1024x2": seeded(3, 1 << 10, 2).tolist(),
+                   "seed4_64x7": seeded(4, 1 << 6, 7).tolist(), "seed5_16x5": seeded(5, 16, 5).tolist()}, open(sys.argv[2], "w"))
+        print("wrote", sys.argv[2])
+        return
     v = {}
     v["poseidon2_permute_0_to_15"] = oracle.permute(np.arange(16, dtype=np.uint32)).tolist()
     v["sponge_hash_0_to_30"] = oracle.sponge_hash(np.arange(31, dtype=np.uint32)).tolist()

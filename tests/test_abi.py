@@ -52,3 +52,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """integration/bf-gpu-sys/src/lib.rs is generated from include/bfgpu.h (scripts/gen_rust_sys.py): the committed file must be what
+    the generator emits today, and it must declare every symbol the library exports."""
+    import importlib.util
+    import re
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "scripts", "gen_rust_sys.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    src, names = g.render()
+    assert open(g.OUT).read() == src, "run `python scripts/gen_rust_sys.py`"
+    declared = set(re.findall(r"pub fn (bfgpu_[a-z_0-9]+)\(", src))
+    assert declared == set(bf.ABI), (declared ^ set(bf.ABI))
