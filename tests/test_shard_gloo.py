@@ -62,3 +62,47 @@ def test_two_rank_gather_and_max():
     assert sorted(flat) == [0, 1, 2, 3, 4]
     for rank, grp in enumerate(g0):
         assert all(owner0[row[0] // 8] == rank for row in grp)
+
+
+# ---- control plane of the sharded prover: the bfgpu_comm callbacks the C library calls (all-gather of host bytes, barrier) ----------
+def _comm_worker(rank, world, port, q):
+    import ctypes as C
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dp = shard.DistributedProver(None, dist)  # no device context needed for the callbacks themselves
+        ag, br = dp._comm.all_gather, dp._comm.barrier
+        out = []
+        for nbytes in (32, 64, 5 * 64, 4096 + 12):
+            send = (C.c_uint8 * nbytes)(*[(rank * 37 + i) % 251 for i in range(nbytes)])
+            recv = (C.c_uint8 * (nbytes * world))()
+            rc = ag(None, C.cast(send, C.c_void_p), C.cast(recv, C.c_void_p), nbytes)
+            out.append((rc, bytes(recv)))
+            assert br(None) == 0
+        q.put((rank, None, out, dict(dp.calls)))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:
+        import traceback
+        q.put((rank, traceback.format_exc() + repr(e), None, None))
+
+
+def test_sharded_prover_control_plane_callbacks_world2():
+    """what csrc/dist_prove.cuh relies on: recv = the ranks' byte strings in rank order, identical on every rank; barrier returns 0"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_comm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err, out, calls in res:
+        assert err is None, err
+        assert calls["all_gather"] == 4 and calls["barrier"] == 4
+        for (rc, blob), nbytes in zip(out, (32, 64, 5 * 64, 4096 + 12)):
+            assert rc == 0
+            want = b"".join(bytes((r * 37 + i) % 251 for i in range(nbytes)) for r in range(world))
+            assert blob == want
