@@ -548,7 +548,8 @@ def main():
             barrier()
             sharded_prove[name] = {"cycles": rec.cycles, "proof_words": int(words.size), "prove_ms": min(times), "prove_ms_median": statistics.median(times),
                                    "program_to_proof_ms": min(ptimes), "trace_rows_per_s": float(1 << (20 if "2^20" in name else 22)) / (min(times) * 1e-3),
-                                   "control_plane_calls_per_proof": calls, "phases_ms_rank0": ph, **(single or {})}
+                                   "control_plane": dp.control_plane, "control_plane_calls_per_proof": calls if dp.control_plane == "dist" else None,
+                                   "phases_ms_rank0": ph, **(single or {})}
             pk.free()
             rec.free()
         ctx.set_input_space(bf.MEM_DEVICE)

@@ -336,6 +336,11 @@ typedef struct {
     int32_t (*all_gather)(void* user, const void* send, void* recv, uint64_t bytes_per_rank);
     int32_t (*barrier)(void* user);
 } bfgpu_comm;
+/* A ready-made control plane for one process per GPU on ONE node: bfgpu_comm served from a POSIX shared-memory segment (two atomics
+ * and a slot per rank: ~2-5 us per call instead of 150-300 us through a Python / TCP collective).  Every rank calls with the same
+ * job-unique name (e.g. "/bfgpu-<port>-<pid of rank 0>"); returns once all ranks are attached (the name is unlinked then). */
+int32_t bfgpu_comm_shm_create(const char* name, uint32_t rank, uint32_t world, uint64_t slot_bytes, bfgpu_comm** out);
+void bfgpu_comm_shm_destroy(bfgpu_comm* comm);
 int32_t bfgpu_dist_prove_record(bfgpu_ctx* ctx, const bfgpu_comm* comm, uint32_t rank, uint32_t world, const bfgpu_pk* pk, const bfgpu_record* rec,
                                 bfgpu_challenger* ch, int64_t fixed_pow_witness, bfgpu_shard_proof** out);
 int32_t bfgpu_dist_prove(bfgpu_ctx* ctx, const bfgpu_comm* comm, uint32_t rank, uint32_t world, const bfgpu_pk* pk, const char* const* names,

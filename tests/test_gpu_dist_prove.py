@@ -29,7 +29,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, fri, from_traces, q, gather_log=None):
+def _worker(rank, world, port, case, fri, from_traces, q, gather_log=None, control_plane="shm"):
     try:
         if gather_log is not None:  # force sharded FRI rounds on small proofs
             os.environ["BFGPU_DIST_FRI_GATHER_LOG"] = str(gather_log)
@@ -43,7 +43,7 @@ def _worker(rank, world, port, case, fri, from_traces, q, gather_log=None):
         ctx.set_fri_params(*fri)
         code, stdin = PROGRAMS[case]
         prover = bf.CudaProver(ctx)
-        dp = shard.DistributedProver(ctx, dist)
+        dp = shard.DistributedProver(ctx, dist, control_plane=control_plane)
         rec = prover.execute(code, stdin)
         pk = prover.setup_record(rec)
         out = []
@@ -80,11 +80,11 @@ def _worker(rank, world, port, case, fri, from_traces, q, gather_log=None):
         q.put((rank, traceback.format_exc() + repr(e), None))
 
 
-def _run(world, case, fri=(1, 12, 6), from_traces=False, gather_log=None):
+def _run(world, case, fri=(1, 12, 6), from_traces=False, gather_log=None, control_plane="shm"):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, fri, from_traces, q, gather_log)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, fri, from_traces, q, gather_log, control_plane)) for r in range(world)]
     for p in procs:
         p.start()
     res = []
@@ -124,3 +124,11 @@ def test_sharded_proof_full_parameters_from_host_traces():
     """84 queries / 16 PoW bits (kb31_poseidon2.rs:54-64), traces handed in from the host on every rank"""
     for rank, _, r in _run(2, "fibo", fri=(1, 84, 16), from_traces=True):
         assert all(r["same"]) and r["verdict"] is None, (rank, r)
+
+
+def test_sharded_proof_through_caller_supplied_callbacks():
+    """control plane through the caller's own bfgpu_comm (torch.distributed / gloo callbacks: what a multi-node caller supplies) instead
+    of the library's shared-memory communicator"""
+    for rank, _, r in _run(4, "tiny", gather_log=6, control_plane="dist"):
+        assert all(r["same"]) and r["verdict"] is None, (rank, r)
+        assert r["calls"]["all_gather"] >= 10 and r["calls"]["barrier"] >= 6

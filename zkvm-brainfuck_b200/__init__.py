@@ -111,6 +111,8 @@ ABI = {
     "bfgpu_dist_commit_open_batch": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "bfgpu_dist_commit_rows_per_rank": (C.c_uint64, [C.c_void_p]),
     "bfgpu_dist_commit_free": (None, [C.c_void_p]),
+    "bfgpu_comm_shm_create": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "bfgpu_comm_shm_destroy": (None, [C.c_void_p]),
     "bfgpu_dist_prove_record": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
     "bfgpu_dist_prove": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(Mat), C.c_int32, C.c_void_p,
                                      C.c_int64, C.POINTER(C.c_void_p)]),

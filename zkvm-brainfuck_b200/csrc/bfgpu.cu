@@ -2654,6 +2654,7 @@ static int32_t quotient_values_impl(bfgpu_ctx* ctx, const char* chip, const bfgp
 // one shard proof over several GPUs
 // =====================================================================================================
 #include "dist_prove.cuh"
+#include "comm_shm.h"
 
 // =====================================================================================================
 // native verifier (host only)

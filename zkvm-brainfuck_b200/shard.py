@@ -199,11 +199,15 @@ class DistributedProver:
     serialised proof, word for word the single-GPU one.  The library's control plane (bfgpu_comm: all-gather of small host
     buffers + barrier) is served by a gloo group created next to the caller's group."""
 
-    def __init__(self, ctx, dist, group=None):
+    def __init__(self, ctx, dist, group=None, control_plane="shm"):
+        """control_plane: "shm" = the library's shared-memory communicator (one node; the name is agreed on through `dist` once),
+        "dist" = every call through torch.distributed (gloo) callbacks — works across nodes, ~100x the latency per call."""
         import ctypes as C
         from . import lib
         self._C, self._lib, self.ctx, self.dist = C, lib(), ctx, dist
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._shm = None
+        self.control_plane = control_plane
         backend = str(dist.get_backend(group))
         # host-side exchanges: gloo.  (new_group is collective: every rank of the default group constructs its DistributedProver)
         self._cpu_group = group if "gloo" in backend and "nccl" not in backend else dist.new_group(backend="gloo")
@@ -241,6 +245,28 @@ class DistributedProver:
 
         self._cb = (AG(all_gather), BR(barrier))  # keep the thunks alive
         self._comm = Comm(None, self._cb[0], self._cb[1])
+        self._comm_ptr = C.cast(C.pointer(self._comm), C.c_void_p)
+        if control_plane == "shm":
+            import os
+            tag = os.urandom(6).hex() if self.rank == 0 else ""
+            name = _all_gather_bytes(tag.ljust(12).encode(), dist, self._cpu_group)[0].decode().strip()
+            h = C.c_void_p()
+            rc = self._lib.bfgpu_comm_shm_create(f"/bfgpu-{name}".encode(), self.rank, self.world, 1 << 20, C.byref(h))
+            if rc != 0:
+                raise RuntimeError(f"bfgpu_comm_shm_create failed ({rc})")
+            self._shm = h
+            self._comm_ptr = h
+
+    def close(self):
+        if self._shm is not None:
+            self._lib.bfgpu_comm_shm_destroy(self._shm)
+            self._shm = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
 
     def _finish(self, h):
         C, L = self._C, self._lib
@@ -254,7 +280,7 @@ class DistributedProver:
         """proof words from an execution record (`bf.Record`): device-side trace generation replicated, the rest sharded"""
         C = self._C
         h = C.c_void_p()
-        self.ctx.check(self._lib.bfgpu_dist_prove_record(self.ctx._h, C.byref(self._comm), self.rank, self.world, pk._h, rec._h, challenger._h,
+        self.ctx.check(self._lib.bfgpu_dist_prove_record(self.ctx._h, self._comm_ptr, self.rank, self.world, pk._h, rec._h, challenger._h,
                                                           -1 if pow_witness is None else int(pow_witness), C.byref(h)))
         return self._finish(h)
 
@@ -265,6 +291,6 @@ class DistributedProver:
         named = list(traces.items())
         cn, arr, keep = _named_mats(named)
         h = C.c_void_p()
-        self.ctx.check(self._lib.bfgpu_dist_prove(self.ctx._h, C.byref(self._comm), self.rank, self.world, pk._h, cn, arr, len(named), challenger._h,
+        self.ctx.check(self._lib.bfgpu_dist_prove(self.ctx._h, self._comm_ptr, self.rank, self.world, pk._h, cn, arr, len(named), challenger._h,
                                                    -1 if pow_witness is None else int(pow_witness), C.byref(h)))
         return self._finish(h)
