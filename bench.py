@@ -383,8 +383,10 @@ def main():
             ctx.check(lib.bfgpu_pcs_commit(ctx._h, C.byref(mat), None, 1, root_p, C.byref(h)))
             lib.bfgpu_pcs_data_free(h)
     else:
+        shm = shard.ShmComm(dist)  # handles / barrier / caps of every commitment through shared memory instead of NCCL collectives
+
         def commit_once(src=None):
-            dc = shard.DistributedCommit(ctx, dist, [R], [W], exchange="p2p")
+            dc = shard.DistributedCommit(ctx, dist, [R], [W], exchange="p2p", comm=shm)
             root[:] = dc.commit([src if src is not None else (trace.data_ptr(), R, nloc)])
             dc.free()
 

@@ -249,7 +249,7 @@ static int32_t dist_lde_coefs(bfgpu_dist_commit* dc, const std::vector<DMat>& co
             break;
         }
         // at least ~4 blocks per matrix so that only the last quarter of the exchange is exposed (16..64 columns each)
-        const uint32_t chunk = std::min(DIST_CHUNK_COLS, std::max(16u, ((m.ncols + 3) / 4 + 7) / 8 * 8));
+        const uint32_t chunk = std::min(DIST_CHUNK_COLS, std::max(ctx->dist_min_chunk, ((m.ncols + 3) / 4 + 7) / 8 * 8));
         for (uint32_t c = 0; c < m.ncols && rc == BFGPU_OK; c += chunk) {
             uint32_t nc = std::min(chunk, m.ncols - c);
             if ((rc = retire(1)) != BFGPU_OK) break;  // at most two LDE blocks alive: one in the NTT, one being scattered
