@@ -172,7 +172,9 @@ def prove_timings(ctx, bf, with_cpu):
         best = min(times[1:])
         entry = {"cycles": rec.cycles, "cpu_rows": int(traces["Cpu"].shape[0]), "committed_main_cells": int(sum(v.size for v in traces.values())),
                  "prove_ms": best, "trace_rows_per_s": float(traces["Cpu"].shape[0]) / (best * 1e-3), "khz": rec.cycles / best,
-                 "main_root": [int(x) for x in proof["commitment"]["main"]]}
+                 "main_root": [int(x) for x in proof["commitment"]["main"]],
+                 # the reference's `proofSize` (utils/prove.rs:47-56): bytes of bincode::serialize(&MachineProof)
+                 "proof_size_bytes": len(bf.proof_to_bincode(pk.names, pk.heights, buf)), "proof_words": int(buf.size)}
         # ProverClient::prove end to end on this backend: native executor -> 16 B/cycle records -> device-side trace
         # generation -> commit -> open (setup excluded, as in the reference where the pk is an input of prove)
         ptimes, etimes = [], []

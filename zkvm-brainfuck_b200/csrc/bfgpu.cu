@@ -103,7 +103,7 @@ struct bfgpu_ctx {
     std::vector<std::vector<void*>*> scopes;
     // transcript options (bfgpu_set_transcript_option): the choices inside Plonky3 that cannot be confirmed offline (SURVEY.md P3 marks)
     uint32_t opt[BFGPU_NUM_OPTS] = {1, 0, 0};
-    uint32_t dist_min_chunk = 16;  // dist_commit.cuh: smallest LDE / scatter block in columns ($BFGPU_DIST_MIN_CHUNK)
+    uint32_t dist_min_chunk = 32;  // dist_commit.cuh: smallest LDE / scatter block in columns ($BFGPU_DIST_MIN_CHUNK)
     unsigned dist_fri_gather_log = 20;  // dist_prove.cuh: global FRI length below which the sharded prover gathers ($BFGPU_DIST_FRI_GATHER_LOG)
     // test hook (bfgpu_debug_fail_alloc): the n-th dalloc from now fails with BFGPU_ERR_OOM
     int64_t fail_alloc_in = -1;
