@@ -183,8 +183,13 @@ __device__ __forceinline__ uint32_t tile_idx(uint32_t d, uint32_t l) {
 
 // G1 in 0..4 (g = G1 + 4).  Threads per CTA = 2^g.  CONTIG: p == 0 (lanes = 16 consecutive runs of 2^g words).
 // EPI: the fused coset epilogue (separate instantiation: keeps its registers out of the plain passes)
-template <bool INV, int G1, bool CONTIG, bool EPI = false>
+// DUAL (forward, strided, G1 > 0): the FIRST forward pass of a blow-up-2 LDE reads each coefficient tile ONCE and produces both
+// cosets from it: v = x * pw_h on load (pw_h[k] = shift_h^k / n), transform, store into half-column h of the output — the coset
+// scaling needs no pass of its own and no second read of the coefficients (round 2: replaces the EPI epilogue of the last inverse
+// pass, which wrote 2n words per column that this pass then read back; -9 GB of 90 at 2^22 x 256).
+template <bool INV, int G1, bool CONTIG, bool EPI = false, bool DUAL = false>
 __global__ void __launch_bounds__(256, EPI ? 1 : NTT2_MINBLOCKS) k_pass(PassArgs A) {
+    static_assert(!DUAL || (!INV && !CONTIG && !EPI && G1 > 0), "DUAL is the strided forward pass with two register phases");
     constexpr int g = G1 + G2, NT = 1 << g;
     constexpr int RA = 1 << G1, NGA = 16 >> G1;  // phase A: radix, groups per thread
     constexpr int TILE_WORDS = CONTIG ? 16 * (NT + 16) : NT * ROW;
@@ -320,11 +325,38 @@ __global__ void __launch_bounds__(256, EPI ? 1 : NTT2_MINBLOCKS) k_pass(PassArgs
     if (c_begin < c_end) load_first(c_begin);
     uint32_t v[16];
     int buf = 0;
-    for (uint32_t c = c_begin; c < c_end; c++, buf ^= 1) {
+    for (uint32_t c = c_begin; c < c_end; c++, buf ^= DUAL ? 0 : 1) {
         uint32_t* s = sm[buf];
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = nx[i];
         if (c + 1 < c_end) load_first(c + 1);  // software pipeline: next column's tile in flight during the butterflies
+        if (DUAL) {
+            // two exchanges per column: they alternate between the two shared tiles (h = 0: sm[buf], h = 1: sm[buf ^ 1]), so one barrier
+            // per exchange still separates every reuse of a tile from the reads of its previous contents
+            const uint64_t n = 1ull << A.log_n;
+            uint32_t x[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = v[i];
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                const uint32_t* pw = A.pw + (uint64_t)h * n + base;
+#pragma unroll
+                for (int j = 0; j < NGA; j++)
+#pragma unroll
+                    for (int a = 0; a < RA; a++) {
+                        const uint32_t off = goff(((uint32_t)a << G2) | r1A[j], laneA[j]);
+                        v[j * RA + a] = kb::mul(x[j * RA + a], __ldg(pw + off));
+                    }
+                uint32_t* sh = sm[buf ^ h];
+                phase<false, G1, true>(v, twA);
+                sts_A(sh, v);
+                __syncthreads();
+                lds_B(sh, v);
+                phase<false, G2, true>(v, twB);
+                store_B(A.out + (uint64_t)c * (2 * n) + (uint64_t)h * n + base, v);
+            }
+            continue;
+        }
         if (!INV) {
             if (G1 > 0) {
                 phase<false, G1, true>(v, twA);
