@@ -124,6 +124,33 @@ def cpu_commit(log_rows, cols, steps, warmup):
                 perms_per_s=num_perms(1 << lr, cols) / sec)
 
 
+def cpu_prove_lower_bound(shapes):
+    """A LOWER BOUND for a CPU prove of the same statement: only the three commitments (main, LogUp, quotient), each matrix extended
+    and hashed on its own by the tuned CPU implementation (oracle/fast_commit.c, all host threads) on random data of the right shape;
+    LogUp trace generation, quotient evaluation, openings, FRI and the injection layers of the trees are NOT included.
+    shapes: [(rows, main_width, perm_base_width)] per chip."""
+    import numpy as np
+    import oracle
+    if not oracle.fast_available():
+        return None
+    oracle.set_threads(host_threads())
+    rng = np.random.default_rng(7)
+    total, cells = 0.0, 0
+    for rows, mw, pw in shapes:
+        for w in (mw, pw, 4, 4):
+            if rows < 16 or w == 0:
+                continue
+            m = rng.integers(0, P, (rows, w), dtype=np.uint32)
+            oracle.fast_pcs_commit(m)  # warm the work buffers of this size
+            t = time.perf_counter()
+            oracle.fast_pcs_commit(m)
+            total += time.perf_counter() - t
+            cells += rows * w
+    oracle.fast_release()
+    return {"ms": total * 1e3, "committed_cells": cells, "cores": oracle.get_threads(),
+            "what": "LOWER BOUND of a CPU prove: the three commitments only (per-matrix LDE + leaf hashing + tree, tuned AVX-512 port); no LogUp, quotient, openings or FRI"}
+
+
 def bench_config(args, world):
     """`config` of the JSON line: identical for the b200 arm and the reference arm at the same N."""
     R, W = 1 << args.log_rows, args.cols
@@ -205,6 +232,7 @@ def prove_timings(ctx, bf, with_cpu):
         ctx.profile_enable(False)
         info = {c[0]: c for c in prover.chips}
         lde_cells = quot_bytes = 0
+        shard_names, shard_heights = list(shard.names), list(shard.heights)
         for nm, h in zip(shard.names, shard.heights):
             _, mw, pw, ew, _lo = info[nm]
             lde_cells += 2 * h * (pw + mw + 4 * ew + 8)             # prep + main + perm + two 4-column quotient chunks (each 2h x 4)
@@ -254,6 +282,8 @@ def prove_timings(ctx, bf, with_cpu):
             entry["proof_matches_cpu_oracle"] = bool(all((np.asarray(proof["commitment"][k]) == ref["commitment"][k]).all() for k in ("main", "permutation", "quotient"))
                                                      and (np.asarray(proof["opening_proof"]["final_poly"]) == ref["opening_proof"]["final_poly"]).all()
                                                      and proof["opening_proof"]["pow_witness"] == ref["opening_proof"]["pow_witness"])
+        if with_cpu and "2^22" in name:
+            entry["cpu_prove_lower_bound"] = cpu_prove_lower_bound([(h, info[nm][1], 4 * info[nm][3]) for nm, h in zip(shard_names, shard_heights)])
         out[name] = entry
         pk.free()
         ctx.free_pinned()

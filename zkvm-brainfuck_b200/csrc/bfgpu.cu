@@ -103,6 +103,7 @@ struct bfgpu_ctx {
     std::vector<std::vector<void*>*> scopes;
     // transcript options (bfgpu_set_transcript_option): the choices inside Plonky3 that cannot be confirmed offline (SURVEY.md P3 marks)
     uint32_t opt[BFGPU_NUM_OPTS] = {1, 0, 0};
+    bool ntt_turn = true;  // last inverse pass fused with the first forward pass (k_pass TURN); $BFGPU_NTT_TURN=0 runs them as two launches
     bool ntt_dual = true;  // coset scaling on load in the first forward pass (k_pass DUAL) instead of the inverse-pass epilogue ($BFGPU_NTT_DUAL=0)
     uint32_t dist_min_chunk = 32;  // dist_commit.cuh: smallest LDE / scatter block in columns ($BFGPU_DIST_MIN_CHUNK)
     unsigned dist_fri_gather_log = 20;  // dist_prove.cuh: global FRI length below which the sharded prover gathers ($BFGPU_DIST_FRI_GATHER_LOG)
@@ -330,6 +331,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (const char* e = getenv("BFGPU_X4_MAX")) ctx->x4_layer_max = strtoull(e, nullptr, 10);
     if (const char* e = getenv("BFGPU_PIPE_SPLITS")) ctx->pipe_tail_splits = atoi(e);
     if (const char* e = getenv("BFGPU_NTT_DUAL")) ctx->ntt_dual = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_NTT_TURN")) ctx->ntt_turn = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_DIST_MIN_CHUNK")) ctx->dist_min_chunk = (uint32_t)std::max(8, atoi(e)) / 8 * 8;
     if (const char* e = getenv("BFGPU_DIST_FRI_GATHER_LOG")) ctx->dist_fri_gather_log = (unsigned)std::min(24, std::max(4, atoi(e)));
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
@@ -769,7 +771,8 @@ static void launch_pass(bfgpu_ctx* ctx, const ntt2::PassArgs& a, dim3 grid) {
 
 template <int G1>
 static void launch_pass_dual(bfgpu_ctx* ctx, const ntt2::PassArgs& a, dim3 grid) {
-    ntt2::k_pass<false, G1, false, false, true><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
+    if (a.twA2) ntt2::k_pass<true, G1, false, false, false, true><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);  // TURN
+    else ntt2::k_pass<false, G1, false, false, true><<<grid, 1u << (G1 + 4), 0, ctx->stream>>>(a);
 }
 
 // Run all stages of a size-2^log_n transform on `ncols` column vectors (stride col_stride words).
@@ -782,13 +785,14 @@ struct CosetEpilogue {
 constexpr unsigned NTT2_MIN_LOG = 12;
 
 template <bool INVERSE>
-static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols, CosetEpilogue epi = CosetEpilogue()) {
+static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols, CosetEpilogue epi = CosetEpilogue(),
+                       bool skip_last = false) {
     if (log_n == 0 || ncols == 0) return BFGPU_OK;
     Phase ph(ctx, INVERSE ? BFGPU_PHASE_INTT : BFGPU_PHASE_NTT);
     if (log_n < NTT2_MIN_LOG) return run_ntt_small<INVERSE>(ctx, data, col_stride, log_n, ncols);
     const std::vector<bfgpu_ctx::NttPass>* plan = nullptr;
     TRY(get_plan(ctx, log_n, INVERSE, &plan));
-    size_t np = plan->size();
+    size_t np = plan->size() - (skip_last ? 1 : 0);  // skip_last: the top pass runs inside the TURN kernel of run_ntt_forward_dual
     for (size_t s = 0; s < np; s++) {
         const auto& ps = (*plan)[INVERSE ? s : np - 1 - s];  // inverse DIT: low bits first; forward DIF: high bits first
         uint32_t tiles = 1u << (log_n - ps.g - 4);
@@ -796,7 +800,7 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
         uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
         uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, ncols), (ncols + want_groups - 1) / want_groups);
         cpc = std::min<uint32_t>(cpc, 64);
-        ntt2::PassArgs a{data, col_stride, ncols, cpc, ps.p, ps.twA, ps.twB, nullptr, nullptr, 0, log_n};
+        ntt2::PassArgs a{data, col_stride, ncols, cpc, ps.p, ps.twA, ps.twB, nullptr, nullptr, 0, log_n, nullptr, nullptr};
         if (INVERSE && s + 1 == np && epi.pw) {
             a.pw = epi.pw;
             a.out = epi.out;
@@ -820,10 +824,13 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
 // Forward half of a blow-up-2 coset LDE from the (unscaled) coefficients: the top pass reads coef once, scales by the two coset
 // vectors on load and writes both half-columns of `out` (ntt2::k_pass<..., DUAL>); the remaining passes run in place on the 2W
 // half-columns.  BFGPU_NTT_DUAL=0 falls back to the epilogue-in-the-inverse-pass path of round 1.
-static int32_t run_ntt_forward_dual(bfgpu_ctx* ctx, const uint32_t* coef, uint32_t* out, const uint32_t* pw, unsigned log_n, uint32_t ncols) {
+// turn: `coef` still lacks the top inverse pass, which the first launch executes too (ntt2::k_pass<..., TURN>).
+static int32_t run_ntt_forward_dual(bfgpu_ctx* ctx, const uint32_t* coef, uint32_t* out, const uint32_t* pw, unsigned log_n, uint32_t ncols, bool turn) {
     Phase ph(ctx, BFGPU_PHASE_NTT);
     const std::vector<bfgpu_ctx::NttPass>* plan = nullptr;
+    const std::vector<bfgpu_ctx::NttPass>* iplan = nullptr;
     TRY(get_plan(ctx, log_n, false, &plan));
+    if (turn) TRY(get_plan(ctx, log_n, true, &iplan));
     const size_t np = plan->size();
     const uint64_t n = 1ull << log_n;
     for (size_t s = 0; s < np; s++) {
@@ -834,12 +841,20 @@ static int32_t run_ntt_forward_dual(bfgpu_ctx* ctx, const uint32_t* coef, uint32
         uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
         uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, cols), (cols + want_groups - 1) / want_groups);
         cpc = std::min<uint32_t>(cpc, dual ? 32 : 64);
-        ntt2::PassArgs a{dual ? const_cast<uint32_t*>(coef) : out, n, cols, cpc, ps.p, ps.twA, ps.twB, nullptr, nullptr, 0, log_n};
+        ntt2::PassArgs a{dual ? const_cast<uint32_t*>(coef) : out, n, cols, cpc, ps.p, ps.twA, ps.twB, nullptr, nullptr, 0, log_n, nullptr, nullptr};
         dim3 grid(tiles, (cols + cpc - 1) / cpc);
         if (dual) {
             a.pw = pw;
             a.out = out;
             a.ncosets = 2;
+            if (turn) {  // inverse tables drive the first half of the kernel, the forward ones of the same (p, g) the second
+                const auto& ips = iplan->back();
+                if (ips.p != ps.p || ips.g != ps.g) return fail(ctx, BFGPU_ERR_STATE, "internal: inverse and forward top passes differ");
+                a.twA = ips.twA;
+                a.twB = ips.twB;
+                a.twA2 = ps.twA;
+                a.twB2 = ps.twB;
+            }
             if (ps.p == 0 || ps.g < 5) return fail(ctx, BFGPU_ERR_STATE, "internal: dual pass needs a strided two-phase top pass");
             switch (ps.g - 4) {
                 case 1: launch_pass_dual<1>(ctx, a, grid); break;
@@ -906,8 +921,8 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     else TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
     if (log_n >= NTT2_MIN_LOG && ncosets == 2 && ctx->ntt_dual) {
         // plain inverse transform; the coset scaling and the 2-fold expansion happen on load in the first forward pass
-        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols));
-        TRY(run_ntt_forward_dual(ctx, coef.d, out->d, pw, log_n, coef.cols));
+        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols, CosetEpilogue(), ctx->ntt_turn));
+        TRY(run_ntt_forward_dual(ctx, coef.d, out->d, pw, log_n, coef.cols, ctx->ntt_turn));
         if (consume) dfree(ctx, coef.d);  // stream order keeps it alive for the pass above
         return BFGPU_OK;
     }

@@ -167,6 +167,9 @@ struct PassArgs {
     uint32_t* out;
     uint32_t ncosets;
     uint32_t log_n;
+    // TURN (last inverse pass fused with the first forward pass): forward tables of the same (p, g)
+    const TWT* twA2;
+    const TWT* twB2;
 };
 
 // Shared tile index of element (digit d, lane l).
@@ -187,9 +190,17 @@ __device__ __forceinline__ uint32_t tile_idx(uint32_t d, uint32_t l) {
 // cosets from it: v = x * pw_h on load (pw_h[k] = shift_h^k / n), transform, store into half-column h of the output — the coset
 // scaling needs no pass of its own and no second read of the coefficients (round 2: replaces the EPI epilogue of the last inverse
 // pass, which wrote 2n words per column that this pass then read back; -9 GB of 90 at 2^22 x 256).
-template <bool INV, int G1, bool CONTIG, bool EPI = false, bool DUAL = false>
-__global__ void __launch_bounds__(256, EPI ? 1 : NTT2_MINBLOCKS) k_pass(PassArgs A) {
+// TURN (inverse, strided, G1 > 0): the LAST inverse pass and the DUAL first forward pass in one kernel.  Both act on the same tile
+// (top g index bits) and the inverse pass ends in exactly the register layout the forward pass starts from (phase A), so the
+// coefficients never travel to HBM and back between the two: 4 B read + 8 B written per element instead of 8 + 12, one set of global
+// loads / stores instead of two.  Three shared exchanges per column alternate between the two tiles.
+#ifndef NTT2_TURN_MINBLOCKS
+#define NTT2_TURN_MINBLOCKS 3  // CTAs of 2^g <= 128 threads per SM the register budget is set for (g = 8: one)
+#endif
+template <bool INV, int G1, bool CONTIG, bool EPI = false, bool DUAL = false, bool TURN = false>
+__global__ void __launch_bounds__(TURN ? (1 << (G1 + 4)) : 256, TURN ? (G1 == 4 ? 1 : NTT2_TURN_MINBLOCKS) : EPI ? 1 : NTT2_MINBLOCKS) k_pass(PassArgs A) {
     static_assert(!DUAL || (!INV && !CONTIG && !EPI && G1 > 0), "DUAL is the strided forward pass with two register phases");
+    static_assert(!TURN || (INV && !CONTIG && !EPI && !DUAL && G1 > 0), "TURN is the strided last inverse pass with two register phases");
     constexpr int g = G1 + G2, NT = 1 << g;
     constexpr int RA = 1 << G1, NGA = 16 >> G1;  // phase A: radix, groups per thread
     constexpr int TILE_WORDS = CONTIG ? 16 * (NT + 16) : NT * ROW;
@@ -242,8 +253,24 @@ __global__ void __launch_bounds__(256, EPI ? 1 : NTT2_MINBLOCKS) k_pass(PassArgs
         for (uint32_t i = t; i < 15 * LANES; i += NT) s_twb[i / LANES][i % LANES] = A.twB[(uint64_t)(i / LANES) << p | (lo_base + i % LANES)];
         __syncthreads();
     }
+    // TURN: forward twiddles of the same tile position; phase A in registers, phase B in shared memory like the inverse ones
+    TWT twa2[TURN ? 15 : 1];
+    __shared__ TWT s_twb2[TURN ? 15 : 1][LANES];
+    if (TURN) {
+#pragma unroll
+        for (int j = 0; j < NGA; j++) {
+            uint32_t m = (r1A[j] << p) | (lo_base + laneA[j]);
+            uint32_t M = 1u << (p + 4);
+#pragma unroll
+            for (int q = 1; q < RA; q++) twa2[TURN ? j * (RA - 1) + q - 1 : 0] = A.twA2[(uint64_t)(q - 1) * M + m];
+        }
+        for (uint32_t i = t; i < 15 * LANES; i += NT) s_twb2[TURN ? i / LANES : 0][i % LANES] = A.twB2[(uint64_t)(i / LANES) << p | (lo_base + i % LANES)];
+        __syncthreads();
+    }
     auto twA = [&](int i) { return twa[i]; };
     auto twB = [&](int i) { return s_twb[i][laneB]; };
+    auto twA2 = [&](int i) { return twa2[TURN ? i : 0]; };
+    auto twB2 = [&](int i) { return s_twb2[TURN ? i : 0][laneB]; };
     const uint32_t c_begin = blockIdx.y * A.cols_per_cta;
     const uint32_t c_end = min(A.ncols, c_begin + A.cols_per_cta);
 
@@ -327,6 +354,40 @@ __global__ void __launch_bounds__(256, EPI ? 1 : NTT2_MINBLOCKS) k_pass(PassArgs
     int buf = 0;
     for (uint32_t c = c_begin; c < c_end; c++, buf ^= DUAL ? 0 : 1) {
         uint32_t* s = sm[buf];
+        if (TURN) {
+            // inverse pass (phase B, exchange, phase A), then per coset: scale, forward phase A, exchange, phase B, store
+            const uint64_t n = 1ull << A.log_n;
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = nx[i];
+            if (c + 1 < c_end) load_first(c + 1);
+            phase<true, G2, true>(v, twB);
+            sts_B(s, v);
+            __syncthreads();
+            lds_A(s, v);
+            phase<true, G1, true>(v, twA);
+            uint32_t x[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = v[i];
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                const uint32_t* pw = A.pw + (uint64_t)h * n + base;
+#pragma unroll
+                for (int j = 0; j < NGA; j++)
+#pragma unroll
+                    for (int a = 0; a < RA; a++) {
+                        const uint32_t off = goff(((uint32_t)a << G2) | r1A[j], laneA[j]);
+                        v[j * RA + a] = kb::mul(x[j * RA + a], __ldg(pw + off));
+                    }
+                uint32_t* sh = sm[buf ^ 1 ^ h];  // exchanges alternate tiles: inverse sm[buf], h = 0 sm[buf^1], h = 1 sm[buf]; next column starts at sm[buf^1]
+                phase<false, G1, true>(v, twA2);
+                sts_A(sh, v);
+                __syncthreads();
+                lds_B(sh, v);
+                phase<false, G2, true>(v, twB2);
+                store_B(A.out + (uint64_t)c * (2 * n) + (uint64_t)h * n + base, v);
+            }
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = nx[i];
         if (c + 1 < c_end) load_first(c + 1);  // software pipeline: next column's tile in flight during the butterflies
