@@ -23,6 +23,7 @@
 #include "kernels_hash.cuh"
 #include "kernels_ntt.cuh"
 #include "kernels_ntt2.cuh"
+#include "kernels_ntt3.cuh"
 #include <array>
 #include <functional>
 #include <map>
@@ -103,6 +104,8 @@ struct bfgpu_ctx {
     std::vector<std::vector<void*>*> scopes;
     // transcript options (bfgpu_set_transcript_option): the choices inside Plonky3 that cannot be confirmed offline (SURVEY.md P3 marks)
     uint32_t opt[BFGPU_NUM_OPTS] = {1, 0, 0};
+    bool ntt_tma = true;   // strided NTT passes through the TMA-fed 32-lane kernels (kernels_ntt3.cuh); $BFGPU_NTT_TMA=0: ntt2::k_pass
+    std::set<int> ntt3_configured;  // (mode, G1) instantiations whose dynamic shared-memory limit has been raised on this device
     bool ntt_turn = true;  // last inverse pass fused with the first forward pass (k_pass TURN); $BFGPU_NTT_TURN=0 runs them as two launches
     bool ntt_dual = true;  // coset scaling on load in the first forward pass (k_pass DUAL) instead of the inverse-pass epilogue ($BFGPU_NTT_DUAL=0)
     uint32_t dist_min_chunk = 32;  // dist_commit.cuh: smallest LDE / scatter block in columns ($BFGPU_DIST_MIN_CHUNK)
@@ -332,6 +335,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (const char* e = getenv("BFGPU_PIPE_SPLITS")) ctx->pipe_tail_splits = atoi(e);
     if (const char* e = getenv("BFGPU_NTT_DUAL")) ctx->ntt_dual = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_NTT_TURN")) ctx->ntt_turn = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_NTT_TMA")) ctx->ntt_tma = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_DIST_MIN_CHUNK")) ctx->dist_min_chunk = (uint32_t)std::max(8, atoi(e)) / 8 * 8;
     if (const char* e = getenv("BFGPU_DIST_FRI_GATHER_LOG")) ctx->dist_fri_gather_log = (unsigned)std::min(24, std::max(4, atoi(e)));
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
@@ -758,6 +762,84 @@ static int32_t get_plan(bfgpu_ctx* ctx, unsigned log_n, bool inverse, const std:
     return BFGPU_OK;
 }
 
+
+// ---- TMA-fed strided passes (kernels_ntt3.cuh) -------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (tmap_encode_fn)f;
+    }();
+    return fn;
+}
+static bool ntt3_usable(bfgpu_ctx* ctx, const bfgpu_ctx::NttPass& ps) { return ctx->ntt_tma && ps.p >= 5 && ps.g >= 5 && ps.g <= 8 && tmap_encoder() != nullptr; }
+
+template <int MODE, int G1>
+static int32_t launch3(bfgpu_ctx* ctx, const CUtensorMap& tm_in, const CUtensorMap& tm_out, const ntt3::PassArgs& a, dim3 grid) {
+    const int key = MODE * 8 + G1;
+    if (!ctx->ntt3_configured.count(key)) {
+        CU(cudaFuncSetAttribute(ntt3::k_pass3<MODE, G1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt3::smem_bytes(MODE, G1)));
+        ctx->ntt3_configured.insert(key);
+    }
+    ntt3::k_pass3<MODE, G1><<<grid, 1u << (G1 + 5), ntt3::smem_bytes(MODE, G1), ctx->stream>>>(tm_in, tm_out, a);
+    return BFGPU_OK;
+}
+template <int MODE>
+static int32_t launch3_g(bfgpu_ctx* ctx, unsigned g, const CUtensorMap& tm_in, const CUtensorMap& tm_out, const ntt3::PassArgs& a, dim3 grid) {
+    switch (g - 4) {
+        case 1: return launch3<MODE, 1>(ctx, tm_in, tm_out, a, grid);
+        case 2: return launch3<MODE, 2>(ctx, tm_in, tm_out, a, grid);
+        case 3: return launch3<MODE, 3>(ctx, tm_in, tm_out, a, grid);
+        case 4: return launch3<MODE, 4>(ctx, tm_in, tm_out, a, grid);
+    }
+    return fail(ctx, BFGPU_ERR_STATE, "internal: bad pass size %u", g);
+}
+// 4-d view [column][hi][digit][lo] of `ncols` column vectors of 2^log_n words for the pass (p, g); box = 32 lanes x box_digits digits
+static int32_t pass_tensor_map(bfgpu_ctx* ctx, CUtensorMap* tm, const uint32_t* base, uint64_t col_stride, uint32_t ncols, unsigned log_n, unsigned p, unsigned g,
+                               uint32_t box_digits) {
+    const cuuint64_t gdim[4] = {1ull << p, 1ull << g, 1ull << (log_n - p - g), ncols};
+    const cuuint64_t gstride[3] = {4ull << p, 4ull << (p + g), col_stride * 4};
+    const cuuint32_t box[4] = {32, box_digits, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = tmap_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<uint32_t*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, BFGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a 2^%u x %u pass p=%u g=%u", (int)r, log_n, ncols, p, g);
+    return BFGPU_OK;
+}
+// One strided pass (p, g) of size-2^log_n transforms over `ncols` column vectors at src (stride src_stride words).
+// FWD / INV: in place.  TURN: reads the columns of src, writes the 2*ncols half-columns of `out` (a.pw, a.twA2, a.twB2 set by the caller).
+static int32_t run_pass3(bfgpu_ctx* ctx, int mode, const uint32_t* src, uint64_t src_stride, uint32_t ncols, unsigned log_n, const bfgpu_ctx::NttPass& ps,
+                         ntt3::PassArgs a, uint32_t* out = nullptr) {
+    const unsigned p = ps.p, g = ps.g;
+    CUtensorMap tm_in, tm_out;
+    TRY(pass_tensor_map(ctx, &tm_in, src, src_stride, ncols, log_n, p, g, 1u << g));
+    if (mode == ntt3::FWD) TRY(pass_tensor_map(ctx, &tm_out, src, src_stride, ncols, log_n, p, g, 16));
+    else if (mode == ntt3::INV) tm_out = tm_in;
+    else TRY(pass_tensor_map(ctx, &tm_out, out, 1ull << log_n, 2 * ncols, log_n, p, g, 16));
+    const uint32_t tiles = 1u << (log_n - g - 5);
+    // CTAs hold 2^(g+1) threads: fill the machine several times over, but keep >= 8 columns per CTA (twiddle loads, ring start-up)
+    const uint32_t want_groups = std::max<uint32_t>(1, (148u * 8 + tiles - 1) / tiles);
+    uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, ncols), (ncols + want_groups - 1) / want_groups);
+    cpc = std::min<uint32_t>(cpc, mode == ntt3::TURN ? 32 : 64);
+    a.ncols = ncols;
+    a.cols_per_cta = cpc;
+    a.p = p;
+    a.log_n = log_n;
+    dim3 grid(tiles, (ncols + cpc - 1) / cpc);
+    switch (mode) {
+        case ntt3::FWD: TRY((launch3_g<ntt3::FWD>(ctx, g, tm_in, tm_out, a, grid))); break;
+        case ntt3::INV: TRY((launch3_g<ntt3::INV>(ctx, g, tm_in, tm_out, a, grid))); break;
+        default: TRY((launch3_g<ntt3::TURN>(ctx, g, tm_in, tm_out, a, grid))); break;
+    }
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    return BFGPU_OK;
+}
+
 template <bool INVERSE, int G1>
 static void launch_pass(bfgpu_ctx* ctx, const ntt2::PassArgs& a, dim3 grid) {
     if (INVERSE && a.pw != nullptr) {  // last inverse pass with the fused coset epilogue (always a strided pass: log_n >= 12)
@@ -795,6 +877,11 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
     size_t np = plan->size() - (skip_last ? 1 : 0);  // skip_last: the top pass runs inside the TURN kernel of run_ntt_forward_dual
     for (size_t s = 0; s < np; s++) {
         const auto& ps = (*plan)[INVERSE ? s : np - 1 - s];  // inverse DIT: low bits first; forward DIF: high bits first
+        if (ntt3_usable(ctx, ps) && !(INVERSE && s + 1 == np && epi.pw)) {
+            ntt3::PassArgs a3{0, 0, 0, 0, ps.twA, ps.twB, nullptr, nullptr, nullptr};
+            TRY(run_pass3(ctx, INVERSE ? ntt3::INV : ntt3::FWD, data, col_stride, ncols, log_n, ps, a3));
+            continue;
+        }
         uint32_t tiles = 1u << (log_n - ps.g - 4);
         // enough CTAs to fill the machine several times, but >= 8 columns per CTA to amortise the twiddle loads
         uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
@@ -837,6 +924,22 @@ static int32_t run_ntt_forward_dual(bfgpu_ctx* ctx, const uint32_t* coef, uint32
         const auto& ps = (*plan)[np - 1 - s];  // forward DIF: high bits first
         const bool dual = s == 0;
         const uint32_t cols = dual ? ncols : 2 * ncols;
+        if (ntt3_usable(ctx, ps) && (!dual || turn)) {  // (the DUAL pass without the inverse half exists only in ntt2::k_pass)
+            ntt3::PassArgs a3{0, 0, 0, 0, ps.twA, ps.twB, nullptr, nullptr, nullptr};
+            if (dual) {
+                const auto& ips = iplan->back();
+                if (ips.p != ps.p || ips.g != ps.g) return fail(ctx, BFGPU_ERR_STATE, "internal: inverse and forward top passes differ");
+                a3.twA = ips.twA;
+                a3.twB = ips.twB;
+                a3.twA2 = ps.twA;
+                a3.twB2 = ps.twB;
+                a3.pw = pw;
+                TRY(run_pass3(ctx, ntt3::TURN, coef, n, cols, log_n, ps, a3, out));
+            } else {
+                TRY(run_pass3(ctx, ntt3::FWD, out, n, cols, log_n, ps, a3));
+            }
+            continue;
+        }
         uint32_t tiles = 1u << (log_n - ps.g - 4);
         uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
         uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, cols), (cols + want_groups - 1) / want_groups);

@@ -1,0 +1,285 @@
+// kernels_ntt3.cuh — strided NTT passes whose tiles travel by TMA in both directions (32-lane tiles, in-place shared tiles).
+//
+// Same role and arithmetic as the strided instantiations of ntt2::k_pass (reference: `Radix2DitParallel::coset_lde_batch`
+// behind `TwoAdicFriPcs::commit`, crates/stark/src/prover.rs:227,334,411); what changes is how a tile moves:
+//   * a tile is 2^g digits x 32 lanes (128-byte segments = whole L2 lines; ntt2 moves 64-byte segments), so every warp-wide
+//     shared access of either register phase is ONE row of 32 consecutive words: dense tile, no padding, no swizzle;
+//   * the input tile of a later column is fetched by ONE `cp.async.bulk.tensor.4d` (TMA box 32 x 2^g of the 4-d view
+//     [column][hi][digit][lo] of the matrix) issued by thread 0 into a ring of slots, completion on an mbarrier;
+//   * the column is transformed IN PLACE in its slot: each register phase reads and writes the words the thread owns in that
+//     phase's layout, so the only hazards are the layout changes (one barrier each);
+//   * results leave by TMA too: in the forward layout a warp owns 16 consecutive digits, so every warp stores its own 2 KB box
+//     (`cp.async.bulk.tensor` shared -> global) after a warp-level sync — no per-element address arithmetic, no STG.
+// The SM therefore issues no global load/store instructions at all for the data of a pass (ncu of the register-prefetching
+// passes: ~20 % of the issued instructions were address arithmetic and LSU global traffic in an issue-bound kernel).
+//
+// Slot reuse: a slot is refilled by thread 0 right after the first barrier of an iteration; by then every warp has waited
+// (`cp.async.bulk.wait_group.read`) for its own store out of that slot — the wait sits before that barrier in program order.
+//
+// Modes: FWD / INV = one forward / inverse pass in place; TURN = LAST inverse pass + coset scaling + FIRST forward pass of a
+// blow-up-2 LDE in one kernel: both act on the same tile (top g index bits) and the inverse pass ends in exactly the register
+// layout the forward pass starts from, so the coefficients never travel to HBM between the two.
+#pragma once
+#include <cuda.h>
+
+#include "kernels_ntt2.cuh"
+
+namespace ntt3 {
+
+using ntt2::G2;
+using ntt2::TWT;
+using ntt2::phase;
+
+constexpr int LANES = 32;
+enum Mode { FWD = 0, INV = 1, TURN = 2 };
+
+struct PassArgs {
+    uint32_t ncols;
+    uint32_t cols_per_cta;
+    uint32_t p;          // low bit of the pass (>= 5)
+    uint32_t log_n;
+    const TWT* twA;      // tables of the pass (TURN: the inverse ones)
+    const TWT* twB;
+    const TWT* twA2;     // TURN: forward tables of the same (p, g)
+    const TWT* twB2;
+    const uint32_t* pw;  // TURN: coset scale vectors [2][n]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)tm), "r"(smem_u32(src)), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__host__ __device__ constexpr int nslots(int mode) { return mode == TURN ? 2 : 4; }
+__host__ __device__ constexpr int ntiles(int mode) { return mode == TURN ? 6 : 4; }  // TURN: 2 slots + 2 exchange tiles + 2 tiles of coset scale factors
+constexpr size_t smem_bytes(int mode, int G1) {
+    return (size_t)ntiles(mode) * ((size_t)4 << (G1 + 4 + 5)) + 2 * 15 * LANES * sizeof(TWT) + 4 * sizeof(uint64_t);
+}
+
+extern __shared__ __align__(1024) uint32_t smem3[];
+
+// Threads per CTA = 2^(g+1) (16 elements per thread).  Register budget: TURN 128 per thread (512 threads resident per SM), the
+// plain passes 80 (768 threads: three CTAs of 256 at g = 7; their four slots are 64 KB per CTA).
+#ifndef NTT3_RESIDENT
+#define NTT3_RESIDENT 768
+#endif
+template <int MODE, int G1>
+__global__ void __launch_bounds__(1 << (G1 + 5), G1 >= 4 ? 1 : ((MODE == TURN ? 512 : NTT3_RESIDENT) >> (G1 + 5)))
+    k_pass3(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, PassArgs A) {
+    static_assert(G1 >= 1 && G1 <= 4, "two register phases");
+    constexpr int g = G1 + G2, NT = 1 << (g + 1);
+    constexpr int RA = 1 << G1, NGA = 16 >> G1;
+    constexpr int TILE = (1 << g) * LANES;  // words
+    constexpr int NSLOT = nslots(MODE);
+    uint32_t* const s_slot = smem3;                               // [NSLOT][TILE]
+    uint32_t* const s_ex = smem3 + NSLOT * TILE;                   // TURN: [2][TILE]
+    uint32_t* const s_pw = smem3 + (NSLOT + 2) * TILE;             // TURN: [2][TILE]
+    TWT(*const s_twb)[LANES] = reinterpret_cast<TWT(*)[LANES]>(smem3 + ntiles(MODE) * TILE);  // [15][LANES]
+    TWT(*const s_twb2)[LANES] = s_twb + 15;                                                      // [15][LANES] (TURN)
+    uint64_t* const full = reinterpret_cast<uint64_t*>(s_twb2 + 15);                             // [NSLOT]
+
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t p = A.p;
+    const uint32_t lo_blocks_log = p - 5;
+    const uint32_t lo_base = (blockIdx.x & ((1u << lo_blocks_log) - 1)) << 5;
+    const uint32_t hi = blockIdx.x >> lo_blocks_log;
+    const uint32_t c_begin = blockIdx.y * A.cols_per_cta;
+    const uint32_t c_end = min(A.ncols, c_begin + A.cols_per_cta);
+    if (c_begin >= c_end) return;
+    const uint32_t ncol = c_end - c_begin;
+
+    // ---- ring of tiles -------------------------------------------------------------------------------------------------
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    __syncthreads();
+    auto issue = [&](uint32_t i) {  // thread 0: tile of the i-th column of this CTA into slot i % NSLOT
+        const uint32_t s = i % NSLOT;
+        mbar_expect_tx(&full[s], TILE * 4);
+        tma_load_4d(s_slot + s * TILE, &tm_in, &full[s], (int)lo_base, 0, (int)hi, (int)(c_begin + i));
+    };
+    constexpr uint32_t AHEAD = MODE == TURN ? 1 : 2;  // columns in flight beyond the current one
+    if (t == 0) {
+#pragma unroll
+        for (uint32_t s = 0; s < AHEAD; s++)
+            if (s < ncol) issue(s);
+    }
+
+    // ---- per-thread coordinates: phase A combos (r1, lane) x NGA, phase B combo (aB = warp, lane) ----------------------
+    uint32_t offA[NGA];  // word offset of (digit r1, lane) in a tile; element a of the group sits (a << 9) words further
+#pragma unroll
+    for (int j = 0; j < NGA; j++) {
+        const uint32_t cidx = t + j * NT;
+        offA[j] = ((cidx >> 5) << 5) + (cidx & 31);
+    }
+    const uint32_t offB = (warp << (G2 + 5)) + lane;  // (digit warp*16, lane); element b sits (b << 5) words further
+
+    // twiddles of this tile position: phase A in registers, phase B (lane-only) in shared memory
+    TWT twa[15];
+    TWT twa2[MODE == TURN ? 15 : 1];
+    {
+        const uint32_t M = 1u << (p + 4);
+#pragma unroll
+        for (int j = 0; j < NGA; j++) {
+            const uint32_t cidx = t + j * NT;
+            const uint32_t m = ((cidx >> 5) << p) | (lo_base + (cidx & 31));
+#pragma unroll
+            for (int q = 1; q < RA; q++) {
+                twa[j * (RA - 1) + q - 1] = A.twA[(uint64_t)(q - 1) * M + m];
+                if (MODE == TURN) twa2[MODE == TURN ? j * (RA - 1) + q - 1 : 0] = A.twA2[(uint64_t)(q - 1) * M + m];
+            }
+        }
+        for (uint32_t i = t; i < 15 * LANES; i += NT) {
+            s_twb[i / LANES][i % LANES] = A.twB[(uint64_t)(i / LANES) << p | (lo_base + i % LANES)];
+            if (MODE == TURN) s_twb2[i / LANES][i % LANES] = A.twB2[(uint64_t)(i / LANES) << p | (lo_base + i % LANES)];
+        }
+        if (MODE == TURN) {  // coset scale factors of this tile position, same for every column
+            const uint64_t n = 1ull << A.log_n;
+            const uint64_t base = ((uint64_t)hi << (p + g)) | lo_base;
+            for (uint32_t i = t; i < 2 * TILE; i += NT) {
+                const uint32_t h = i / TILE, w = i % TILE;
+                s_pw[i] = __ldg(A.pw + (uint64_t)h * n + base + ((uint64_t)(w >> 5) << p) + (w & 31));
+            }
+        }
+        __syncthreads();
+    }
+    auto twA = [&](int i) { return twa[i]; };
+    auto twB = [&](int i) { return s_twb[i][lane]; };
+    auto twA2 = [&](int i) { return twa2[MODE == TURN ? i : 0]; };
+    auto twB2 = [&](int i) { return s_twb2[i][lane]; };
+
+    // ---- register <-> shared moves in the two phase layouts ----------------------------------------------------------------
+    auto lds_A = [&](const uint32_t* s, uint32_t* r) {
+#pragma unroll
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) r[j * RA + a] = s[offA[j] + (a << (G2 + 5))];
+    };
+    auto sts_A = [&](uint32_t* s, const uint32_t* r) {
+#pragma unroll
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) s[offA[j] + (a << (G2 + 5))] = r[j * RA + a];
+    };
+    auto lds_B = [&](const uint32_t* s, uint32_t* r) {
+#pragma unroll
+        for (int b = 0; b < 16; b++) r[b] = s[offB + (b << 5)];
+    };
+    auto sts_B = [&](uint32_t* s, const uint32_t* r) {
+#pragma unroll
+        for (int b = 0; b < 16; b++) s[offB + (b << 5)] = r[b];
+    };
+    // the warp's 16 digits x 32 lanes of tile s (forward layout) -> column `col` of the output view
+    auto store_warp_rows = [&](const uint32_t* s, uint32_t col) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_4d(&tm_out, s + (warp << (G2 + 5)), (int)lo_base, (int)(warp << G2), (int)hi, (int)col);
+            bulk_commit();
+        }
+    };
+
+    uint32_t v[16];
+    for (uint32_t i = 0; i < ncol; i++) {
+        const uint32_t c = c_begin + i;
+        uint32_t* const S = s_slot + (i % NSLOT) * TILE;
+        if (MODE == TURN && lane == 0) bulk_wait_read<1>();  // own stores of column i-1 (slot) and i-2 (exchange tile) have left shared memory
+        while (!mbar_try_wait(&full[i % NSLOT], (i / NSLOT) & 1)) {
+        }
+        if constexpr (MODE == FWD) {
+            lds_A(S, v);
+            phase<false, G1, true>(v, twA);
+            sts_A(S, v);
+            __syncthreads();
+            if (t == 0 && i + AHEAD < ncol) issue(i + AHEAD);  // slot of column i-2: every warp waited for its store before the barrier
+            lds_B(S, v);
+            phase<false, G2, true>(v, twB);
+            sts_B(S, v);
+            store_warp_rows(S, c);
+            if (lane == 0) bulk_wait_read<1>();  // store of column i-1 has left its slot
+        } else if constexpr (MODE == INV) {
+            lds_B(S, v);
+            phase<true, G2, true>(v, twB);
+            sts_B(S, v);
+            __syncthreads();
+            if (t == 0 && i + AHEAD < ncol) issue(i + AHEAD);
+            lds_A(S, v);
+            phase<true, G1, true>(v, twA);
+            sts_A(S, v);
+            fence_async_smem();
+            __syncthreads();
+            if (t == 0) {  // the inverse layout scatters a warp's digits over the tile: one store of the whole tile
+                tma_store_4d(&tm_out, S, (int)lo_base, 0, (int)hi, (int)c);
+                bulk_commit();
+                bulk_wait_read<1>();
+            }
+        } else {
+            uint32_t* const E = s_ex + (i & 1) * TILE;
+            lds_B(S, v);
+            phase<true, G2, true>(v, twB);
+            sts_B(S, v);
+            __syncthreads();
+            if (t == 0 && i + AHEAD < ncol) issue(i + AHEAD);  // other slot: its store was waited for at the top of this iteration
+            lds_A(S, v);
+            phase<true, G1, true>(v, twA);
+            uint32_t x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = v[k];
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                const uint32_t* pw = s_pw + h * TILE;
+                uint32_t* const X = h ? E : S;  // h = 0 continues in place; h = 1 needs a tile of its own (S is being stored)
+#pragma unroll
+                for (int j = 0; j < NGA; j++)
+#pragma unroll
+                    for (int a = 0; a < RA; a++) v[j * RA + a] = kb::mul(x[j * RA + a], pw[offA[j] + (a << (G2 + 5))]);
+                phase<false, G1, true>(v, twA2);
+                sts_A(X, v);
+                __syncthreads();
+                lds_B(X, v);
+                phase<false, G2, true>(v, twB2);
+                sts_B(X, v);
+                store_warp_rows(X, 2 * c + h);
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_all();  // shared memory must outlive the stores
+}
+
+}  // namespace ntt3
