@@ -95,6 +95,9 @@ def _emit_rlc(em, lk, tag):
     return f"rlc_{tag}", m
 
 
+INV_GROUP = int(os.environ.get("BFGPU_GEN_INV_GROUP", "4"))  # LogUp batches sharing one extension inversion
+
+
 def gen_chip(chip, index):
     name = _cname(chip)
     n_base = len(chip.constraints)
@@ -124,7 +127,7 @@ def gen_chip(chip, index):
         em.emit(f"{{  // batch {j}: entry * prod(rlc) - sum_i m_i * prod_(j != i) rlc_j")
         em.emit("    kb::Ext prod = " + rl[0][0] + ";")
         for r, _, _ in rl[1:]:
-            em.emit(f"    prod = kb::ext_mul(prod, {r});")
+            em.emit(f"    prod = AIR_EXT_MUL(prod, {r});")
         em.emit("    kb::Ext num = kb::ext_zero();")
         for i, (r, m, is_send) in enumerate(rl):
             others = [x[0] for k, x in enumerate(rl) if k != i]
@@ -133,11 +136,11 @@ def gen_chip(chip, index):
             else:
                 o = others[0]
                 for x in others[1:]:
-                    o = f"kb::ext_mul({o}, {x})"
+                    o = f"AIR_EXT_MUL({o}, {x})"
                 term = f"kb::ext_scale({o}, {m})"
             em.emit(f"    num = kb::ext_{'add' if is_send else 'sub'}(num, {term});")
-        em.emit(f"    kb::Ext cst = kb::ext_sub(kb::ext_mul(prod, ld.perm0({j})), num);")
-        em.emit(f"    acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 1 - (n_base + j)}], cst));")
+        em.emit(f"    kb::Ext cst = kb::ext_sub(AIR_EXT_MUL(prod, ld.perm0({j})), num);")
+        em.emit(f"    acc = kb::ext_add(acc, AIR_EXT_MUL(apow[{total - 1 - (n_base + j)}], cst));")
         em.emit("}")
     W = chip.perm_width
     em.emit("{")
@@ -147,9 +150,9 @@ def gen_chip(chip, index):
         em.emit(f"    sum_next = kb::ext_add(sum_next, ld.perm1({j}));")
     em.emit(f"    const kb::Ext phi_local = ld.perm0({W - 1}), phi_next = ld.perm1({W - 1});")
     k0 = n_base + W - 1
-    em.emit(f"    acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 1 - k0}], kb::ext_scale(kb::ext_sub(phi_local, sum_local), sel.is_first)));")
-    em.emit(f"    acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 2 - k0}], kb::ext_scale(kb::ext_sub(kb::ext_sub(phi_next, phi_local), sum_next), sel.is_trans)));")
-    em.emit(f"    acc = kb::ext_add(acc, kb::ext_mul(apow[{total - 3 - k0}], kb::ext_scale(kb::ext_sub(phi_local, ch.cumulative_sum), sel.is_last)));")
+    em.emit(f"    acc = kb::ext_add(acc, AIR_EXT_MUL(apow[{total - 1 - k0}], kb::ext_scale(kb::ext_sub(phi_local, sum_local), sel.is_first)));")
+    em.emit(f"    acc = kb::ext_add(acc, AIR_EXT_MUL(apow[{total - 2 - k0}], kb::ext_scale(kb::ext_sub(kb::ext_sub(phi_next, phi_local), sum_next), sel.is_trans)));")
+    em.emit(f"    acc = kb::ext_add(acc, AIR_EXT_MUL(apow[{total - 3 - k0}], kb::ext_scale(kb::ext_sub(phi_local, ch.cumulative_sum), sel.is_last)));")
     em.emit("}")
     out.append(f"template <class L>\n__device__ __forceinline__ void air_constraints_{name}(const L& ld, const Selectors& sel, const Challenges& ch, const kb::Ext* __restrict__ apow, kb::Ext& acc) {{")
     out += em.lines
@@ -169,19 +172,29 @@ def gen_chip(chip, index):
             em.emit(f"kb::ExtAcc nacc_{j} = kb::ext_acc_zero();")
             em.emit(f"kb::ext_mac(nacc_{j}, {r1}, {m0 if s0 else f'kb::neg({m0})'});")
             em.emit(f"kb::ext_mac(nacc_{j}, {r0}, {m1 if s1 else f'kb::neg({m1})'});")
-            em.emit(f"const kb::Ext num_{j} = kb::ext_acc_reduce(nacc_{j}), den_{j} = kb::ext_mul({r0}, {r1});")
+            em.emit(f"const kb::Ext num_{j} = kb::ext_acc_reduce(nacc_{j}), den_{j} = AIR_EXT_MUL({r0}, {r1});")
         else:
             (r0, m0, s0), = terms
             em.emit(f"const kb::Ext num_{j} = kb::ext_from_base({m0 if s0 else f'kb::neg({m0})'}), den_{j} = {r0};")
-        # Montgomery's trick over PAIRS of batches: one extension inversion (~1 200 instructions) per two batches
-        if j % 2 == 1:
-            em.emit("{")
-            em.emit(f"    const kb::Ext ip = kb::ext_inv(kb::ext_mul(den_{j - 1}, den_{j}));")
-            em.emit(f"    out[{j - 1}] = kb::ext_mul(num_{j - 1}, kb::ext_mul(ip, den_{j}));")
-            em.emit(f"    out[{j}] = kb::ext_mul(num_{j}, kb::ext_mul(ip, den_{j - 1}));")
-            em.emit("}")
-        elif j == chip.perm_width - 2:
-            em.emit(f"out[{j}] = kb::ext_mul(num_{j}, kb::ext_inv(den_{j}));")
+    # Montgomery's trick over groups of INV_GROUP batch denominators: one extension inversion (~1 200 instructions) per group,
+    # three extension products per batch (prefix product, running inverse, quotient); the group size bounds the live registers
+    nb = chip.perm_width - 1
+    for g0 in range(0, nb, INV_GROUP):
+        g1 = min(nb, g0 + INV_GROUP)
+        if g1 - g0 == 1:
+            em.emit(f"out[{g0}] = AIR_EXT_MUL(num_{g0}, AIR_EXT_INV(den_{g0}));")
+            continue
+        em.emit("{")
+        em.emit(f"    kb::Ext pre[{g1 - g0}];  // pre[j] = den_{g0} * ... * den_(g0+j)")
+        em.emit(f"    pre[0] = den_{g0};")
+        for j in range(g0 + 1, g1):
+            em.emit(f"    pre[{j - g0}] = AIR_EXT_MUL(pre[{j - g0 - 1}], den_{j});")
+        em.emit(f"    kb::Ext run = AIR_EXT_INV(pre[{g1 - g0 - 1}]);  // 1 / (den_{g0} ... den_j) while walking down")
+        for j in range(g1 - 1, g0, -1):
+            em.emit(f"    out[{j}] = AIR_EXT_MUL(num_{j}, AIR_EXT_MUL(run, pre[{j - g0 - 1}]));")
+            em.emit(f"    run = AIR_EXT_MUL(run, den_{j});")
+        em.emit(f"    out[{g0}] = AIR_EXT_MUL(num_{g0}, run);")
+        em.emit("}")
     out.append(f"template <class L>\n__device__ __forceinline__ void air_perm_row_{name}(const L& ld, const Challenges& ch, kb::Ext* out) {{")
     out += em.lines
     out.append("}")

@@ -104,6 +104,7 @@ struct bfgpu_ctx {
     std::vector<std::vector<void*>*> scopes;
     // transcript options (bfgpu_set_transcript_option): the choices inside Plonky3 that cannot be confirmed offline (SURVEY.md P3 marks)
     uint32_t opt[BFGPU_NUM_OPTS] = {1, 0, 0};
+    bool ntt_ingest = true;  // row-major input -> first inverse pass in one kernel (ntt3::k_ingest_pass); $BFGPU_NTT_INGEST=0: transpose, then pass
     bool ntt_tma = true;   // strided NTT passes through the TMA-fed 32-lane kernels (kernels_ntt3.cuh); $BFGPU_NTT_TMA=0: ntt2::k_pass
     std::set<int> ntt3_configured;  // (mode, G1) instantiations whose dynamic shared-memory limit has been raised on this device
     bool ntt_turn = true;  // last inverse pass fused with the first forward pass (k_pass TURN); $BFGPU_NTT_TURN=0 runs them as two launches
@@ -336,6 +337,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (const char* e = getenv("BFGPU_NTT_DUAL")) ctx->ntt_dual = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_NTT_TURN")) ctx->ntt_turn = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_NTT_TMA")) ctx->ntt_tma = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_NTT_INGEST")) ctx->ntt_ingest = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_DIST_MIN_CHUNK")) ctx->dist_min_chunk = (uint32_t)std::max(8, atoi(e)) / 8 * 8;
     if (const char* e = getenv("BFGPU_DIST_FRI_GATHER_LOG")) ctx->dist_fri_gather_log = (unsigned)std::min(24, std::max(4, atoi(e)));
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
@@ -633,10 +635,21 @@ static void prestage_clear(bfgpu_ctx* ctx) {
     ctx->prestaged.clear();
 }
 
+// Transpose fused with the first inverse NTT pass (defined with the NTT orchestration below); *done = false: not applicable, nothing launched
+static int32_t ingest_first_pass(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows, uint32_t cols, uint32_t* dst, uint64_t pitch, bool* done);
+
 // row-major device words in the caller's representation -> column-major Montgomery words at dst
-static int32_t ingest_device(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows, uint32_t cols, bool bitrev, uint32_t* dst, uint64_t src_pitch = 0) {
+// first_pass_done != null (bit-reversed ingest feeding an inverse transform): the first inverse pass may be executed on the way
+// (*first_pass_done = true), in which case the caller runs the transform with skip_first.
+static int32_t ingest_device(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows, uint32_t cols, bool bitrev, uint32_t* dst, uint64_t src_pitch = 0,
+                             bool* first_pass_done = nullptr) {
     Phase ph(ctx, BFGPU_PHASE_INGEST);
     const uint64_t pitch = src_pitch ? src_pitch : cols;
+    if (first_pass_done) {
+        *first_pass_done = false;
+        if (bitrev) TRY(ingest_first_pass(ctx, src, rows, cols, dst, pitch, first_pass_done));
+        if (*first_pass_done) return BFGPU_OK;
+    }
     if (rows >= 128 && rows % 128 == 0 && cols % 4 == 0 && pitch % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
         dim3 grid((unsigned)(rows / 128), (unsigned)((cols + 31) / 32));
         nttk::k_ingest_wide<<<grid, 256, 0, ctx->stream>>>(src, dst, rows, cols, ilog2(rows), bitrev ? 1 : 0, ctx->repr == BFGPU_REPR_CANONICAL, pitch);
@@ -649,7 +662,8 @@ static int32_t ingest_device(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows,
     return BFGPU_OK;
 }
 
-static int32_t ingest(bfgpu_ctx* ctx, const bfgpu_mat& m, bool bitrev, DMat* out) {
+static int32_t ingest(bfgpu_ctx* ctx, const bfgpu_mat& m, bool bitrev, DMat* out, bool* first_pass_done = nullptr) {
+    if (first_pass_done) *first_pass_done = false;
     out->rows = m.rows;
     out->cols = (uint32_t)m.cols;
     size_t bytes = (size_t)m.rows * m.cols * 4;
@@ -671,7 +685,7 @@ static int32_t ingest(bfgpu_ctx* ctx, const bfgpu_mat& m, bool bitrev, DMat* out
         }
         src = staged;
     }
-    int32_t rc = ingest_device(ctx, src, m.rows, (uint32_t)m.cols, bitrev, out->d);
+    int32_t rc = ingest_device(ctx, src, m.rows, (uint32_t)m.cols, bitrev, out->d, 0, first_pass_done);
     dfree(ctx, staged);
     return rc;
 }
@@ -840,6 +854,56 @@ static int32_t run_pass3(bfgpu_ctx* ctx, int mode, const uint32_t* src, uint64_t
     return BFGPU_OK;
 }
 
+
+template <int G1>
+static int32_t launch_ingest_pass(bfgpu_ctx* ctx, const CUtensorMap& tm, const ntt3::IngestArgs& a, dim3 grid) {
+    const bool canon = ctx->repr == BFGPU_REPR_CANONICAL;
+    const int key = 64 + G1 * 2 + (canon ? 1 : 0);
+    const size_t smem = ntt3::ingest_smem_bytes(G1);
+    if (!ctx->ntt3_configured.count(key)) {
+        if (canon) CU(cudaFuncSetAttribute(ntt3::k_ingest_pass<G1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CU(cudaFuncSetAttribute(ntt3::k_ingest_pass<G1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->ntt3_configured.insert(key);
+    }
+    if (canon) ntt3::k_ingest_pass<G1, true><<<grid, 1u << (G1 + 5), smem, ctx->stream>>>(tm, a);
+    else ntt3::k_ingest_pass<G1, false><<<grid, 1u << (G1 + 5), smem, ctx->stream>>>(tm, a);
+    return BFGPU_OK;
+}
+static int32_t ingest_first_pass(bfgpu_ctx* ctx, const uint32_t* src, uint64_t rows, uint32_t cols, uint32_t* dst, uint64_t pitch, bool* done) {
+    *done = false;
+    if (!ctx->ntt_tma || !ctx->ntt_ingest || !is_pow2(rows) || tmap_encoder() == nullptr) return BFGPU_OK;
+    const unsigned log_n = ilog2(rows);
+    if (log_n < 12 || log_n > (unsigned)kb::TWO_ADICITY || pitch % 4 != 0 || ((uintptr_t)src & 15) != 0 || ((uintptr_t)dst & 15) != 0) return BFGPU_OK;
+    const std::vector<bfgpu_ctx::NttPass>* plan = nullptr;
+    TRY(get_plan(ctx, log_n, true, &plan));
+    const auto& ps = plan->front();
+    if (ps.p != 0 || ps.g < 6 || ps.g > 8) return BFGPU_OK;
+    const unsigned g = ps.g;
+    // 3-d view [k = high g row bits][low row bits][column] of the row-major source; box = 32 columns x 1 x 2^g
+    CUtensorMap tm;
+    const cuuint64_t gdim[3] = {cols, 1ull << (log_n - g), 1ull << g};
+    const cuuint64_t gstride[2] = {pitch * 4, (pitch * 4) << (log_n - g)};
+    const cuuint32_t box[3] = {32, 1, 1u << g};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = tmap_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint32_t*>(src), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return BFGPU_OK;  // shapes the encoder refuses go through the two-kernel path
+    const uint32_t tiles = 1u << (log_n - g), nblk = (cols + 31) / 32;
+    // ~16 CTAs per SM over the launch, at most 64 tiles per CTA (twiddle loads and the ring start-up are paid once per CTA)
+    const uint32_t tpc = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, ((uint64_t)tiles * nblk) / (148u * 16)));
+    ntt3::IngestArgs a{dst, cols, tpc, log_n, ps.twA};
+    dim3 grid(nblk, (tiles + tpc - 1) / tpc);
+    switch (g - 4) {
+        case 2: TRY(launch_ingest_pass<2>(ctx, tm, a, grid)); break;
+        case 3: TRY(launch_ingest_pass<3>(ctx, tm, a, grid)); break;
+        default: TRY(launch_ingest_pass<4>(ctx, tm, a, grid)); break;
+    }
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    *done = true;
+    return BFGPU_OK;
+}
+
 template <bool INVERSE, int G1>
 static void launch_pass(bfgpu_ctx* ctx, const ntt2::PassArgs& a, dim3 grid) {
     if (INVERSE && a.pw != nullptr) {  // last inverse pass with the fused coset epilogue (always a strided pass: log_n >= 12)
@@ -868,14 +932,14 @@ constexpr unsigned NTT2_MIN_LOG = 12;
 
 template <bool INVERSE>
 static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsigned log_n, uint32_t ncols, CosetEpilogue epi = CosetEpilogue(),
-                       bool skip_last = false) {
+                       bool skip_last = false, bool skip_first = false) {
     if (log_n == 0 || ncols == 0) return BFGPU_OK;
     Phase ph(ctx, INVERSE ? BFGPU_PHASE_INTT : BFGPU_PHASE_NTT);
     if (log_n < NTT2_MIN_LOG) return run_ntt_small<INVERSE>(ctx, data, col_stride, log_n, ncols);
     const std::vector<bfgpu_ctx::NttPass>* plan = nullptr;
     TRY(get_plan(ctx, log_n, INVERSE, &plan));
     size_t np = plan->size() - (skip_last ? 1 : 0);  // skip_last: the top pass runs inside the TURN kernel of run_ntt_forward_dual
-    for (size_t s = 0; s < np; s++) {
+    for (size_t s = skip_first ? 1 : 0; s < np; s++) {  // skip_first (inverse): ntt3::k_ingest_pass has run the first pass already
         const auto& ps = (*plan)[INVERSE ? s : np - 1 - s];  // inverse DIT: low bits first; forward DIF: high bits first
         if (ntt3_usable(ctx, ps) && !(INVERSE && s + 1 == np && epi.pw)) {
             ntt3::PassArgs a3{0, 0, 0, 0, ps.twA, ps.twB, nullptr, nullptr, nullptr};
@@ -1010,8 +1074,9 @@ static int32_t coset_powers(bfgpu_ctx* ctx, unsigned log_n, unsigned added_bits,
 
 // coset LDE of a column-major device matrix whose rows are already in bit-reversed order (consumed) ->
 // column-major device matrix with bit-reversed rows.  shift_mont: Montgomery form of the coset shift.
+// first_pass_done: the first inverse pass has been executed by the fused ingest (ntt3::k_ingest_pass)
 static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, uint32_t shift_mont, DMat* out, bool consume = true,
-                               uint32_t* out_buf = nullptr) {
+                               uint32_t* out_buf = nullptr, bool first_pass_done = false) {
     unsigned log_n = ilog2(coef.rows);
     if (log_n + added_bits > kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
     uint64_t n = coef.rows, N = n << added_bits;
@@ -1024,7 +1089,7 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     else TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
     if (log_n >= NTT2_MIN_LOG && ncosets == 2 && ctx->ntt_dual) {
         // plain inverse transform; the coset scaling and the 2-fold expansion happen on load in the first forward pass
-        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols, CosetEpilogue(), ctx->ntt_turn));
+        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols, CosetEpilogue(), ctx->ntt_turn, first_pass_done));
         TRY(run_ntt_forward_dual(ctx, coef.d, out->d, pw, log_n, coef.cols, ctx->ntt_turn));
         if (consume) dfree(ctx, coef.d);  // stream order keeps it alive for the pass above
         return BFGPU_OK;
@@ -1035,9 +1100,9 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
         epi.pw = pw;
         epi.out = out->d;
         epi.ncosets = ncosets;
-        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols, epi));
+        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols, epi, false, first_pass_done));
     } else {
-        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols));
+        TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols, CosetEpilogue(), false, first_pass_done));
         Phase ph(ctx, BFGPU_PHASE_SCALE);
         dim3 grid((unsigned)((n + 255) / 256), coef.cols);
         nttk::k_scale_cosets<<<grid, 256, 0, ctx->stream>>>(coef.d, out->d, pw, n, ncosets, coef.cols);
@@ -1104,14 +1169,15 @@ static int32_t lde_device(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigned added_bit
     if (ilog2(m.rows) + added_bits > kb::TWO_ADICITY)
         return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity (2^%d)", ilog2(m.rows) + added_bits, kb::TWO_ADICITY);
     DMat coef;
-    TRY(ingest(ctx, m, /*bitrev=*/true, &coef));
+    bool first_pass_done = false;
+    TRY(ingest(ctx, m, /*bitrev=*/true, &coef, keep ? nullptr : &first_pass_done));  // a kept copy must be the plain transposed trace
     if (keep) {
         *keep = coef;
         size_t bytes = (size_t)coef.rows * coef.cols * 4;
         TRY(dalloc(ctx, (void**)&keep->d, bytes));
         CU(cudaMemcpyAsync(keep->d, coef.d, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    return lde_from_bitrev(ctx, coef, added_bits, shift_mont, out);
+    return lde_from_bitrev(ctx, coef, added_bits, shift_mont, out, true, nullptr, first_pass_done);
 }
 
 static int32_t coset_lde_batch_impl(bfgpu_ctx* ctx, const bfgpu_mat* mat, uint32_t added_bits, uint32_t shift, int bit_reversed_rows,
@@ -1537,19 +1603,20 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
         DMat coef, blk;
         coef.rows = R;
         coef.cols = cb;
+        bool first_pass_done = false;
         if ((rc = dalloc(ctx, (void**)&coef.d, R * cb * 4)) != BFGPU_OK) break;
         if (from_device) {
-            if ((rc = ingest_device(ctx, m.data + start[b], R, cb, /*bitrev=*/true, coef.d, W)) != BFGPU_OK) break;
+            if ((rc = ingest_device(ctx, m.data + start[b], R, cb, /*bitrev=*/true, coef.d, W, &first_pass_done)) != BFGPU_OK) break;
         } else {
             CU(cudaStreamWaitEvent(ctx->stream, ready[slot], 0));
-            if ((rc = ingest_device(ctx, staged[slot], R, cb, /*bitrev=*/true, coef.d)) != BFGPU_OK) break;
+            if ((rc = ingest_device(ctx, staged[slot], R, cb, /*bitrev=*/true, coef.d, 0, &first_pass_done)) != BFGPU_OK) break;
             CU(cudaEventRecord(consumed[slot], ctx->stream));
             // enqueue the copy after next only now: its wait on consumed[slot] must see this record
             if (b + 1 < nb && b == 0) rc = copy_block(1);
             if (rc == BFGPU_OK && b + 2 < nb) rc = copy_block(b + 2);
             if (rc != BFGPU_OK) break;
         }
-        if ((rc = lde_from_bitrev(ctx, coef, added_bits, shift_mont, &blk, /*consume=*/true, lde->d + (uint64_t)start[b] * N)) != BFGPU_OK) break;
+        if ((rc = lde_from_bitrev(ctx, coef, added_bits, shift_mont, &blk, /*consume=*/true, lde->d + (uint64_t)start[b] * N, first_pass_done)) != BFGPU_OK) break;
         Phase ph(ctx, BFGPU_PHASE_LEAF);
         cudaStream_t hs = ctx->stream;
         if (from_device) {  // sponge on the second stream, behind this block's LDE

@@ -20,6 +20,23 @@ struct Challenges {
     kb::Ext cumulative_sum;
 };
 
+// Extension products / inversions of the generated programs.  Inlined, the Cpu constraint program is ~100 KB of straight-line
+// SASS (48 products of ~140 instructions each) and the warps of an SM, all at different places in it, stall on instruction fetch
+// (ncu r2: stall_no_instruction 3.8 / 5.2 warps per issue slot in k_quotient<Cpu> / k_perm_rows<Cpu>, the top stall reason);
+// as calls to ONE copy of the product the program is a few KB and the product's body stays in the instruction cache.
+#ifndef BFGPU_AIR_NOINLINE
+#define BFGPU_AIR_NOINLINE 1
+#endif
+#if BFGPU_AIR_NOINLINE
+__device__ __noinline__ kb::Ext ext_mul_call(kb::Ext a, kb::Ext b) { return kb::ext_mul(a, b); }
+__device__ __noinline__ kb::Ext ext_inv_call(kb::Ext a) { return kb::ext_inv(a); }
+#define AIR_EXT_MUL air::ext_mul_call
+#define AIR_EXT_INV air::ext_inv_call
+#else
+#define AIR_EXT_MUL kb::ext_mul
+#define AIR_EXT_INV kb::ext_inv
+#endif
+
 }  // namespace air
 #include "gen_air.cuh"
 

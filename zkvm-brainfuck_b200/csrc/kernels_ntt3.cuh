@@ -282,4 +282,135 @@ __global__ void __launch_bounds__(1 << (G1 + 5), G1 >= 4 ? 1 : ((MODE == TURN ? 
     if (lane == 0) bulk_wait_all();  // shared memory must outlive the stores
 }
 
+
+// ---- ingest fused with the first inverse pass ---------------------------------------------------------------------------------
+// `Pcs::commit` receives row-major matrices (RowMajorMatrix<Val>, reference crates/stark/src/prover.rs:227); the device layout is
+// column-major with bit-reversed rows.  The stand-alone transpose (nttk::k_ingest_wide: 8 B of HBM traffic per element) and the
+// first inverse pass (contiguous, stage bits [0, g): another 8 B) both stream the whole matrix; here one kernel does both:
+//   * a tile is 2^g stored positions x 32 COLUMNS.  Stored position base + d holds natural row brev(base + d), so the tile's rows
+//     are the 2^g natural rows  k * 2^(log_n - g) + brev(base >> g),  k < 2^g: a TMA box (32 columns, 1, 2^g) of the 3-d view
+//     [k][row low bits][column] of the caller's matrix, landing as a dense [k][32] tile with d = brev_g(k);
+//   * both register phases run in place on that tile exactly like the contiguous pass of ntt2::k_pass (lane = column);
+//   * the result goes through a padded [column][2^g + 1] staging tile so that each warp stores whole 128-byte runs of a column.
+// CANON: caller words are canonical residues (converted to Montgomery form on load) instead of Montgomery words.
+struct IngestArgs {
+    uint32_t* dst;        // column-major coefficients-in-progress: column c at dst + c * n
+    uint32_t ncols;       // columns of the matrix
+    uint32_t tiles_per_cta;   // tiles (of 2^g stored positions) a CTA walks through for its 32-column block
+    uint32_t log_n;
+    const TWT* twA;       // phase-A table of the contiguous inverse pass: [(2^G1 - 1)][16]
+};
+constexpr int INGEST_SLOTS = 2;  // 2 x 32 KB + 33 KB of staging at g = 8: two CTAs of 512 threads per SM
+constexpr size_t ingest_smem_bytes(int G1) {
+    return (size_t)INGEST_SLOTS * ((size_t)4 << (G1 + 4 + 5)) + (size_t)32 * ((1 << (G1 + 4)) + 1) * 4 + INGEST_SLOTS * sizeof(uint64_t) + 16;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ constexpr uint32_t brev_c(uint32_t x, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+template <int G1, bool CANON>
+__global__ void __launch_bounds__(1 << (G1 + 5), 1) k_ingest_pass(const __grid_constant__ CUtensorMap tm_src, IngestArgs A) {
+    static_assert(G1 >= 1 && G1 <= 4, "two register phases");
+    constexpr int g = G1 + G2, NT = 1 << (g + 1), ND = 1 << g;
+    constexpr int RA = 1 << G1, NGA = 16 >> G1;
+    constexpr int TILE = ND * LANES, PITCH = ND + 1;
+    uint32_t* const s_slot = smem3;                        // [INGEST_SLOTS][TILE]
+    uint32_t* const s_out = smem3 + INGEST_SLOTS * TILE;   // [32][PITCH]
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem3 + INGEST_SLOTS * TILE + ((32 * PITCH + 3) & ~3));
+
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint64_t n = 1ull << A.log_n;
+    // A CTA keeps ONE 32-column block (blockIdx.x) and walks through tiles_per_cta tiles.  Tile index = low bits of the natural rows,
+    // so the CTAs dispatched together (consecutive blockIdx.x) read the neighbouring 128-byte segments of the SAME rows of the
+    // row-major source at about the same time (one DRAM page per row instead of one per segment), and consecutive iterations read
+    // consecutive rows; the tile's stored position is brev(tile), which costs nothing: a tile is written as whole 1 KB runs.
+    const uint32_t ntiles_all = 1u << (A.log_n - g);
+    const uint32_t t_begin = blockIdx.y * A.tiles_per_cta;
+    const uint32_t t_end = min(ntiles_all, t_begin + A.tiles_per_cta);
+    if (t_begin >= t_end) return;
+    const uint32_t nblk = t_end - t_begin;  // iterations
+    const uint32_t col0 = blockIdx.x << 5;
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < INGEST_SLOTS; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    __syncthreads();
+    auto issue = [&](uint32_t i) {
+        const uint32_t s = i % INGEST_SLOTS;
+        mbar_expect_tx(&full[s], TILE * 4);
+        tma_load_3d(s_slot + s * TILE, &tm_src, &full[s], (int)col0, (int)(t_begin + i), 0);
+    };
+    if (t == 0) {
+#pragma unroll
+        for (uint32_t s = 0; s < (uint32_t)INGEST_SLOTS; s++)
+            if (s < nblk) issue(s);
+    }
+    // phase B: thread (aB = warp, lane) owns digits (aB << 4) | b  = tile rows  brev4(b) << G1 | brev_G1(aB)
+    const uint32_t offB = ((__brev(warp) >> (32 - G1)) << 5) + lane;
+    // phase A: combo j: r1 = (t + j NT) >> 5 owns digits (a << 4) | r1 = tile rows  brev4(r1) << G1 | brev_G1(a)
+    uint32_t offA[NGA], r1A[NGA];
+#pragma unroll
+    for (int j = 0; j < NGA; j++) {
+        r1A[j] = (t + j * NT) >> 5;
+        offA[j] = (((__brev(r1A[j]) >> 28) << G1) << 5) + lane;
+    }
+    TWT twa[15];
+#pragma unroll
+    for (int j = 0; j < NGA; j++)
+#pragma unroll
+        for (int q = 1; q < RA; q++) twa[j * (RA - 1) + q - 1] = A.twA[(q - 1) * 16 + r1A[j]];
+    auto twA = [&](int i) { return twa[i]; };
+    auto twB = [&](int) { return TWT(); };
+
+    uint32_t v[16];
+    for (uint32_t i = 0; i < nblk; i++) {
+        uint32_t* const S = s_slot + (i % INGEST_SLOTS) * TILE;
+        while (!mbar_try_wait(&full[i % INGEST_SLOTS], (i / INGEST_SLOTS) & 1)) {
+        }
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const uint32_t x = S[offB + ((brev_c(b, 4) << G1) << 5)];
+            v[b] = CANON ? kb::to_mont(x) : x;
+        }
+        phase<true, G2, false>(v, twB);
+#pragma unroll
+        for (int b = 0; b < 16; b++) S[offB + ((brev_c(b, 4) << G1) << 5)] = v[b];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) v[j * RA + a] = S[offA[j] + (brev_c(a, G1) << 5)];
+        phase<true, G1, true>(v, twA);
+        // staging: [column = lane][digit], pitch 2^g + 1: conflict free here and in the row reads below
+#pragma unroll
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) s_out[lane * PITCH + ((uint32_t)a << G2) + r1A[j]] = v[j * RA + a];
+        __syncthreads();
+        if (t == 0 && i + INGEST_SLOTS < nblk) issue(i + INGEST_SLOTS);  // the slot was last read before the barrier above
+        // warp w stores columns w, w + NT/32, ... of the block: runs of 32 consecutive words
+        const uint32_t tile = t_begin + i;
+        const uint64_t base = (uint64_t)(A.log_n > (unsigned)g ? __brev(tile) >> (32 - (A.log_n - g)) : 0u) << g;  // first stored position of the tile
+#pragma unroll
+        for (int cc = 0; cc < 32 / (NT / 32); cc++) {
+            const uint32_t c = warp + cc * (NT / 32);
+            if (col0 + c < A.ncols) {
+                uint32_t* o = A.dst + (uint64_t)(col0 + c) * n + base + lane;
+#pragma unroll
+                for (int k = 0; k < ND / 32; k++) o[k * 32] = s_out[c * PITCH + k * 32 + lane];
+            }
+        }
+    }
+}
+
 }  // namespace ntt3
