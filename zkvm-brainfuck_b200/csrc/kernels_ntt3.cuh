@@ -316,7 +316,7 @@ __device__ __forceinline__ constexpr uint32_t brev_c(uint32_t x, int bits) {
 }
 
 template <int G1, bool CANON>
-__global__ void __launch_bounds__(1 << (G1 + 5), 1) k_ingest_pass(const __grid_constant__ CUtensorMap tm_src, IngestArgs A) {
+__global__ void __launch_bounds__(1 << (G1 + 5), 1024 >> (G1 + 5)) k_ingest_pass(const __grid_constant__ CUtensorMap tm_src, IngestArgs A) {
     static_assert(G1 >= 1 && G1 <= 4, "two register phases");
     constexpr int g = G1 + G2, NT = 1 << (g + 1), ND = 1 << g;
     constexpr int RA = 1 << G1, NGA = 16 >> G1;
