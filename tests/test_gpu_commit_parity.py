@@ -77,13 +77,51 @@ def test_dft_and_idft(ctx, oracle, log_n, cols):
 
 
 @pytest.mark.parametrize("log_n,cols,added,shift", [(0, 2, 1, 3), (1, 3, 1, 3), (3, 1, 1, 3), (4, 5, 1, 3), (4, 5, 2, 3), (6, 12, 1, 3),
-                                                  (9, 36, 1, 3), (10, 3, 1, 7), (12, 41, 1, 3), (15, 4, 1, 3), (18, 2, 1, 3)])
+                                                  (9, 36, 1, 3), (10, 3, 1, 7), (12, 41, 1, 3), (15, 4, 1, 3), (18, 2, 1, 3),
+                                                  # round 2: every instantiation of the TMA passes (kernels_ntt3.cuh).  Pass plans: 13 = 7+6,
+                                                  # 14 = 7+7, 16 = 8+8, 17 = 6+6+5, 19 = 7+6+6, 20 = 7+7+6; widths with a pitch that is a multiple
+                                                  # of four take the fused ingest + first inverse pass (k_ingest_pass, g = 6, 7, 8), with whole
+                                                  # and partial 32-column boxes; the others the stand-alone transpose
+                                                  (13, 64, 1, 3), (14, 33, 1, 3), (14, 96, 1, 3), (16, 5, 1, 3), (16, 32, 1, 7), (17, 36, 1, 3),
+                                                  (19, 8, 1, 3), (20, 4, 1, 3), (13, 12, 2, 3)])
 def test_coset_lde(ctx, oracle, log_n, cols, added, shift):
     rng = np.random.default_rng(200 + log_n)
     m = rand_mat(rng, 1 << log_n, cols)
     dft = bf.Radix2Dit(ctx)
     assert (dft.coset_lde_batch(m, added, shift) == oracle.coset_lde_batch(m, added, shift)).all()
     assert (dft.coset_lde_batch(m, added, shift, bit_reversed_rows=True) == oracle.coset_lde_batch_bitrev(m, added, shift)).all()
+
+
+@pytest.mark.parametrize("env", [{"BFGPU_NTT_TMA": "0"}, {"BFGPU_NTT_TMA": "0", "BFGPU_NTT_TURN": "0"}, {"BFGPU_NTT_TURN": "0"},
+                                 {"BFGPU_NTT_INGEST": "0"}, {"BFGPU_NTT_CFWD": "1"}, {"BFGPU_NTT_TMA": "0", "BFGPU_NTT_DUAL": "0"}])
+def test_coset_lde_kernel_switches(oracle, env, monkeypatch):
+    """The NTT kernel families behind the run-time switches (register-prefetching ntt2 passes, unfused turn, separate transpose,
+    round-1 epilogue path) produce the same LDE; a context reads the switches when it is created."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c = bf.Context()
+    try:
+        dft = bf.Radix2Dit(c)
+        for log_n, cols in [(13, 40), (16, 8), (17, 4)]:
+            m = rand_mat(np.random.default_rng(300 + log_n), 1 << log_n, cols)
+            assert (dft.coset_lde_batch(m, 1, 3, bit_reversed_rows=True) == oracle.coset_lde_batch_bitrev(m, 1, 3)).all(), (env, log_n, cols)
+    finally:
+        c.close()
+
+
+def test_coset_lde_montgomery_repr_fused_ingest(oracle):
+    """Montgomery-form caller words (what a Rust `Vec<KoalaBear>` holds) through the fused ingest + first inverse pass (no conversion on load)."""
+    R32 = (1 << 32) % P
+    rinv = pow(R32, P - 2, P)
+    c = bf.Context(repr=bf.REPR_MONTY)
+    try:
+        for log_n, cols in [(13, 64), (16, 36)]:
+            m = rand_mat(np.random.default_rng(400 + log_n), 1 << log_n, cols)
+            mm = (m.astype(np.uint64) * np.uint64(R32) % np.uint64(P)).astype(np.uint32)
+            out = bf.Radix2Dit(c).coset_lde_batch(mm, 1, R32 * 3 % P, bit_reversed_rows=True)
+            assert ((out.astype(np.uint64) * np.uint64(rinv) % np.uint64(P)) == oracle.coset_lde_batch_bitrev(m, 1, 3)).all()
+    finally:
+        c.close()
 
 
 def test_coset_lde_against_definition(ctx):

@@ -104,6 +104,9 @@ struct bfgpu_ctx {
     std::vector<std::vector<void*>*> scopes;
     // transcript options (bfgpu_set_transcript_option): the choices inside Plonky3 that cannot be confirmed offline (SURVEY.md P3 marks)
     uint32_t opt[BFGPU_NUM_OPTS] = {1, 0, 0};
+    bool ntt_cfwd = false;  // contiguous forward pass through bulk copies (ntt3::k_cfwd, $BFGPU_NTT_CFWD=1).  MEASURED SLOWER than ntt2::k_pass
+                            // at 2^22 x 256 (3.79 vs 3.61 ms: two CTA barriers per column and 512-thread CTAs cost more than the LDG.32
+                            // address arithmetic saves), so it stays off; parity-tested behind the switch
     bool ntt_ingest = true;  // row-major input -> first inverse pass in one kernel (ntt3::k_ingest_pass); $BFGPU_NTT_INGEST=0: transpose, then pass
     bool ntt_tma = true;   // strided NTT passes through the TMA-fed 32-lane kernels (kernels_ntt3.cuh); $BFGPU_NTT_TMA=0: ntt2::k_pass
     std::set<int> ntt3_configured;  // (mode, G1) instantiations whose dynamic shared-memory limit has been raised on this device
@@ -338,6 +341,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (const char* e = getenv("BFGPU_NTT_TURN")) ctx->ntt_turn = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_NTT_TMA")) ctx->ntt_tma = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_NTT_INGEST")) ctx->ntt_ingest = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_NTT_CFWD")) ctx->ntt_cfwd = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_DIST_MIN_CHUNK")) ctx->dist_min_chunk = (uint32_t)std::max(8, atoi(e)) / 8 * 8;
     if (const char* e = getenv("BFGPU_DIST_FRI_GATHER_LOG")) ctx->dist_fri_gather_log = (unsigned)std::min(24, std::max(4, atoi(e)));
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
@@ -855,6 +859,39 @@ static int32_t run_pass3(bfgpu_ctx* ctx, int mode, const uint32_t* src, uint64_t
 }
 
 
+
+// Contiguous forward pass (p = 0) through the bulk-copy kernel ntt3::k_cfwd
+template <int G1>
+static int32_t launch_cfwd(bfgpu_ctx* ctx, const ntt3::CfwdArgs& a, dim3 grid) {
+    const int key = 128 + G1;
+    if (!ctx->ntt3_configured.count(key)) {
+        CU(cudaFuncSetAttribute(ntt3::k_cfwd<G1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt3::cfwd_smem_bytes(G1)));
+        ctx->ntt3_configured.insert(key);
+    }
+    ntt3::k_cfwd<G1><<<grid, 1u << (G1 + 5), ntt3::cfwd_smem_bytes(G1), ctx->stream>>>(a);
+    return BFGPU_OK;
+}
+static bool cfwd_usable(bfgpu_ctx* ctx, const bfgpu_ctx::NttPass& ps, unsigned log_n, const uint32_t* data, uint64_t col_stride) {
+    return ctx->ntt_tma && ctx->ntt_cfwd && ps.p == 0 && ps.g >= 5 && ps.g <= 8 && log_n >= ps.g + 5 && ((uintptr_t)data & 15) == 0 && col_stride % 4 == 0;
+}
+static int32_t run_cfwd(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, uint32_t ncols, unsigned log_n, const bfgpu_ctx::NttPass& ps) {
+    const uint32_t tiles = 1u << (log_n - ps.g - 5);
+    const uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
+    uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, ncols), (ncols + want_groups - 1) / want_groups);
+    cpc = std::min<uint32_t>(cpc, 64);
+    ntt3::CfwdArgs a{data, col_stride, ncols, cpc, ps.twA};
+    dim3 grid(tiles, (ncols + cpc - 1) / cpc);
+    switch (ps.g - 4) {
+        case 1: TRY(launch_cfwd<1>(ctx, a, grid)); break;
+        case 2: TRY(launch_cfwd<2>(ctx, a, grid)); break;
+        case 3: TRY(launch_cfwd<3>(ctx, a, grid)); break;
+        default: TRY(launch_cfwd<4>(ctx, a, grid)); break;
+    }
+    LAUNCHED(ctx);
+    CU(cudaGetLastError());
+    return BFGPU_OK;
+}
+
 template <int G1>
 static int32_t launch_ingest_pass(bfgpu_ctx* ctx, const CUtensorMap& tm, const ntt3::IngestArgs& a, dim3 grid) {
     const bool canon = ctx->repr == BFGPU_REPR_CANONICAL;
@@ -941,6 +978,10 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
     size_t np = plan->size() - (skip_last ? 1 : 0);  // skip_last: the top pass runs inside the TURN kernel of run_ntt_forward_dual
     for (size_t s = skip_first ? 1 : 0; s < np; s++) {  // skip_first (inverse): ntt3::k_ingest_pass has run the first pass already
         const auto& ps = (*plan)[INVERSE ? s : np - 1 - s];  // inverse DIT: low bits first; forward DIF: high bits first
+        if (!INVERSE && cfwd_usable(ctx, ps, log_n, data, col_stride)) {
+            TRY(run_cfwd(ctx, data, col_stride, ncols, log_n, ps));
+            continue;
+        }
         if (ntt3_usable(ctx, ps) && !(INVERSE && s + 1 == np && epi.pw)) {
             ntt3::PassArgs a3{0, 0, 0, 0, ps.twA, ps.twB, nullptr, nullptr, nullptr};
             TRY(run_pass3(ctx, INVERSE ? ntt3::INV : ntt3::FWD, data, col_stride, ncols, log_n, ps, a3));
@@ -988,6 +1029,10 @@ static int32_t run_ntt_forward_dual(bfgpu_ctx* ctx, const uint32_t* coef, uint32
         const auto& ps = (*plan)[np - 1 - s];  // forward DIF: high bits first
         const bool dual = s == 0;
         const uint32_t cols = dual ? ncols : 2 * ncols;
+        if (!dual && cfwd_usable(ctx, ps, log_n, out, n)) {
+            TRY(run_cfwd(ctx, out, n, cols, log_n, ps));
+            continue;
+        }
         if (ntt3_usable(ctx, ps) && (!dual || turn)) {  // (the DUAL pass without the inverse half exists only in ntt2::k_pass)
             ntt3::PassArgs a3{0, 0, 0, 0, ps.twA, ps.twB, nullptr, nullptr, nullptr};
             if (dual) {

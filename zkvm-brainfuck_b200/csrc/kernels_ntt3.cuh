@@ -413,4 +413,110 @@ __global__ void __launch_bounds__(1 << (G1 + 5), 1024 >> (G1 + 5)) k_ingest_pass
     }
 }
 
+// ---- contiguous forward pass (stage bits [0, g): the LAST pass of a forward transform) fed by bulk copies ----------------------------
+// A tile is 32 consecutive runs of 2^g words = one contiguous chunk of a column.  Each run travels by its own 1-d bulk copy
+// (`cp.async.bulk`, 2^g * 4 bytes, issued by lane `run` of warp 0) into a slot whose runs are 2^g + 4 words apart: with that pitch
+//   * phase A (thread = 4 low digits x 8 runs per warp; element a of the thread 16 words further) and
+//   * phase B (thread = 16 consecutive words of one run, 32 runs per warp, four 128-bit accesses)
+// are both free of bank conflicts, and both phases work in place.  The result leaves by 32 bulk copies of whole runs.
+// Ring of three slots: current, prefetched, being stored; the slot being stored is refilled one iteration later by the same lanes
+// that stored from it (each lane waits for its own store only).
+struct CfwdArgs {
+    uint32_t* data;       // first column, transformed in place
+    uint64_t col_stride;  // words between columns
+    uint32_t ncols;
+    uint32_t cols_per_cta;
+    const TWT* twA;       // phase-A table of the contiguous forward pass: [(2^G1 - 1)][16]
+};
+constexpr int CFWD_SLOTS = 3;
+constexpr size_t cfwd_smem_bytes(int G1) { return (size_t)CFWD_SLOTS * 32 * ((1 << (G1 + 4)) + 4) * 4 + 15 * 16 * sizeof(TWT) + CFWD_SLOTS * sizeof(uint64_t); }
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+template <int G1>
+__global__ void __launch_bounds__(1 << (G1 + 5), 1024 >> (G1 + 5)) k_cfwd(CfwdArgs A) {
+    static_assert(G1 >= 1 && G1 <= 4, "two register phases");
+    constexpr int g = G1 + G2, NT = 1 << (g + 1), ND = 1 << g;
+    constexpr int RA = 1 << G1, NGA = 16 >> G1;
+    constexpr int PITCH = ND + 4, SLOT = 32 * PITCH;
+    uint32_t* const s_slot = smem3;                                                      // [CFWD_SLOTS][32][PITCH]
+    TWT(*const s_tw)[16] = reinterpret_cast<TWT(*)[16]>(smem3 + CFWD_SLOTS * SLOT);      // [15][16]
+    uint64_t* const full = reinterpret_cast<uint64_t*>(s_tw + 15);                        // [CFWD_SLOTS]
+
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint64_t base = (uint64_t)blockIdx.x << (g + 5);  // first word of the chunk inside a column
+    const uint32_t c_begin = blockIdx.y * A.cols_per_cta;
+    const uint32_t c_end = min(A.ncols, c_begin + A.cols_per_cta);
+    if (c_begin >= c_end) return;
+    const uint32_t ncol = c_end - c_begin;
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < CFWD_SLOTS; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    for (uint32_t i = t; i < (RA - 1) * 16; i += NT) s_tw[i >> 4][i & 15] = A.twA[i];
+    __syncthreads();
+    auto issue = [&](uint32_t i) {  // warp 0, all lanes: run `lane` of the i-th column of this CTA into slot i % CFWD_SLOTS
+        const uint32_t s = i % CFWD_SLOTS;
+        if (lane == 0) mbar_expect_tx(&full[s], 32 * ND * 4);
+        __syncwarp();
+        bulk_load_1d(s_slot + s * SLOT + lane * PITCH, A.data + (uint64_t)(c_begin + i) * A.col_stride + base + (lane << g), ND * 4, &full[s]);
+    };
+    if (warp == 0) {
+        if (0 < ncol) issue(0);
+        if (1 < ncol) issue(1);
+    }
+    // phase A combos: cidx = t + j NT -> digit low part r1 = (cidx >> 5 & 3) * 4 + (cidx & 3), run = (cidx >> 7) * 8 + (cidx >> 2 & 7)
+    uint32_t offA[NGA], r1A[NGA];
+#pragma unroll
+    for (int j = 0; j < NGA; j++) {
+        const uint32_t cidx = t + j * NT;
+        r1A[j] = (((cidx >> 5) & 3) << 2) | (cidx & 3);
+        offA[j] = (((cidx >> 7) << 3) | ((cidx >> 2) & 7)) * PITCH + r1A[j];
+    }
+    const uint32_t offB = lane * PITCH + (warp << 4);  // phase B: run = lane, digits warp * 16 + b
+    uint32_t v[16];
+    for (uint32_t i = 0; i < ncol; i++) {
+        uint32_t* const S = s_slot + (i % CFWD_SLOTS) * SLOT;
+        while (!mbar_try_wait(&full[i % CFWD_SLOTS], (i / CFWD_SLOTS) & 1)) {
+        }
+#pragma unroll
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) v[j * RA + a] = S[offA[j] + (a << G2)];
+        // flat twiddle index of ntt2::phase = group * (RA - 1) + (q - 1); the table is indexed by the group's low digit part
+        phase<false, G1, true>(v, [&](int k) { return s_tw[k % (RA - 1)][r1A[k / (RA - 1)]]; });
+#pragma unroll
+        for (int j = 0; j < NGA; j++)
+#pragma unroll
+            for (int a = 0; a < RA; a++) S[offA[j] + (a << G2)] = v[j * RA + a];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint4 x = *reinterpret_cast<const uint4*>(S + offB + 4 * k);
+            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+        }
+        phase<false, G2, false>(v, [&](int) { return TWT(); });
+#pragma unroll
+        for (int k = 0; k < 4; k++) *reinterpret_cast<uint4*>(S + offB + 4 * k) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        fence_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            bulk_store_1d(A.data + (uint64_t)(c_begin + i) * A.col_stride + base + (lane << g), S + lane * PITCH, ND * 4);
+            bulk_commit();
+            bulk_wait_read<1>();  // this lane's store of column i-1 has left its slot: refill it with column i+2
+            if (i + 2 < ncol) issue(i + 2);
+        }
+    }
+    if (warp == 0) bulk_wait_all();
+}
+
 }  // namespace ntt3
