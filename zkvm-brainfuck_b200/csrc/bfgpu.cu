@@ -84,6 +84,8 @@ struct bfgpu_ctx {
     // the host source may die right after the call (upload_small)
     uint8_t* ring = nullptr;
     size_t ring_size = 0, ring_pos = 0;
+    uint32_t top_x1_max = 0;  // cluster tops: levels of at most this many nodes per CTA use the one-thread permutation ($BFGPU_TOP_X1_MAX); MEASURED: every setting > 0 is slower (hello 3.65 ms at 0, 3.74 at 1, 3.87 at 64): the four-lane chain is the shorter one
+    bool top_cluster = true;  // tree tops of >= 256 digests on an 8-CTA cluster (hashk::k_compress_top_cluster); $BFGPU_TOP_CLUSTER=0: one CTA
     uint64_t x4_layer_max = 1u << 15;  // Merkle layers up to this many nodes use k_compress_layer_x4 ($BFGPU_X4_MAX)
     // opening points evaluated per pass over a matrix; one pass per point ($BFGPU_BARY_POINTS=1, 66 instead of 110 registers but the
     // matrix read twice) measured slower: open_eval 2.91 vs 2.51 ms at 2^22 rows
@@ -342,6 +344,8 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (const char* e = getenv("BFGPU_NTT_TMA")) ctx->ntt_tma = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_NTT_INGEST")) ctx->ntt_ingest = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_NTT_CFWD")) ctx->ntt_cfwd = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_TOP_CLUSTER")) ctx->top_cluster = atoi(e) != 0;
+    if (const char* e = getenv("BFGPU_TOP_X1_MAX")) ctx->top_x1_max = (uint32_t)atoi(e);
     if (const char* e = getenv("BFGPU_DIST_MIN_CHUNK")) ctx->dist_min_chunk = (uint32_t)std::max(8, atoi(e)) / 8 * 8;
     if (const char* e = getenv("BFGPU_DIST_FRI_GATHER_LOG")) ctx->dist_fri_gather_log = (unsigned)std::min(24, std::max(4, atoi(e)));
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
@@ -1472,7 +1476,12 @@ static int32_t build_tree(bfgpu_ctx* ctx, std::vector<DMat> mats, bool owns, bfg
         dfree(ctx, (void*)colptr);
     }
     if (top.nlevels) {
-        hashk::k_compress_top<<<1, hashk::TOP_THREADS, 0, ctx->stream>>>(top);
+        top.x1_max = ctx->top_x1_max;
+        // wide tops run on a cluster of 8 CTAs (their first levels are bound by one SM's issue rate), narrow ones on one CTA
+        if (ctx->top_cluster && top.len0 >= (uint32_t)hashk::TOPC_MIN_LEN0 && top.nlevels == ilog2(top.len0))
+            hashk::k_compress_top_cluster<<<hashk::TOPC_CLUSTER, hashk::TOPC_THREADS, 0, ctx->stream>>>(top);
+        else
+            hashk::k_compress_top<<<1, hashk::TOP_THREADS, 0, ctx->stream>>>(top);
         LAUNCHED(ctx);
         CU(cudaGetLastError());
         for (void* p : colptrs_to_free) dfree(ctx, p);

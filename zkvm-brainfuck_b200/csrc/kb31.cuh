@@ -60,6 +60,15 @@ KB_HD void mac(uint64_t& acc, uint32_t a, uint32_t b) {
     hi = umin_(hi, hi - P);
     acc = ((uint64_t)hi << 32) | (uint32_t)acc;
 }
+// Two products per conditional subtraction: acc < 2^32 p and 2 p^2 < 0.4923 * 2^64 keep the sum below 2^64, and one subtraction of
+// 2^32 p brings it back under 2^32 p (0.9884 - 0.4961 < 0.4961): one add/min per TWO terms of a long dot product.
+KB_HD void mac2(uint64_t& acc, uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1) {
+    acc += (uint64_t)a0 * b0;
+    acc += (uint64_t)a1 * b1;
+    uint32_t hi = (uint32_t)(acc >> 32);
+    hi = umin_(hi, hi - P);
+    acc = ((uint64_t)hi << 32) | (uint32_t)acc;
+}
 // Montgomery product.  Exact for a in [0, 2^32), b in [0, p): result in [0, p).
 KB_HD uint32_t mul(uint32_t a, uint32_t b) { return mont_reduce((uint64_t)a * b); }
 KB_HD uint32_t sqr(uint32_t a) { return mul(a, a); }

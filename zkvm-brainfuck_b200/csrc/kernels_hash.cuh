@@ -166,6 +166,7 @@ struct TopArgs {
     uint32_t row_stride[TOP_LEVELS];
     uint32_t len0;
     uint32_t nlevels;
+    uint32_t x1_max;  // cluster kernel: levels with at most this many nodes per CTA use one thread per node (0: always four lanes)
 };
 // Levels with at most TOP_THREADS / 4 nodes run the four-lane permutation (p2::permute_x4): a level costs one
 // permutation LATENCY whatever its width, and the four-lane form has a third of the dependent chain.
@@ -247,6 +248,124 @@ __global__ void __launch_bounds__(TOP_THREADS) k_compress_top(TopArgs A) {
             for (int w = 0; w < 8; w++) cur[8 * i + w] = s[w];
         }
         __syncthreads();
+    }
+}
+
+// ---- the same top of the tree on a CLUSTER of 8 CTAs (8 SMs) -------------------------------------------------------------------------
+// k_compress_top runs on ONE SM, and its wide levels are bound by that SM's issue rate, not by latency: 512 + 256 + 128 permutations
+// are ~26 us of the ~40 us a 1024-digest top takes (ncu launch list of a small proof: 14 launches x 85 us = 31 % of the proof).
+// Here CTA r of an 8-CTA thread-block cluster reduces digests [r * len0/8, (r+1) * len0/8) to one digest with the four-lane
+// permutation (every level of its subtree fits 256 threads), the cluster synchronises once (barrier.cluster, release/acquire at cluster
+// scope, so the digests written to global memory are visible), and CTA 0 finishes the last three levels.  Each level is written to
+// its global array exactly as k_compress_top does.
+constexpr int TOPC_CLUSTER = 8, TOPC_THREADS = 256, TOPC_MIN_LEN0 = 256;
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// one level with four lanes per node: nodes [0, len) of this CTA are global nodes node0 + i of level k; cur holds the 2 len children
+__device__ __forceinline__ void top_level_x4(const TopArgs& A, uint32_t k, uint32_t* cur, uint32_t len, uint32_t node0, const p2::X4& xc, int q, uint32_t t) {
+    const uint32_t i = t >> 2;
+    const bool warp_on = ((t & ~31u) >> 2) < len, on = i < len;  // whole warps without a node skip the level
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (on) {
+        uint4 x = *reinterpret_cast<const uint4*>(cur + 16 * i + 4 * q);
+        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+    }
+    __syncthreads();  // everyone has read its pair before the layer is overwritten
+    if (warp_on) {
+        p2::permute_x4(w, xc, q);
+        if (A.ncols[k]) {
+            uint32_t h[4] = {0, 0, 0, 0};
+            const uint32_t nc = A.ncols[k];
+            for (uint32_t c0 = 0; c0 < nc; c0 += 8) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t c = c0 + 4 * q + j;
+                    if (on && q < 2 && c < nc) h[j] = __ldg(A.colptr[k][c] + (uint64_t)(node0 + i) * A.row_stride[k]);
+                }
+                p2::permute_x4(h, xc, q);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t from_low = __shfl_xor_sync(0xffffffffu, h[j], 2);
+                if (q >= 2) w[j] = from_low;
+            }
+            p2::permute_x4(w, xc, q);
+        }
+        if (on && q < 2) {
+            uint4 o = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(A.out[k] + 8 * (uint64_t)(node0 + i) + 4 * q) = o;
+            *reinterpret_cast<uint4*>(cur + 8 * i + 4 * q) = o;
+        }
+    }
+    __syncthreads();
+}
+// one level with ONE thread per node (len <= TOPC_THREADS): no shuffles; with at most one warp per scheduler the dependent chain of
+// the plain permutation is shorter than the four-lane form's (whose every round pays two shuffle latencies)
+__device__ __forceinline__ void top_level_x1(const TopArgs& A, uint32_t k, uint32_t* cur, uint32_t len, uint32_t node0, uint32_t t) {
+    uint32_t s[16];
+    const bool on = t < len;
+    if (on) {
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            uint4 x = *reinterpret_cast<const uint4*>(cur + 16 * t + 4 * w);
+            s[4 * w] = x.x; s[4 * w + 1] = x.y; s[4 * w + 2] = x.z; s[4 * w + 3] = x.w;
+        }
+    }
+    __syncthreads();  // everyone has read its pair before the layer is overwritten
+    if (on) {
+        p2::permute(s);
+        if (A.ncols[k]) {
+            uint32_t h[16];
+#pragma unroll
+            for (int w = 0; w < 16; w++) h[w] = 0;
+            sponge_rows(h, A.colptr[k], A.ncols[k], (uint64_t)(node0 + t) * A.row_stride[k]);
+#pragma unroll
+            for (int w = 0; w < 8; w++) s[8 + w] = h[w];
+            p2::permute(s);
+        }
+        store_digest(A.out[k] + 8 * (uint64_t)(node0 + t), s);
+        *reinterpret_cast<uint4*>(cur + 8 * t) = make_uint4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<uint4*>(cur + 8 * t + 4) = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+    __syncthreads();
+}
+__global__ void __cluster_dims__(TOPC_CLUSTER, 1, 1) __launch_bounds__(TOPC_THREADS) k_compress_top_cluster(TopArgs A) {
+    __shared__ __align__(16) uint32_t cur[(TOP_MAX / TOPC_CLUSTER) * 8];
+    __shared__ uint32_t s_ext[8 * 16], s_int[16];
+    const uint32_t t = threadIdx.x, rank = cluster_cta_rank();
+    const uint32_t seg = A.len0 / TOPC_CLUSTER;  // >= 32 digests per CTA, 4 * seg / 2 <= TOPC_THREADS
+    for (uint32_t i = t; i < seg * 2; i += TOPC_THREADS) reinterpret_cast<uint4*>(cur)[i] = reinterpret_cast<const uint4*>(A.in + (uint64_t)rank * seg * 8)[i];
+    if (t < 128) s_ext[t] = p2::c_p2.ext_s[t >> 4][t & 15];
+    if (t < 16) s_int[t] = p2::c_p2.internal_s[t];
+    __syncthreads();
+    const int q = t & 3;
+    const p2::X4 xc = p2::x4_setup(s_ext, s_int, q);
+    uint32_t k = 0, len = seg, node0 = rank * seg;
+    while (len > 1) {  // this CTA's subtree
+        len >>= 1;
+        node0 >>= 1;
+        if (len <= A.x1_max) top_level_x1(A, k, cur, len, node0, t);
+        else top_level_x4(A, k, cur, len, node0, xc, q, t);
+        k++;
+    }
+    __threadfence();
+    cluster_sync_all();
+    if (rank != 0) return;
+    // CTA 0: the TOPC_CLUSTER subtree roots (level k - 1) -> root.  They were written by other SMs: read around L1.
+    if (t < TOPC_CLUSTER * 2) reinterpret_cast<uint4*>(cur)[t] = __ldcg(reinterpret_cast<const uint4*>(A.out[k - 1]) + t);
+    __syncthreads();
+    len = TOPC_CLUSTER;
+    while (k < A.nlevels) {
+        len >>= 1;
+        if (len <= A.x1_max) top_level_x1(A, k, cur, len, 0, t);
+        else top_level_x4(A, k, cur, len, 0, xc, q, t);
+        k++;
     }
 }
 

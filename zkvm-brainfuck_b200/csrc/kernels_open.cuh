@@ -67,8 +67,32 @@ __device__ __forceinline__ void bary_dot_body(const uint32_t* __restrict__ mat, 
     const uint32_t* colp[BARY_COLS];
 #pragma unroll
     for (int c = 0; c < BARY_COLS; c++) colp[c] = mat + (uint64_t)min(c0 + c, ncols - 1) * col_stride;  // tail columns recompute the last one
-#pragma unroll BARY_UNROLL  // several rows of loads in flight: the kernel was latency bound (ncu: long_scoreboard ~10 cycles / issue)
-    for (uint32_t r = chunk * BARY_ROWS + threadIdx.x; r < r_end; r += BARY_THREADS) {
+    // two rows per iteration: two rows of loads in flight (the kernel was latency bound: ncu long_scoreboard ~10 cycles / issue) and
+    // their products share one conditional subtraction (kb::mac2)
+    uint32_t r = chunk * BARY_ROWS + threadIdx.x;
+    for (; r + BARY_THREADS < r_end; r += 2 * BARY_THREADS) {
+        const uint32_t r2 = r + BARY_THREADS;
+        Ext wa[NP], wb[NP];
+        wa[0] = ld_ext(w0 + 4 * (uint64_t)r);
+        wb[0] = ld_ext(w0 + 4 * (uint64_t)r2);
+        if (NP > 1) {
+            wa[NP - 1] = ld_ext(w1 + 4 * (uint64_t)r);
+            wb[NP - 1] = ld_ext(w1 + 4 * (uint64_t)r2);
+        }
+        uint32_t va[BARY_COLS], vb[BARY_COLS];
+#pragma unroll
+        for (int c = 0; c < BARY_COLS; c++) {
+            va[c] = colp[c][r];
+            vb[c] = colp[c][r2];
+        }
+#pragma unroll
+        for (int c = 0; c < BARY_COLS; c++)
+#pragma unroll
+            for (int t = 0; t < NP; t++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) kb::mac2(acc[c][t][k], wa[t].c[k], va[c], wb[t].c[k], vb[c]);
+    }
+    if (r < r_end) {
         Ext w[NP];
         w[0] = ld_ext(w0 + 4 * (uint64_t)r);
         if (NP > 1) w[NP - 1] = ld_ext(w1 + 4 * (uint64_t)r);
@@ -189,6 +213,7 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
         const RoMat& M = mats[m];
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // unreduced sum_k alpha^k M[r][k]
         const uint32_t* col = M.d + r;
+        // (pairing two columns per conditional subtraction with kb::mac2 was MEASURED slower here: 3.27 vs 2.56 ms at 2^22 rows)
 #pragma unroll RO_UNROLL
         for (uint32_t k = 0; k < M.width; k++) {
             uint32_t v = col[(uint64_t)k * M.stride];

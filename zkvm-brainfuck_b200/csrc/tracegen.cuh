@@ -19,6 +19,9 @@
 // generators and the resulting proofs word for word.
 #pragma once
 #include <unordered_map>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "gen_layout.cuh"
 
@@ -145,28 +148,43 @@ extern "C" int32_t bfgpu_execute(bfgpu_ctx* ctx, const char* code, const uint8_t
     struct Cell { uint32_t ts; uint8_t val; uint8_t seen; };
     std::vector<Cell> flat(1u << 16, Cell{0, 0, 0});
     std::unordered_map<uint32_t, Cell> far;
-    Cell* flat_p = flat.data();
-    uint32_t flat_n = (uint32_t)flat.size();
-    auto slow_cell = [&](uint32_t a) -> Cell* {  // beyond the flat table: grow it (addresses below 2^26) or use the map (wrapped pointers)
+    auto slow_cell = [&flat, &far](uint32_t a) -> Cell* {  // beyond the flat table: grow it (addresses below 2^26) or use the map (wrapped pointers)
         if (a < (1u << 26)) {
             size_t s = flat.size();
             while (s <= a) s *= 2;
             flat.resize(s, Cell{0, 0, 0});
-            flat_p = flat.data();
-            flat_n = (uint32_t)flat.size();
-            return flat_p + a;
+            return flat.data() + a;
         }
         return &far[a];
     };
     std::vector<uint32_t> first_order;  // addresses in first-access order
-    const uint8_t* ops = r->ops.data();
-    const uint32_t* args = r->args.data();
-    uint32_t* counts = r->prog_counts.data();
-    uint4* cyc = r->cycles;
+    // Everything the loop touches every cycle lives in locals whose address is never taken (the lambda above captures only the two
+    // containers): with `flat_p / flat_n / i` captured by reference, every store through `counts`, `cyc` or a cell pointer could
+    // alias them and the compiler reloaded them from the stack each cycle.
+    const uint8_t* __restrict__ ops = r->ops.data();
+    const uint32_t* __restrict__ args = r->args.data();
+    uint32_t* __restrict__ counts = r->prog_counts.data();
+    uint4* __restrict__ cyc = r->cycles;
+    Cell* flat_p = flat.data();
+    uint32_t flat_n = (uint32_t)flat.size();
     // the limit applies to recycled (pooled, already large) record buffers as well: clamp before the loop, not only after a growth
-    uint64_t cap = std::min<uint64_t>(r->cap, max_cycles + 1), n_alu = 0, n_jump = 0, n_mem = 0, n_io = 0;
+    uint64_t cap = std::min<uint64_t>(r->cap, max_cycles + 1);
     uint32_t pc = 0, mp = 0;
     uint64_t i = 0;
+    // 16 bytes per cycle into a buffer that is only read back by the DMA engine: non-temporal stores skip the read-for-ownership of
+    // every cache line (half of the interpreter's memory traffic).  $BFGPU_EXEC_NT=0/1 overrides (default: on for page-locked buffers,
+    // whose pages exist already; on fresh pageable memory the page faults dominate either way).
+    bool nt_store = r->pinned;
+    if (const char* e = getenv("BFGPU_EXEC_NT")) nt_store = atoi(e) != 0;
+    auto put = [nt_store](uint4* dst, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+#if defined(__x86_64__)
+        if (nt_store) {
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst), _mm_set_epi32((int)w, (int)z, (int)y, (int)x));
+            return;
+        }
+#endif
+        *dst = make_uint4(x, y, z, w);
+    };
     while (pc != n) {
         if (i + 2 > cap) {
             if (i >= max_cycles) {
@@ -181,29 +199,35 @@ extern "C" int32_t bfgpu_execute(bfgpu_ctx* ctx, const char* code, const uint8_t
             cap = std::min<uint64_t>(r->cap, max_cycles + 1);  // re-enter this branch exactly when the limit is reached
         }
         const uint32_t op = ops[pc], clk = (uint32_t)(2 * i);
-        uint32_t next_pc = pc + 1;
         counts[pc]++;
-        uint4 rec = make_uint4(pc, mp, 0, 0);
         if (op == OP_MEM_FWD || op == OP_MEM_BWD) {
+            put(cyc + i, pc, mp, 0, 0);
             mp = op == OP_MEM_FWD ? mp + 1 : mp - 1;
-            n_mem++;
+            pc++;
+            i++;
+            continue;
+        }
+        Cell* c;
+        if (mp < flat_n) c = flat_p + mp;
+        else {
+            c = slow_cell(mp);
+            flat_p = flat.data();
+            flat_n = (uint32_t)flat.size();
+        }
+        if (!c->seen) {
+            c->seen = 1;
+            first_order.push_back(mp);
+            r->mem_events.insert(r->mem_events.end(), {mp, c->ts, (uint32_t)c->val, 0u, 0u});
+        }
+        const uint32_t pv = c->val, pt = c->ts;
+        uint32_t mv = pv, next_pc = pc + 1;
+        if (op == OP_ADD || op == OP_SUB) {
+            c->val = (uint8_t)(op == OP_ADD ? mv + 1 : mv - 1);
+            c->ts = clk + 2;
         } else {
-            Cell* c = mp < flat_n ? flat_p + mp : slow_cell(mp);
-            if (!c->seen) {
-                c->seen = 1;
-                first_order.push_back(mp);
-                r->mem_events.insert(r->mem_events.end(), {mp, c->ts, (uint32_t)c->val, 0u, 0u});
-            }
-            const uint32_t pv = c->val, pt = c->ts;
-            uint32_t mv = pv;
             c->ts = clk + 1;
-            if (op == OP_ADD || op == OP_SUB) {
-                c->val = (uint8_t)(op == OP_ADD ? mv + 1 : mv - 1);
-                c->ts = clk + 2;
-                n_alu++;
-            } else if (op == OP_LOOP_START || op == OP_LOOP_END) {
+            if (op == OP_LOOP_START || op == OP_LOOP_END) {
                 if ((op == OP_LOOP_START) == (mv == 0)) next_pc = args[pc];  // '[' jumps on zero, ']' on non-zero
-                n_jump++;
             } else if (op == OP_INPUT) {
                 if (n_stdin == 0) {
                     r->err = "',' executed with empty stdin";
@@ -211,27 +235,36 @@ extern "C" int32_t bfgpu_execute(bfgpu_ctx* ctx, const char* code, const uint8_t
                 }
                 mv = stdin_bytes[0];  // the reference never advances the input pointer (executor.rs:183)
                 c->val = (uint8_t)mv;
-                n_io++;
             } else {  // OUTPUT
                 r->output.push_back((uint8_t)mv);
-                n_io++;
             }
-            rec.z = pt;
-            rec.w = mv | (pv << 8);
         }
-        cyc[i] = rec;
+        put(cyc + i, pc, mp, pt, mv | (pv << 8));
         pc = next_pc;
         i++;
+    }
+    // event counts per chip: every execution of an instruction is one event of its class
+    uint64_t n_alu = 0, n_jump = 0, n_mem = 0, n_io = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t op = ops[k];
+        const uint64_t cnt = counts[k];
+        if (op == OP_MEM_FWD || op == OP_MEM_BWD) n_mem += cnt;
+        else if (op == OP_ADD || op == OP_SUB) n_alu += cnt;
+        else if (op == OP_LOOP_START || op == OP_LOOP_END) n_jump += cnt;
+        else n_io += cnt;
     }
     r->n_alu = n_alu;
     r->n_jump = n_jump;
     r->n_mem = n_mem;
     r->n_io = n_io;
-    auto cell = [&](uint32_t a) -> Cell& { return a < flat_n ? flat_p[a] : far[a]; };
+    auto cell = [&flat, &far](uint32_t a) -> Cell& { return a < flat.size() ? flat[a] : far[a]; };
     if (!record_grow(r, i + 1, i)) {
         r->err = "out of host memory";
         return BFGPU_ERR_OOM;
     }
+#if defined(__x86_64__)
+    _mm_sfence();  // non-temporal record stores are globally visible before anything (DMA included) reads the buffer
+#endif
     r->cycles[i] = make_uint4(pc, mp, 0, 0);  // sentinel: next_pc / next_mp of the last cycle
     r->n_cycles = i;
     for (size_t k = 0; k < first_order.size(); k++) {
