@@ -224,7 +224,9 @@ constexpr uint32_t DIST_CHUNK_COLS = 64;
 // LDE + exchange of this rank's columns of every matrix, from coefficient-side inputs already on the device in the prover's layout
 // (column-major, Montgomery, bit-reversed rows; coefs[i] = the rank's ncols(i) columns, TRANSFORMED IN PLACE: pass a copy to keep them).
 // shift_mont[i]: LDE coset shift of matrix i.  Asynchronous, same completion protocol as bfgpu_dist_commit_lde.
-static int32_t dist_lde_coefs(bfgpu_dist_commit* dc, const std::vector<DMat>& coefs, const std::vector<uint32_t>& shift_mont) {
+// first_pass_done[i]: the first inverse NTT pass of matrix i was executed by the fused ingest (ntt3::k_ingest_pass)
+static int32_t dist_lde_coefs(bfgpu_dist_commit* dc, const std::vector<DMat>& coefs, const std::vector<uint32_t>& shift_mont,
+                              const std::vector<char>* first_pass_done = nullptr) {
     bfgpu_ctx* ctx = dc->ctx;
     if (dc->lde_done) return fail(ctx, BFGPU_ERR_STATE, "LDE already done");
     if (!dc->staging && dc->peer_recv.empty()) return fail(ctx, BFGPU_ERR_STATE, "neither peers nor a staging buffer set");
@@ -256,7 +258,9 @@ static int32_t dist_lde_coefs(bfgpu_dist_commit* dc, const std::vector<DMat>& co
             DMat slice = coef, lde;
             slice.d = coef.d + (uint64_t)c * coef.rows;
             slice.cols = nc;
-            if ((rc = lde_from_bitrev(ctx, slice, ctx->log_blowup, shift_mont[i], &lde, /*consume=*/false)) != BFGPU_OK) break;
+            if ((rc = lde_from_bitrev(ctx, slice, ctx->log_blowup, shift_mont[i], &lde, /*consume=*/false, nullptr,
+                                      first_pass_done && (*first_pass_done)[i])) != BFGPU_OK)
+                break;
             Phase ph(ctx, BFGPU_PHASE_EXCHANGE);
             cudaEvent_t ready, done;
             cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
@@ -293,6 +297,7 @@ static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* loca
     const uint32_t gen = kb::to_mont(kb::GEN);
     std::vector<DMat> coefs(dc->mats.size());
     std::vector<uint32_t> shifts(dc->mats.size(), gen);
+    std::vector<char> first_done(dc->mats.size(), 0);
     int32_t rc = BFGPU_OK;
     for (size_t i = 0; i < dc->mats.size() && rc == BFGPU_OK; i++) {
         const auto& m = dc->mats[i];
@@ -311,9 +316,11 @@ static int32_t dist_commit_lde_impl(bfgpu_dist_commit* dc, const bfgpu_mat* loca
             }
             shifts[i] = kb::mul(gen, kb::inv(ds));
         }
-        rc = ingest(ctx, local[i], /*bitrev=*/true, &coefs[i]);
+        bool fd = false;
+        rc = ingest(ctx, local[i], /*bitrev=*/true, &coefs[i], &fd);  // transpose + first inverse pass in one kernel where the shape allows
+        first_done[i] = fd;
     }
-    if (rc == BFGPU_OK) rc = dist_lde_coefs(dc, coefs, shifts);
+    if (rc == BFGPU_OK) rc = dist_lde_coefs(dc, coefs, shifts, &first_done);
     // the coefficient matrices were transformed in place slice by slice; all work on them is in compute-stream order
     for (DMat& c : coefs) dfree(ctx, c.d);
     return rc;
