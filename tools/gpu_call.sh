@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
 export PYTHONUNBUFFERED=1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_c34_bench_n4.json 2> gpurun_out/r2_c34_bench_n4.err; echo "bench n4 rc=$?"
+timeout 1200 python tools/stress_lde.py 12 > gpurun_out/r2_c36_stress.log 2>&1; echo "stress rc=$?"
+tail -n 12 gpurun_out/r2_c36_stress.log
