@@ -114,6 +114,8 @@ struct bfgpu_ctx {
     std::set<int> ntt3_configured;  // (mode, G1) instantiations whose dynamic shared-memory limit has been raised on this device
     bool ntt_turn = true;  // last inverse pass fused with the first forward pass (k_pass TURN); $BFGPU_NTT_TURN=0 runs them as two launches
     bool ntt_dual = true;  // coset scaling on load in the first forward pass (k_pass DUAL) instead of the inverse-pass epilogue ($BFGPU_NTT_DUAL=0)
+    bool dist_fused_scatter = true;  // sharded commitment: the last forward NTT pass stores straight into the peers' row shards
+                                     // (ntt3::k_cfwd with CfwdArgs::scatter) instead of a k_scatter_rows pass over the finished block; $BFGPU_DIST_FUSED_SCATTER=0
     uint32_t dist_min_chunk = 32;  // dist_commit.cuh: smallest LDE / scatter block in columns ($BFGPU_DIST_MIN_CHUNK)
     unsigned dist_fri_gather_log = 20;  // dist_prove.cuh: global FRI length below which the sharded prover gathers ($BFGPU_DIST_FRI_GATHER_LOG)
     // test hook (bfgpu_debug_fail_alloc): the n-th dalloc from now fails with BFGPU_ERR_OOM
@@ -346,6 +348,7 @@ extern "C" int32_t bfgpu_ctx_create(int device, bfgpu_ctx** out) {
     if (const char* e = getenv("BFGPU_NTT_CFWD")) ctx->ntt_cfwd = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_TOP_CLUSTER")) ctx->top_cluster = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_TOP_X1_MAX")) ctx->top_x1_max = (uint32_t)atoi(e);
+    if (const char* e = getenv("BFGPU_DIST_FUSED_SCATTER")) ctx->dist_fused_scatter = atoi(e) != 0;
     if (const char* e = getenv("BFGPU_DIST_MIN_CHUNK")) ctx->dist_min_chunk = (uint32_t)std::max(8, atoi(e)) / 8 * 8;
     if (const char* e = getenv("BFGPU_DIST_FRI_GATHER_LOG")) ctx->dist_fri_gather_log = (unsigned)std::min(24, std::max(4, atoi(e)));
     if (const char* q = getenv("FRI_QUERIES")) ctx->num_queries = (uint32_t)atoi(q);  // kb31_poseidon2.rs:59-62
@@ -866,30 +869,53 @@ static int32_t run_pass3(bfgpu_ctx* ctx, int mode, const uint32_t* src, uint64_t
 
 // Contiguous forward pass (p = 0) through the bulk-copy kernel ntt3::k_cfwd
 template <int G1>
-static int32_t launch_cfwd(bfgpu_ctx* ctx, const ntt3::CfwdArgs& a, dim3 grid) {
+static int32_t launch_cfwd(bfgpu_ctx* ctx, const ntt3::CfwdArgs& a, dim3 grid, cudaStream_t st) {
     const int key = 128 + G1;
     if (!ctx->ntt3_configured.count(key)) {
         CU(cudaFuncSetAttribute(ntt3::k_cfwd<G1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ntt3::cfwd_smem_bytes(G1)));
         ctx->ntt3_configured.insert(key);
     }
-    ntt3::k_cfwd<G1><<<grid, 1u << (G1 + 5), ntt3::cfwd_smem_bytes(G1), ctx->stream>>>(a);
+    ntt3::k_cfwd<G1><<<grid, 1u << (G1 + 5), ntt3::cfwd_smem_bytes(G1), st>>>(a);
     return BFGPU_OK;
 }
-static bool cfwd_usable(bfgpu_ctx* ctx, const bfgpu_ctx::NttPass& ps, unsigned log_n, const uint32_t* data, uint64_t col_stride) {
-    return ctx->ntt_tma && ctx->ntt_cfwd && ps.p == 0 && ps.g >= 5 && ps.g <= 8 && log_n >= ps.g + 5 && ((uintptr_t)data & 15) == 0 && col_stride % 4 == 0;
+static bool cfwd_possible(bfgpu_ctx* ctx, const bfgpu_ctx::NttPass& ps, unsigned log_n, const uint32_t* data, uint64_t col_stride) {
+    return ctx->ntt_tma && ps.p == 0 && ps.g >= 5 && ps.g <= 8 && log_n >= ps.g + 5 && ((uintptr_t)data & 15) == 0 && col_stride % 4 == 0;
 }
-static int32_t run_cfwd(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, uint32_t ncols, unsigned log_n, const bfgpu_ctx::NttPass& ps) {
+static bool cfwd_usable(bfgpu_ctx* ctx, const bfgpu_ctx::NttPass& ps, unsigned log_n, const uint32_t* data, uint64_t col_stride) {
+    return ctx->ntt_cfwd && cfwd_possible(ctx, ps, log_n, data, col_stride);
+}
+// where the last forward pass of a sharded LDE block sends its rows (ntt3::CfwdArgs::scatter)
+struct ScatterTarget {
+    uint32_t log_rpg = 0, dcol0 = 0, world = 0;
+    uint32_t* dst[16] = {};
+};
+static int32_t run_cfwd(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, uint32_t ncols, unsigned log_n, const bfgpu_ctx::NttPass& ps,
+                        const ScatterTarget* sc = nullptr, cudaStream_t stream = nullptr) {
     const uint32_t tiles = 1u << (log_n - ps.g - 5);
     const uint32_t want_groups = std::max<uint32_t>(1, (148u * 16 + tiles - 1) / tiles);
     uint32_t cpc = std::max<uint32_t>(std::min<uint32_t>(8, ncols), (ncols + want_groups - 1) / want_groups);
     cpc = std::min<uint32_t>(cpc, 64);
-    ntt3::CfwdArgs a{data, col_stride, ncols, cpc, ps.twA};
+    ntt3::CfwdArgs a;
+    memset(&a, 0, sizeof a);
+    a.data = data;
+    a.col_stride = col_stride;
+    a.ncols = ncols;
+    a.cols_per_cta = cpc;
+    a.twA = ps.twA;
+    a.log_n = log_n;
+    if (sc) {
+        a.scatter = 1;
+        a.log_rpg = sc->log_rpg;
+        a.dcol0 = sc->dcol0;
+        for (uint32_t r = 0; r < sc->world && r < 16; r++) a.dst[r] = sc->dst[r];
+    }
     dim3 grid(tiles, (ncols + cpc - 1) / cpc);
+    cudaStream_t st = stream ? stream : ctx->stream;
     switch (ps.g - 4) {
-        case 1: TRY(launch_cfwd<1>(ctx, a, grid)); break;
-        case 2: TRY(launch_cfwd<2>(ctx, a, grid)); break;
-        case 3: TRY(launch_cfwd<3>(ctx, a, grid)); break;
-        default: TRY(launch_cfwd<4>(ctx, a, grid)); break;
+        case 1: TRY(launch_cfwd<1>(ctx, a, grid, st)); break;
+        case 2: TRY(launch_cfwd<2>(ctx, a, grid, st)); break;
+        case 3: TRY(launch_cfwd<3>(ctx, a, grid, st)); break;
+        default: TRY(launch_cfwd<4>(ctx, a, grid, st)); break;
     }
     LAUNCHED(ctx);
     CU(cudaGetLastError());
@@ -1021,7 +1047,9 @@ static int32_t run_ntt(bfgpu_ctx* ctx, uint32_t* data, uint64_t col_stride, unsi
 // vectors on load and writes both half-columns of `out` (ntt2::k_pass<..., DUAL>); the remaining passes run in place on the 2W
 // half-columns.  BFGPU_NTT_DUAL=0 falls back to the epilogue-in-the-inverse-pass path of round 1.
 // turn: `coef` still lacks the top inverse pass, which the first launch executes too (ntt2::k_pass<..., TURN>).
-static int32_t run_ntt_forward_dual(bfgpu_ctx* ctx, const uint32_t* coef, uint32_t* out, const uint32_t* pw, unsigned log_n, uint32_t ncols, bool turn) {
+// skip_last: stop before the contiguous last pass (the caller runs it itself: sharded commitment, ntt3::k_cfwd with the row scatter)
+static int32_t run_ntt_forward_dual(bfgpu_ctx* ctx, const uint32_t* coef, uint32_t* out, const uint32_t* pw, unsigned log_n, uint32_t ncols, bool turn,
+                                    bool skip_last = false) {
     Phase ph(ctx, BFGPU_PHASE_NTT);
     const std::vector<bfgpu_ctx::NttPass>* plan = nullptr;
     const std::vector<bfgpu_ctx::NttPass>* iplan = nullptr;
@@ -1029,7 +1057,7 @@ static int32_t run_ntt_forward_dual(bfgpu_ctx* ctx, const uint32_t* coef, uint32
     if (turn) TRY(get_plan(ctx, log_n, true, &iplan));
     const size_t np = plan->size();
     const uint64_t n = 1ull << log_n;
-    for (size_t s = 0; s < np; s++) {
+    for (size_t s = 0; s + (skip_last ? 1 : 0) < np; s++) {
         const auto& ps = (*plan)[np - 1 - s];  // forward DIF: high bits first
         const bool dual = s == 0;
         const uint32_t cols = dual ? ncols : 2 * ncols;
@@ -1124,8 +1152,10 @@ static int32_t coset_powers(bfgpu_ctx* ctx, unsigned log_n, unsigned added_bits,
 // coset LDE of a column-major device matrix whose rows are already in bit-reversed order (consumed) ->
 // column-major device matrix with bit-reversed rows.  shift_mont: Montgomery form of the coset shift.
 // first_pass_done: the first inverse pass has been executed by the fused ingest (ntt3::k_ingest_pass)
+// defer_last_pass != null (sharded commitment): if the shape allows, everything but the contiguous last forward pass is enqueued,
+// *defer_last_pass = true and the caller finishes with lde_last_pass_scatter(); otherwise it stays false and the LDE is complete.
 static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, uint32_t shift_mont, DMat* out, bool consume = true,
-                               uint32_t* out_buf = nullptr, bool first_pass_done = false) {
+                               uint32_t* out_buf = nullptr, bool first_pass_done = false, bool* defer_last_pass = nullptr) {
     unsigned log_n = ilog2(coef.rows);
     if (log_n + added_bits > kb::TWO_ADICITY) return fail(ctx, BFGPU_ERR_INVALID, "LDE height 2^%u exceeds the field's two-adicity", log_n + added_bits);
     uint64_t n = coef.rows, N = n << added_bits;
@@ -1138,8 +1168,15 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     else TRY(dalloc(ctx, (void**)&out->d, N * coef.cols * 4));
     if (log_n >= NTT2_MIN_LOG && ncosets == 2 && ctx->ntt_dual) {
         // plain inverse transform; the coset scaling and the 2-fold expansion happen on load in the first forward pass
+        bool defer = false;
+        if (defer_last_pass) {
+            const std::vector<bfgpu_ctx::NttPass>* fplan = nullptr;
+            TRY(get_plan(ctx, log_n, false, &fplan));
+            defer = ctx->dist_fused_scatter && fplan->size() >= 2 && cfwd_possible(ctx, fplan->front(), log_n, out->d, n);
+            *defer_last_pass = defer;
+        }
         TRY(run_ntt<true>(ctx, coef.d, n, log_n, coef.cols, CosetEpilogue(), ctx->ntt_turn, first_pass_done));
-        TRY(run_ntt_forward_dual(ctx, coef.d, out->d, pw, log_n, coef.cols, ctx->ntt_turn));
+        TRY(run_ntt_forward_dual(ctx, coef.d, out->d, pw, log_n, coef.cols, ctx->ntt_turn, defer));
         if (consume) dfree(ctx, coef.d);  // stream order keeps it alive for the pass above
         return BFGPU_OK;
     }
@@ -1161,6 +1198,18 @@ static int32_t lde_from_bitrev(bfgpu_ctx* ctx, DMat coef, unsigned added_bits, u
     if (consume) dfree(ctx, coef.d);
     TRY(run_ntt<false>(ctx, out->d, n, log_n, coef.cols * ncosets));
     return BFGPU_OK;
+}
+
+// Last (contiguous) forward pass of a blow-up-2 LDE block whose earlier passes were enqueued by lde_from_bitrev(defer_last_pass):
+// reads the 2W half-columns of `lde`, sends every run of rows to the rank that owns it (ScatterTarget), on `stream`.
+static int32_t lde_last_pass_scatter(bfgpu_ctx* ctx, const DMat& lde, const ScatterTarget& sc, cudaStream_t stream) {
+    const unsigned log_n = ilog2(lde.rows) - 1;
+    const std::vector<bfgpu_ctx::NttPass>* fplan = nullptr;
+    TRY(get_plan(ctx, log_n, false, &fplan));
+    const auto& ps = fplan->front();
+    if (sc.log_rpg < ps.g) return fail(ctx, BFGPU_ERR_STATE, "internal: a row shard is shorter than a run of the last pass");
+    Phase ph(ctx, BFGPU_PHASE_EXCHANGE);
+    return run_cfwd(ctx, lde.d, 1ull << log_n, 2 * lde.cols, log_n, ps, &sc, stream);
 }
 
 // Coset LDEs of several coefficient matrices (column-major, bit-reversed rows, consumed): columns of at most

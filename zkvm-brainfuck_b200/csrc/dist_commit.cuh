@@ -258,8 +258,11 @@ static int32_t dist_lde_coefs(bfgpu_dist_commit* dc, const std::vector<DMat>& co
             DMat slice = coef, lde;
             slice.d = coef.d + (uint64_t)c * coef.rows;
             slice.cols = nc;
+            // P2P mode with row shards of at least one run of the last pass: that pass sends its results to their owners itself
+            bool deferred = false;
+            const bool try_fused = !dc->staging && ctx->log_blowup == 1;
             if ((rc = lde_from_bitrev(ctx, slice, ctx->log_blowup, shift_mont[i], &lde, /*consume=*/false, nullptr,
-                                      first_pass_done && (*first_pass_done)[i])) != BFGPU_OK)
+                                      first_pass_done && (*first_pass_done)[i], try_fused ? &deferred : nullptr)) != BFGPU_OK)
                 break;
             Phase ph(ctx, BFGPU_PHASE_EXCHANGE);
             cudaEvent_t ready, done;
@@ -268,7 +271,26 @@ static int32_t dist_lde_coefs(bfgpu_dist_commit* dc, const std::vector<DMat>& co
             cudaEventRecord(ready, ctx->stream);
             cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
             cudaEventDestroy(ready);
-            rc = dist_scatter(dc, m, lde.d, c, nc, ctx->copy_stream);
+            if (deferred) {
+                ScatterTarget sc;
+                sc.log_rpg = ilog2(m.rpg);
+                sc.dcol0 = m.col0 + c;
+                sc.world = dc->world;
+                bool ok = sc.log_rpg >= 8;  // >= the longest run (2^8 rows) of a contiguous pass
+                for (uint32_t g = 0; g < dc->world; g++) {
+                    sc.dst[g] = dc->peer_recv[g] + m.recv_off;
+                    ok = ok && ((uintptr_t)sc.dst[g] & 15) == 0;
+                }
+                if (ok) rc = lde_last_pass_scatter(ctx, lde, sc, ctx->copy_stream);
+                else {  // finish the block in place, then the plain scatter
+                    const std::vector<bfgpu_ctx::NttPass>* fplan = nullptr;
+                    rc = get_plan(ctx, ilog2(lde.rows) - 1, false, &fplan);
+                    if (rc == BFGPU_OK) rc = run_cfwd(ctx, lde.d, lde.rows / 2, 2 * lde.cols, ilog2(lde.rows) - 1, fplan->front(), nullptr, ctx->copy_stream);
+                    if (rc == BFGPU_OK) rc = dist_scatter(dc, m, lde.d, c, nc, ctx->copy_stream);
+                }
+            } else {
+                rc = dist_scatter(dc, m, lde.d, c, nc, ctx->copy_stream);
+            }
             cudaEventRecord(done, ctx->copy_stream);
             pending.push_back({lde.d, done});
         }

@@ -427,6 +427,12 @@ struct CfwdArgs {
     uint32_t ncols;
     uint32_t cols_per_cta;
     const TWT* twA;       // phase-A table of the contiguous forward pass: [(2^G1 - 1)][16]
+    // Sharded commitment (dist_commit.cuh): the columns are the 2W half-columns [W][2][n] of an LDE block and the results do not go
+    // back in place but straight to the rank that owns their ROWS: stored row R = (hc & 1) * n + position of LDE column hc >> 1 goes to
+    // dst[R >> log_rpg] + ((dcol0 + (hc >> 1)) << log_rpg) + (R & (2^log_rpg - 1)) — peer HBM mapped over NVLink, written by the same
+    // asynchronous bulk stores (a run of 2^g rows never straddles two ranks: log_rpg >= g).  scatter = 0: in place.
+    uint32_t scatter, log_n, log_rpg, dcol0;
+    uint32_t* dst[16];
 };
 constexpr int CFWD_SLOTS = 3;
 constexpr size_t cfwd_smem_bytes(int G1) { return (size_t)CFWD_SLOTS * 32 * ((1 << (G1 + 4)) + 4) * 4 + 15 * 16 * sizeof(TWT) + CFWD_SLOTS * sizeof(uint64_t); }
@@ -510,7 +516,13 @@ __global__ void __launch_bounds__(1 << (G1 + 5), 1024 >> (G1 + 5)) k_cfwd(CfwdAr
         fence_async_smem();
         __syncthreads();
         if (warp == 0) {
-            bulk_store_1d(A.data + (uint64_t)(c_begin + i) * A.col_stride + base + (lane << g), S + lane * PITCH, ND * 4);
+            uint32_t* o = A.data + (uint64_t)(c_begin + i) * A.col_stride + base + (lane << g);
+            if (A.scatter) {
+                const uint32_t hc = c_begin + i;
+                const uint64_t R = ((uint64_t)(hc & 1) << A.log_n) + base + (lane << g);
+                o = A.dst[R >> A.log_rpg] + ((uint64_t)(A.dcol0 + (hc >> 1)) << A.log_rpg) + (R & ((1ull << A.log_rpg) - 1));
+            }
+            bulk_store_1d(o, S + lane * PITCH, ND * 4);
             bulk_commit();
             bulk_wait_read<1>();  // this lane's store of column i-1 has left its slot: refill it with column i+2
             if (i + 2 < ncol) issue(i + 2);
