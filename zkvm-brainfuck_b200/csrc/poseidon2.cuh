@@ -180,12 +180,20 @@ KB_D void internal_linear(uint32_t (&s)[16]) {
 // BARRIER: __syncthreads() at every round boundary keeps the warps of a CTA at the same PC so that
 // they share instruction-cache lines (all threads of the CTA must call permute the same number of
 // times).
+#ifndef P2_EXT_UNROLL
+#define P2_EXT_UNROLL 1  // external rounds per loop iteration (1, 2 or 4)
+#endif
+#ifndef P2_INT_UNROLL
+#define P2_INT_UNROLL 1  // internal rounds per loop iteration
+#endif
+#define P2_PRAGMA_(x) _Pragma(#x)
+#define P2_UNROLL(n) P2_PRAGMA_(unroll n)
 template <bool BARRIER = false>
 KB_D void permute(uint32_t (&s)[16]) {
     external_linear(s);
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
-#pragma unroll 1
+        P2_UNROLL(P2_EXT_UNROLL)
         for (int r = 0; r < 4; r++) {
             const uint32_t* rc = c_p2.ext[half * 4 + r];
             const uint32_t* rcs = c_p2.ext_s[half * 4 + r];
@@ -195,7 +203,7 @@ KB_D void permute(uint32_t (&s)[16]) {
             external_linear(s);
         }
         if (half == 0) {
-#pragma unroll 1
+            P2_UNROLL(P2_INT_UNROLL)
             for (int r = 0; r < 13; r++) {
                 if (BARRIER) __syncthreads();
                 s[0] = sbox_rc(s[0], c_p2.internal[r], c_p2.internal_s[r]);
