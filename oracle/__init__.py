@@ -34,6 +34,26 @@ def build(force=False):
     return so
 
 
+_AIR = None
+
+
+def air_lib():
+    """oracle/libbfoair.so: CPU arm of the LogUp-trace and quotient phases (oracle/fast_air.cpp)."""
+    global _AIR
+    if _AIR is None:
+        so = os.path.join(_DIR, "libbfoair.so")
+        deps = [os.path.join(_DIR, "fast_air.cpp"), os.path.join(_DIR, "..", "zkvm-brainfuck_b200", "csrc", "gen_air.cuh"),
+                os.path.join(_DIR, "..", "zkvm-brainfuck_b200", "csrc", "kb31.cuh")]
+        if not os.path.exists(so) or any(os.path.exists(d) and os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["make", "-C", _DIR, "libbfoair.so"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        L.bfo_air_chip_info.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L.bfo_air_perm_trace.argtypes = [C.c_int, u32p, u32p, C.c_uint64, u32p, u32p, u32p, u32p]
+        L.bfo_air_quotient.argtypes = [C.c_int, u32p, u32p, u32p, C.c_uint64, u32p, u32p, u32p, u32p, u32p]
+        _AIR = L
+    return _AIR
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -282,3 +302,46 @@ def fast_permute_many(states):
     if lib().bfo_fast_permute_many(_p(s), s.shape[0]) != 0:
         raise RuntimeError("bfo_fast_permute_many: needs AVX-512 and a multiple of 16 states")
     return s
+
+
+# ---- CPU arm of the AIR phases (oracle/fast_air.cpp): timing baseline for bench.py, checked against oracle/prover.py -----------
+def air_chip_info(chip):
+    info = (C.c_int * 4)()
+    if air_lib().bfo_air_chip_info(int(chip), info) != 0:
+        raise ValueError(f"unknown chip {chip}")
+    return dict(main_w=info[0], prep_w=info[1], perm_w=info[2], n_constraints=info[3])
+
+
+def air_perm_trace(chip, main, prep, alpha, beta, timing=False):
+    """generate_permutation_trace on the CPU: (perm trace rows x 4*perm_w canonical, cumulative sum[, seconds of the C call])."""
+    import time
+    inf = air_chip_info(chip)
+    m = _u32(main)
+    pr = _u32(prep) if inf["prep_w"] else None
+    out = np.empty((m.shape[0], 4 * inf["perm_w"]), np.uint32)
+    out.fill(0)  # touch the pages outside the timed call
+    cs = np.zeros(4, np.uint32)
+    t = time.perf_counter()
+    rc = air_lib().bfo_air_perm_trace(int(chip), _p(m), _p(pr) if pr is not None else None, m.shape[0], _p(_u32(alpha)), _p(_u32(beta)), _p(out), _p(cs))
+    dt = time.perf_counter() - t
+    if rc != 0:
+        raise RuntimeError("bfo_air_perm_trace failed")
+    return (out, cs, dt) if timing else (out, cs)
+
+
+def air_quotient(chip, main_lde, prep_lde, perm_lde, alpha_logup, beta, csum, alpha, timing=False):
+    """quotient_values on the CPU from bit-reversed-row LDEs (2n rows): (2, n, 4) canonical chunk values[, seconds of the C call]."""
+    import time
+    inf = air_chip_info(chip)
+    ml, ql = _u32(main_lde), _u32(perm_lde)
+    pl = _u32(prep_lde) if inf["prep_w"] else None
+    n = ml.shape[0] // 2
+    out = np.empty((2, n, 4), np.uint32)
+    out.fill(0)
+    t = time.perf_counter()
+    rc = air_lib().bfo_air_quotient(int(chip), _p(ml), _p(pl) if pl is not None else None, _p(ql), n, _p(_u32(alpha_logup)), _p(_u32(beta)), _p(_u32(csum)),
+                                    _p(_u32(alpha)), _p(out))
+    dt = time.perf_counter() - t
+    if rc != 0:
+        raise RuntimeError("bfo_air_quotient failed")
+    return (out, dt) if timing else out

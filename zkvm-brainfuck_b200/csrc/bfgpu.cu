@@ -1651,11 +1651,30 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
     // after the last byte arrives: the final block is split in two to shorten that tail (narrower strided copies are
     // slower per byte, so only the tail is split).
     std::vector<uint32_t> start;
-    for (uint32_t c = 0; c < W; c += CB) start.push_back(c);
-    for (int split = 0; split < ctx->pipe_tail_splits; split++) {  // halve the final block (down to 16 columns)
-        uint32_t last = start.back(), len = W - last, half = (len / 2 + 7) / 8 * 8;
-        if (len < 32 || half >= len) break;
-        start.push_back(last + half);
+    uint32_t max_block = CB;
+    if (const char* e = getenv("BFGPU_PIPE_SCHEDULE")) {  // experiment: explicit block widths "w0,w1,..." (multiples of 8 summing to W)
+        uint32_t c = 0;
+        bool ok = true;
+        for (const char* q = e; *q && ok;) {
+            char* end = nullptr;
+            const unsigned long w = strtoul(q, &end, 10);
+            if (end == q || w == 0 || w % 8 != 0 || c + w > W) ok = false;
+            else {
+                start.push_back(c);
+                c += (uint32_t)w;
+                max_block = std::max<uint32_t>(max_block, (uint32_t)w);
+                q = *end == ',' ? end + 1 : end;
+            }
+        }
+        if (!ok || c != W) start.clear();
+    }
+    if (start.empty()) {
+        for (uint32_t c = 0; c < W; c += CB) start.push_back(c);
+        for (int split = 0; split < ctx->pipe_tail_splits; split++) {  // halve the final block (down to 16 columns)
+            uint32_t last = start.back(), len = W - last, half = (len / 2 + 7) / 8 * 8;
+            if (len < 32 || half >= len) break;
+            start.push_back(last + half);
+        }
     }
     start.push_back(W);
     const uint32_t nb = (uint32_t)start.size() - 1;
@@ -1667,8 +1686,8 @@ static int32_t commit_host_pipelined(bfgpu_ctx* ctx, const bfgpu_mat& m, unsigne
     uint32_t *staged[2] = {nullptr, nullptr}, *state = nullptr, *layer = nullptr;
     TRY(dalloc(ctx, (void**)&lde->d, N * W * 4));
     if (!from_device) {
-        TRY(dalloc(ctx, (void**)&staged[0], R * CB * 4));
-        TRY(dalloc(ctx, (void**)&staged[1], R * CB * 4));
+        TRY(dalloc(ctx, (void**)&staged[0], R * max_block * 4));
+        TRY(dalloc(ctx, (void**)&staged[1], R * max_block * 4));
     }
     TRY(dalloc(ctx, (void**)&state, N * 16 * 4));
     TRY(dalloc(ctx, (void**)&layer, N * 32));
