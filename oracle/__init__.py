@@ -50,6 +50,8 @@ def air_lib():
         L.bfo_air_chip_info.argtypes = [C.c_int, C.POINTER(C.c_int)]
         L.bfo_air_perm_trace.argtypes = [C.c_int, u32p, u32p, C.c_uint64, u32p, u32p, u32p, u32p]
         L.bfo_air_quotient.argtypes = [C.c_int, u32p, u32p, u32p, C.c_uint64, u32p, u32p, u32p, u32p, u32p]
+        L.bfo_open_eval.argtypes = [u32p, C.c_uint64, C.c_uint32, u32p, u32p]
+        L.bfo_open_reduce_add.argtypes = [u32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, u32p, u32p, C.c_uint64, u32p]
         _AIR = L
     return _AIR
 
@@ -91,6 +93,8 @@ def lib():
         L.bfo_fast_pcs_commit.restype = C.c_int
         L.bfo_fast_permute_many.argtypes = [u32p, C.c_uint64]
         L.bfo_fast_permute_many.restype = C.c_int
+        L.bfo_fast_fri_commit_phase.argtypes = [C.POINTER(u32p), u32p, C.c_int, u32p, C.c_int, u32p, u32p, C.POINTER(C.c_double)]
+        L.bfo_fast_fri_commit_phase.restype = C.c_int
         L.bfo_set_threads.argtypes = [C.c_int]
         L.bfo_get_threads.restype = C.c_int
         _LIB = L
@@ -345,3 +349,49 @@ def air_quotient(chip, main_lde, prep_lde, perm_lde, alpha_logup, beta, csum, al
     if rc != 0:
         raise RuntimeError("bfo_air_quotient failed")
     return (out, dt) if timing else out
+
+
+def open_eval(lde, z, timing=False):
+    """Barycentric evaluation of every column of a committed matrix at the extension point z from its bit-reversed-row LDE (2n x w):
+    (w, 4) canonical[, seconds]."""
+    import time
+    l = _u32(lde)
+    out = np.zeros((l.shape[1], 4), np.uint32)
+    t = time.perf_counter()
+    rc = air_lib().bfo_open_eval(_p(l), l.shape[0] // 2, l.shape[1], _p(_u32(z)), _p(out))
+    dt = time.perf_counter() - t
+    if rc != 0:
+        raise RuntimeError("bfo_open_eval failed")
+    return (out, dt) if timing else out
+
+
+def open_reduce_add(lde, zs, ys, alpha, reduced_before, ro, timing=False):
+    """ro (h x 4 canonical, updated in place) += the reduced openings of one matrix at its npts <= 2 opening points."""
+    import time
+    l = _u32(lde)
+    zs, ys = _u32(zs).reshape(-1, 4), _u32(ys)
+    assert ro.dtype == np.uint32 and ro.flags.c_contiguous and ro.shape == (l.shape[0], 4)
+    t = time.perf_counter()
+    rc = air_lib().bfo_open_reduce_add(_p(l), l.shape[0], l.shape[1], zs.shape[0], _p(zs), _p(ys), _p(_u32(alpha)), int(reduced_before), _p(ro))
+    dt = time.perf_counter() - t
+    if rc != 0:
+        raise RuntimeError("bfo_open_reduce_add failed")
+    return dt if timing else None
+
+
+def fast_fri_commit_phase(inputs, betas, rollin_beta2=False):
+    """FRI commit phase on the CPU with caller-supplied betas (rounds x 4): (roots (rounds, 8), final_poly (4,), {hash, fold} seconds).
+    inputs: extension vectors (len x 4 canonical), strictly decreasing power-of-two lengths."""
+    ins = [_u32(v) for v in inputs]
+    ptrs = (u32p * len(ins))(*[_p(v) for v in ins])
+    logs = np.array([v.shape[0].bit_length() - 1 for v in ins], np.uint32)
+    b = _u32(betas).reshape(-1, 4)
+    rounds = int(logs[0]) - 1
+    assert b.shape[0] >= rounds
+    roots = np.zeros((rounds, 8), np.uint32)
+    fin = np.zeros(4, np.uint32)
+    sec = (C.c_double * 2)()
+    rc = lib().bfo_fast_fri_commit_phase(ptrs, _p(logs), len(ins), _p(b), 1 if rollin_beta2 else 0, _p(roots), _p(fin), sec)
+    if rc != rounds:
+        raise RuntimeError(f"bfo_fast_fri_commit_phase: {rc}")
+    return roots, fin, dict(hash=sec[0], fold=sec[1])

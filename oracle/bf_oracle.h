@@ -73,6 +73,9 @@ int bfo_fast_available(void);
    phase_sec = {LDE, leaf hashing, compression layers}.  Returns 0, -1 if unsupported (rows < 16, no AVX-512). */
 int bfo_fast_pcs_commit(const uint32_t* in, uint64_t rows, uint64_t cols, uint32_t root[8], uint32_t* lde_out, double phase_sec[3]);
 int bfo_fast_permute_many(uint32_t* states, uint64_t n);
+/* CPU arm of the FRI commit phase with caller-supplied folding challenges (oracle/fast_commit.c) */
+int bfo_fast_fri_commit_phase(const uint32_t* const* inputs, const uint32_t* log_len, int n_inputs, const uint32_t* betas, int rollin_beta2, uint32_t* roots,
+                              uint32_t final_poly[4], double sec[2]);
 void bfo_fast_release(void); /* drop the work buffers bfo_fast_pcs_commit keeps between calls */
 
 void bfo_set_threads(int n);

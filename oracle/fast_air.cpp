@@ -10,6 +10,7 @@
 // description — that is what tests/ref_air.py is for.
 #include <omp.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -76,6 +77,28 @@ inline unsigned ilog2(uint64_t x) {
     while ((1ull << l) < x) l++;
     return l;
 }
+
+// g^{bitrev(r, log_n)} for 64 consecutive r at a time: bitrev(r0 + k) = bitrev6(k) << (log_n - 6) | bitrev(r0 >> 6), so the block needs one
+// power for its base and a fixed table of the 64th roots (instead of a ~1.5 log n product chain per row)
+struct BrevPowers {
+    uint32_t g, t64[64];
+    unsigned log_n;
+    BrevPowers(uint32_t gen, unsigned ln) : g(gen), log_n(ln) {
+        if (log_n >= 6) {
+            const uint32_t G = kb::pow(g, 1ull << (log_n - 6));
+            for (uint64_t k = 0; k < 64; k++) t64[k] = kb::pow(G, brev(k, 6));
+        }
+    }
+    // out[k] = g^{bitrev(r0 + k)}, k < cnt <= 64, r0 a multiple of 64 when log_n >= 6
+    void block(uint64_t r0, uint64_t cnt, uint32_t* out) const {
+        if (log_n < 6) {
+            for (uint64_t k = 0; k < cnt; k++) out[k] = kb::pow(g, brev(r0 + k, log_n));
+            return;
+        }
+        const uint32_t base = kb::pow(g, brev(r0 >> 6, log_n - 6));
+        for (uint64_t k = 0; k < cnt; k++) out[k] = kb::mul(base, t64[k]);
+    }
+};
 
 }  // namespace
 
@@ -174,6 +197,131 @@ int bfo_air_quotient(int chip, const uint32_t* main_lde, const uint32_t* prep_ld
             uint32_t* o = q_out + ((i & 1) * n + (i >> 1)) * 4;
             for (int e = 0; e < 4; e++) o[e] = kb::from_mont(acc.c[e]);
         }
+    }
+    return 0;
+}
+
+// ---- openings (first half of `pcs.open`, reference prover.rs:460 -> TwoAdicFriPcs::open) -------------------------------------------------
+// lde: 2n x w canonical, rows bit-reversed; its first n stored rows are the evaluations on the coset GEN * H_n (bit-reversed).
+// out[c] = p_c(z) (w x 4 canonical) by the barycentric formula  p(z) = (z^n - s^n) / (n s^(n-1)) * sum_r p(x_r) g^r / (z - x_r).
+int bfo_open_eval(const uint32_t* lde, uint64_t n, uint32_t w, const uint32_t z[4], uint32_t* out) {
+    if (!lde || !out || n < 1 || (n & (n - 1)) || w == 0) return -1;
+    const unsigned log_n = ilog2(n);
+    const kb::Ext zz = ext_to_mont(z);
+    const uint32_t shift = kb::to_mont(kb::GEN), g = kb::two_adic_generator(log_n);
+    int nt_max = omp_get_max_threads();
+    std::vector<uint64_t> partial((size_t)nt_max * w * 4, 0);
+    constexpr int B = 64;  // rows per batch inversion
+    const BrevPowers bp(g, log_n);
+#pragma omp parallel
+    {
+        const int nt = omp_get_num_threads(), id = omp_get_thread_num();
+        std::vector<kb::ExtAcc> acc(w, kb::ext_acc_zero());
+        const uint64_t nb = (n + B - 1) / B;
+        for (uint64_t blk = (uint64_t)id; blk < nb; blk += (uint64_t)nt) {
+            const uint64_t r0 = blk * B, cnt = std::min<uint64_t>(B, n - r0);
+            kb::Ext d[B], pre[B];
+            uint32_t gp[B];
+            bp.block(r0, cnt, gp);  // g^{br(r)}
+            for (uint64_t k = 0; k < cnt; k++) {
+                d[k] = zz;
+                d[k].c[0] = kb::sub(d[k].c[0], kb::mul(shift, gp[k]));
+                pre[k] = k ? kb::ext_mul(pre[k - 1], d[k]) : d[k];
+            }
+            kb::Ext run = kb::ext_inv(pre[cnt - 1]);
+            for (uint64_t k = cnt; k-- > 0;) {
+                const kb::Ext inv = k ? kb::ext_mul(run, pre[k - 1]) : run;
+                run = kb::ext_mul(run, d[k]);
+                const kb::Ext wgt = kb::ext_scale(inv, gp[k]);
+                const uint32_t* row = lde + (r0 + k) * (uint64_t)w;
+                for (uint32_t c = 0; c < w; c++) kb::ext_mac(acc[c], wgt, kb::to_mont(row[c]));
+            }
+        }
+        for (uint32_t c = 0; c < w; c++) {
+            const kb::Ext e = kb::ext_acc_reduce(acc[c]);
+            for (int k = 0; k < 4; k++) partial[((size_t)id * w + c) * 4 + k] = e.c[k];
+        }
+    }
+    // (z^n - s^n) / (n s^(n-1))
+    kb::Ext zn = zz;
+    for (unsigned k = 0; k < log_n; k++) zn = kb::ext_sqr(zn);
+    zn.c[0] = kb::sub(zn.c[0], kb::pow(shift, n));
+    const uint32_t denom = kb::mul(kb::pow(shift, n - 1), kb::to_mont((uint32_t)(n % kb::P)));
+    const kb::Ext scale = kb::ext_scale(zn, kb::inv(denom));
+    for (uint32_t c = 0; c < w; c++) {
+        kb::Ext e = kb::ext_zero();
+        for (int t = 0; t < nt_max; t++) {
+            kb::Ext pt{{(uint32_t)partial[((size_t)t * w + c) * 4], (uint32_t)partial[((size_t)t * w + c) * 4 + 1], (uint32_t)partial[((size_t)t * w + c) * 4 + 2],
+                        (uint32_t)partial[((size_t)t * w + c) * 4 + 3]}};
+            e = kb::ext_add(e, pt);
+        }
+        e = kb::ext_mul(e, scale);
+        for (int k = 0; k < 4; k++) out[4 * c + k] = kb::from_mont(e.c[k]);
+    }
+    return 0;
+}
+
+// Reduced openings of ONE matrix added into the vector of its height (TwoAdicFriPcs::open, "reduced openings by height"):
+//   ro[r] += sum_t alpha^(off) * (y_red_t - sum_k alpha^k M[r][k]) / (z_t - x_r),   x_r = GEN w_h^{br(r)},  y_red_t = sum_k alpha^k ys_t[k],
+// off = number of columns already reduced at this height (+ w per point).  lde: h x w canonical (rows bit-reversed); zs: npts x 4; ys: npts x w x 4;
+// ro: h x 4 canonical, updated in place.
+int bfo_open_reduce_add(const uint32_t* lde, uint64_t h, uint32_t w, uint32_t npts, const uint32_t* zs, const uint32_t* ys, const uint32_t alpha[4],
+                        uint64_t reduced_before, uint32_t* ro) {
+    if (!lde || !ro || !zs || !ys || h < 2 || (h & (h - 1)) || w == 0 || npts == 0 || npts > 2) return -1;
+    const unsigned log_h = ilog2(h);
+    const kb::Ext a = ext_to_mont(alpha);
+    std::vector<kb::Ext> apow(w);
+    apow[0] = kb::ext_one();
+    for (uint32_t k = 1; k < w; k++) apow[k] = kb::ext_mul(apow[k - 1], a);
+    kb::Ext aw = kb::ext_mul(apow[w - 1], a);  // alpha^w
+    kb::Ext off[2], yred[2], zp[2];
+    kb::Ext o = kb::ext_one();
+    {  // alpha^reduced_before by square and multiply
+        kb::Ext base = a;
+        uint64_t e = reduced_before;
+        while (e) {
+            if (e & 1) o = kb::ext_mul(o, base);
+            base = kb::ext_sqr(base);
+            e >>= 1;
+        }
+    }
+    for (uint32_t t = 0; t < npts; t++) {
+        off[t] = o;
+        o = kb::ext_mul(o, aw);
+        zp[t] = ext_to_mont(zs + 4 * t);
+        kb::Ext y = kb::ext_zero();
+        for (uint32_t k = 0; k < w; k++) y = kb::ext_add(y, kb::ext_mul(apow[k], ext_to_mont(ys + ((uint64_t)t * w + k) * 4)));
+        yred[t] = y;
+    }
+    const uint32_t shift = kb::to_mont(kb::GEN), g = kb::two_adic_generator(log_h);
+    const BrevPowers bp(g, log_h);
+#pragma omp parallel for schedule(static)
+    for (uint64_t r0 = 0; r0 < h; r0 += 64) {
+      uint32_t gp[64];
+      const uint64_t cnt = std::min<uint64_t>(64, h - r0);
+      bp.block(r0, cnt, gp);
+      for (uint64_t r = r0; r < r0 + cnt; r++) {
+        const uint32_t x = kb::mul(shift, gp[r - r0]);
+        kb::ExtAcc acc = kb::ext_acc_zero();
+        const uint32_t* row = lde + r * (uint64_t)w;
+        for (uint32_t k = 0; k < w; k++) kb::ext_mac(acc, apow[k], kb::to_mont(row[k]));
+        const kb::Ext rr = kb::ext_acc_reduce(acc);
+        kb::Ext d[2], inv[2];
+        for (uint32_t t = 0; t < npts; t++) {
+            d[t] = zp[t];
+            d[t].c[0] = kb::sub(d[t].c[0], x);
+        }
+        if (npts == 2) {  // one inversion for both points
+            const kb::Ext ip = kb::ext_inv(kb::ext_mul(d[0], d[1]));
+            inv[0] = kb::ext_mul(ip, d[1]);
+            inv[1] = kb::ext_mul(ip, d[0]);
+        } else {
+            inv[0] = kb::ext_inv(d[0]);
+        }
+        kb::Ext sum{{kb::to_mont(ro[4 * r]), kb::to_mont(ro[4 * r + 1]), kb::to_mont(ro[4 * r + 2]), kb::to_mont(ro[4 * r + 3])}};
+        for (uint32_t t = 0; t < npts; t++) sum = kb::ext_add(sum, kb::ext_mul(off[t], kb::ext_mul(kb::ext_sub(yred[t], rr), inv[t])));
+        for (int k = 0; k < 4; k++) ro[4 * r + k] = kb::from_mont(sum.c[k]);
+      }
     }
     return 0;
 }

@@ -523,3 +523,160 @@ int bfo_fast_permute_many(uint32_t* states, uint64_t n) {
     }
     return 0;
 }
+
+/* ---- FRI commit phase (CPU arm of `pcs.open`, reference crates/stark/src/prover.rs:460 -> p3-fri prover::commit_phase) -----------------
+ * inputs[k]: 2^log_len[k] extension elements (4 canonical words each), heights strictly decreasing, inputs[0] the tallest (the
+ * per-height reduced openings).  Per round: commit the folded vector as an (len/2 x 8) matrix (row i = elements 2i, 2i+1; leaf =
+ * one permutation of (row | 0^8), then TruncatedPermutation compressions: the same packed 16-lane Poseidon2 as the commitments),
+ * fold with the CALLER-SUPPLIED beta of that round (fold_matrix: out[i] = (1/2 + beta/2 g^-br(i)) lo + (1/2 - beta/2 g^-br(i)) hi),
+ * add the input of the new length.  Stops at 2 elements (log_blowup 1).  roots: rounds x 8 canonical; final_poly: 4 canonical words.
+ * sec: {hashing, folding}.  rollin_beta2 != 0: a rolled-in input is multiplied by beta^2 first (the later upstream rule).
+ * Returns the number of rounds, or -1. */
+static inline void e_mul_m(const uint32_t* a, const uint32_t* b, uint32_t* r) { /* F_p[X]/(X^4 - 3), Montgomery words */
+    uint32_t t[7];
+    for (int k = 0; k < 7; k++) t[k] = 0;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            uint32_t s = t[i + j] + m_mul(a[i], b[j]);
+            t[i + j] = s >= FP ? s - FP : s;
+        }
+    for (int k = 0; k < 3; k++) {
+        uint32_t w = m_mul(t[4 + k], m_to(3));
+        uint32_t s = t[k] + w;
+        t[k] = s >= FP ? s - FP : s;
+    }
+    for (int k = 0; k < 4; k++) r[k] = t[k];
+}
+static inline uint32_t m_add(uint32_t a, uint32_t b) {
+    uint32_t s = a + b;
+    return s >= FP ? s - FP : s;
+}
+static inline uint32_t m_sub(uint32_t a, uint32_t b) { return a >= b ? a - b : a + FP - b; }
+TGT static void leaf_group_rows8(const uint32_t* mat, uint64_t i0, uint64_t cnt, uint32_t* digests) { /* rows of 8 Montgomery words, in order */
+    V t[16];
+    for (uint64_t l = 0; l < 16; l++)
+        t[l] = l < cnt ? _mm512_maskz_loadu_epi32(0x00ff, (const void*)(mat + (i0 + l) * 8)) : _mm512_setzero_si512();
+    v_transpose16(t); /* t[k] = word k of the 16 rows; words 8..15 are the zero capacity */
+    v_permute(t);
+    uint32_t tmp[8][16] __attribute__((aligned(64)));
+    for (int k = 0; k < 8; k++) _mm512_store_si512((void*)tmp[k], t[k]);
+    for (uint64_t l = 0; l < cnt; l++)
+        for (int k = 0; k < 8; k++) digests[(i0 + l) * 8 + (uint64_t)k] = tmp[k][l];
+}
+int bfo_fast_fri_commit_phase(const uint32_t* const* inputs, const uint32_t* log_len, int n_inputs, const uint32_t* betas, int rollin_beta2, uint32_t* roots,
+                              uint32_t final_poly[4], double sec[2]) {
+    if (!bfo_fast_available() || n_inputs < 1 || !inputs || !log_len || !betas || !roots) return -1;
+    init_rc();
+    const unsigned L = log_len[0];
+    if (L < 2 || L > KB_TWO_ADICITY) return -1;
+    const uint64_t len0 = 1ull << L;
+    uint32_t* cur = (uint32_t*)aligned_alloc(64, (len0 * 16 + 64 + 63) & ~63ull);
+    uint32_t* nxt = (uint32_t*)aligned_alloc(64, (len0 * 8 + 64 + 63) & ~63ull);
+    uint32_t* lay = (uint32_t*)aligned_alloc(64, (len0 * 16 + 63) & ~63ull); /* digests of the current level */
+    uint32_t* lay2 = (uint32_t*)aligned_alloc(64, (len0 * 8 + 63) & ~63ull);
+    if (!cur || !nxt || !lay || !lay2) {
+        free(cur); free(nxt); free(lay); free(lay2);
+        return -1;
+    }
+#pragma omp parallel for schedule(static)
+    for (uint64_t i = 0; i < len0 * 4; i++) cur[i] = m_to(inputs[0][i]);
+    const uint32_t half = m_pow(m_to(2), (uint64_t)FP - 2);
+    double t_hash = 0, t_fold = 0;
+    int next_in = 1, round = 0;
+    uint64_t len = len0;
+    while (len > 2) {
+        const uint64_t h = len / 2; /* leaves = output length */
+        unsigned log_h = 0;
+        while ((1ull << log_h) < h) log_h++;
+        double t0 = now_s();
+#pragma omp parallel for schedule(static) if (h >= 1024)
+        for (uint64_t g = 0; g < (h + 15) / 16; g++) leaf_group_rows8(cur, g * 16, h - g * 16 < 16 ? h - g * 16 : 16, lay);
+        uint64_t ll = h;
+        uint32_t *a = lay, *b = lay2;
+        while (ll > 1) {
+            uint64_t nl = ll / 2;
+#pragma omp parallel for schedule(static) if (nl >= 1024)
+            for (uint64_t k0 = 0; k0 < nl; k0 += 16) compress_group(a, b, k0, nl - k0 < 16 ? nl - k0 : 16);
+            uint32_t* t = a;
+            a = b;
+            b = t;
+            ll = nl;
+        }
+        for (int k = 0; k < 8; k++) roots[round * 8 + k] = m_from(a[k]);
+        double t1 = now_s();
+        uint32_t beta[4], hb[4], b2[4];
+        for (int k = 0; k < 4; k++) {
+            beta[k] = m_to(betas[round * 4 + k] % FP);
+            hb[k] = m_mul(beta[k], half);
+        }
+        e_mul_m(beta, beta, b2);
+        const uint32_t ginv = m_pow(m_pow(m_to(KB_GENERATOR), (uint64_t)(FP - 1) >> (log_h + 1)), (uint64_t)FP - 2); /* inverse generator of order 2^(log_h+1) */
+        const uint32_t* add = (next_in < n_inputs && log_len[next_in] == log_h) ? inputs[next_in] : NULL;
+#pragma omp parallel
+        {
+            int nt = omp_get_num_threads(), id = omp_get_thread_num();
+            uint64_t i0 = h * (uint64_t)id / (uint64_t)nt, i1 = h * (uint64_t)(id + 1) / (uint64_t)nt;
+            /* pw = ginv^bitrev(i), kept up to date while i counts up: i -> i + 1 clears the trailing ones of i (their mirrored
+               bits leave the exponent: multiply by g^(2^k)) and sets the next bit (multiply by ginv^(2^k)): ~2 products per step */
+            uint32_t GI[32], GG[32];
+            GI[0] = ginv;
+            GG[0] = m_pow(ginv, (uint64_t)FP - 2);
+            for (unsigned k = 1; k < 32; k++) {
+                GI[k] = m_mul(GI[k - 1], GI[k - 1]);
+                GG[k] = m_mul(GG[k - 1], GG[k - 1]);
+            }
+            uint32_t pw = m_pow(ginv, brev64(i0, log_h));
+            for (uint64_t i = i0; i < i1; i++) {
+                if (i != i0) {
+                    uint64_t prev = i - 1;
+                    unsigned b = 0;
+                    while (prev & 1) { /* trailing ones of i - 1: bit b was 1, now 0 */
+                        pw = m_mul(pw, GG[log_h - 1 - b]);
+                        prev >>= 1;
+                        b++;
+                    }
+                    pw = m_mul(pw, GI[log_h - 1 - b]);
+                }
+                uint32_t pa[4], pb[4], x[4], y[4];
+                for (int k = 0; k < 4; k++) {
+                    uint32_t t = m_mul(hb[k], pw);
+                    pa[k] = t;
+                    pb[k] = t ? FP - t : 0;
+                }
+                pa[0] = m_add(pa[0], half);
+                pb[0] = m_add(pb[0], half);
+                e_mul_m(pa, cur + 8 * i, x);
+                e_mul_m(pb, cur + 8 * i + 4, y);
+                for (int k = 0; k < 4; k++) x[k] = m_add(x[k], y[k]);
+                if (add) {
+                    uint32_t r[4];
+                    for (int k = 0; k < 4; k++) r[k] = m_to(add[4 * i + (uint64_t)k]);
+                    if (rollin_beta2) {
+                        uint32_t r2[4];
+                        e_mul_m(b2, r, r2);
+                        for (int k = 0; k < 4; k++) r[k] = r2[k];
+                    }
+                    for (int k = 0; k < 4; k++) x[k] = m_add(x[k], r[k]);
+                }
+                for (int k = 0; k < 4; k++) nxt[4 * i + (uint64_t)k] = x[k];
+            }
+        }
+        if (add) next_in++;
+        double t2 = now_s();
+        t_hash += t1 - t0;
+        t_fold += t2 - t1;
+        uint32_t* t = cur;
+        cur = nxt;
+        nxt = t;
+        len = h;
+        round++;
+    }
+    for (int k = 0; k < 4; k++) final_poly[k] = m_from(cur[k]);
+    if (sec) {
+        sec[0] = t_hash;
+        sec[1] = t_fold;
+    }
+    free(cur); free(nxt); free(lay); free(lay2);
+    (void)m_sub;
+    return round;
+}
