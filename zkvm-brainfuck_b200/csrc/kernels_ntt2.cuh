@@ -46,6 +46,10 @@ struct Tw {
 #ifndef NTT2_MINBLOCKS
 #define NTT2_MINBLOCKS 2
 #endif
+#ifndef NTT2_CONTIG_MINBLOCKS
+#define NTT2_CONTIG_MINBLOCKS 3  // contiguous passes at 85 registers, 3 CTAs/SM: forward pass 3.61 -> 3.39 ms at 2^22 x 512 half-columns (the strided
+                                  // register-prefetching passes lose at 3: 67.4 -> 68.7 ms per commit with $BFGPU_NTT_TMA=0)
+#endif
 #if NTT2_MONT_TW
 using TWT = uint32_t;
 #else
@@ -198,7 +202,7 @@ __device__ __forceinline__ uint32_t tile_idx(uint32_t d, uint32_t l) {
 #define NTT2_TURN_MINBLOCKS 3  // CTAs of 2^g <= 128 threads per SM the register budget is set for (g = 8: one)
 #endif
 template <bool INV, int G1, bool CONTIG, bool EPI = false, bool DUAL = false, bool TURN = false>
-__global__ void __launch_bounds__(TURN ? (1 << (G1 + 4)) : 256, TURN ? (G1 == 4 ? 1 : NTT2_TURN_MINBLOCKS) : EPI ? 1 : NTT2_MINBLOCKS) k_pass(PassArgs A) {
+__global__ void __launch_bounds__(TURN ? (1 << (G1 + 4)) : 256, TURN ? (G1 == 4 ? 1 : NTT2_TURN_MINBLOCKS) : EPI ? 1 : CONTIG ? NTT2_CONTIG_MINBLOCKS : NTT2_MINBLOCKS) k_pass(PassArgs A) {
     static_assert(!DUAL || (!INV && !CONTIG && !EPI && G1 > 0), "DUAL is the strided forward pass with two register phases");
     static_assert(!TURN || (INV && !CONTIG && !EPI && !DUAL && G1 > 0), "TURN is the strided last inverse pass with two register phases");
     constexpr int g = G1 + G2, NT = 1 << g;
