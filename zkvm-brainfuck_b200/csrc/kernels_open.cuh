@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const RoMat* __restrict
         const RoMat& M = mats[m];
         uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // unreduced sum_k alpha^k M[r][k]
         const uint32_t* col = M.d + r;
-        // (pairing two columns per conditional subtraction with kb::mac2 was MEASURED slower here: 3.27 vs 2.56 ms at 2^22 rows)
+        // (MEASURED slower here at 2^22 rows, 2.56 ms as written: pairing two columns per conditional subtraction with kb::mac2 3.27 ms; the
+        // powers of alpha staged in shared memory instead of the uniform global load 2.95 ms)
 #pragma unroll RO_UNROLL
         for (uint32_t k = 0; k < M.width; k++) {
             uint32_t v = col[(uint64_t)k * M.stride];
