@@ -117,3 +117,17 @@ def test_fri_commit_phase_matches_numpy(oracle, rollin):
     g_roots, g_final, _ = oracle.fast_fri_commit_phase(inputs, betas, rollin_beta2=rollin)
     assert (g_roots == np.array(roots)).all()
     assert (g_final == folded[0]).all()
+
+
+def test_bench_cpu_prove_arm_runs_all_spans(oracle):
+    """bench.py's per-phase CPU prove arm on a small program: every span of the reference's prover is exercised and timed."""
+    if not oracle.fast_available():
+        pytest.skip("needs AVX-512")
+    import bench
+    chips = chips_mod.machine_chips()
+    prog = ex.Program("+++++[>+++[>+>+<<-]<-]>>.")
+    traces, preps = tg.generate_traces(ex.execute(prog, [])), tg.preprocessed_traces(prog)
+    r = bench.cpu_prove_phases(traces, preps, [c.name for c in chips], local_only=[c.name for c in chips if c.local_only])
+    assert set(r["phases_ms"]) == {"commit main", "generate permutation traces", "commit permutation traces", "compute quotient values", "commit quotient", "open"}
+    assert all(v > 0 for v in r["phases_ms"].values()) and all(v > 0 for v in r["open_parts_ms"].values())
+    assert abs(r["ms"] - sum(r["phases_ms"].values())) < 1e-6 and r["kind"] == "port"
