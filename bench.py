@@ -127,12 +127,12 @@ def cpu_commit(log_rows, cols, steps, warmup):
 def cpu_prove_phases(traces, preps, chip_names, local_only=()):
     """Per-phase CPU arm of the shard prover on the SAME traces the GPU proves, all host threads, with the reference's span names:
       commit main                   CpuProver::commit              crates/stark/src/prover.rs:209-236   (tuned AVX-512 port, oracle/fast_commit.c)
-      generate permutation traces   prover.rs:281 -> permutation.rs:75-148                              (oracle/fast_air.cpp, scalar Montgomery + OpenMP)
+      generate permutation traces   prover.rs:281 -> permutation.rs:75-148        (oracle/fast_air_packed.cpp: the generated AIR programs on 16 rows per AVX-512 step, OpenMP)
       commit permutation traces     prover.rs:333
       compute quotient values       prover.rs:355 -> quotient.rs:18-165
       commit quotient               prover.rs:410
       open                          prover.rs:460 -> TwoAdicFriPcs::open: barycentric openings at zeta (and zeta * g), reduced openings per
-                                    height, FRI commit phase (packed Poseidon2 trees + folds)            (fast_air.cpp + fast_commit.c)
+                                    height (16 rows per step), FRI commit phase (packed Poseidon2 trees + folds)   (fast_air_packed.cpp + fast_commit.c)
     NOT included: the transcript, the proof-of-work grind (2^16 permutations) and the 84 query openings (microseconds of hashing) — so the
     total is a slight LOWER bound for a CPU prove.  Each matrix is committed on its own (the reference builds one mixed-height tree per
     commitment: same leaf hashing, same number of compressions); quotient chunks are committed on the unshifted domain (same cost); the
@@ -204,8 +204,9 @@ def cpu_prove_phases(traces, preps, chip_names, local_only=()):
     return {"phases_ms": {k: v * 1e3 for k, v in ph.items()}, "open_parts_ms": {k: v * 1e3 for k, v in open_parts.items()}, "ms": sum(ph.values()) * 1e3,
             "committed_cells": int(cells), "cores": oracle.get_threads(), "kind": "port",
             "not_included": "transcript, proof-of-work grind, query openings",
-            "what": "per-phase CPU arm of the shard prover on the same traces: tuned AVX-512 commitments and FRI trees (oracle/fast_commit.c) + scalar OpenMP "
-                    "LogUp / quotient / openings (oracle/fast_air.cpp); all six spans of the reference's prover"}
+            "what": "per-phase CPU arm of the shard prover on the same traces: tuned AVX-512 commitments and FRI trees (oracle/fast_commit.c) + packed AVX-512 "
+                    "(16 rows per step, OpenMP) LogUp / quotient / openings (oracle/fast_air_packed.cpp; scalar fast_air.cpp without AVX-512); "
+                    "all six spans of the reference's prover"}
 
 
 def bench_config(args, world):

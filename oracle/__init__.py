@@ -42,7 +42,8 @@ def air_lib():
     global _AIR
     if _AIR is None:
         so = os.path.join(_DIR, "libbfoair.so")
-        deps = [os.path.join(_DIR, "fast_air.cpp"), os.path.join(_DIR, "..", "zkvm-brainfuck_b200", "csrc", "gen_air.cuh"),
+        deps = [os.path.join(_DIR, "fast_air.cpp"), os.path.join(_DIR, "fast_air_packed.cpp"), os.path.join(_DIR, "packed_kb.h"),
+                os.path.join(_DIR, "..", "zkvm-brainfuck_b200", "csrc", "gen_air.cuh"),
                 os.path.join(_DIR, "..", "zkvm-brainfuck_b200", "csrc", "kb31.cuh")]
         if not os.path.exists(so) or any(os.path.exists(d) and os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["make", "-C", _DIR, "libbfoair.so"], stdout=subprocess.DEVNULL)
@@ -50,8 +51,13 @@ def air_lib():
         L.bfo_air_chip_info.argtypes = [C.c_int, C.POINTER(C.c_int)]
         L.bfo_air_perm_trace.argtypes = [C.c_int, u32p, u32p, C.c_uint64, u32p, u32p, u32p, u32p]
         L.bfo_air_quotient.argtypes = [C.c_int, u32p, u32p, u32p, C.c_uint64, u32p, u32p, u32p, u32p, u32p]
+        L.bfo_air_perm_trace_packed.argtypes = L.bfo_air_perm_trace.argtypes
+        L.bfo_air_quotient_packed.argtypes = L.bfo_air_quotient.argtypes
+        L.bfo_air_packed_available.restype = C.c_int
         L.bfo_open_eval.argtypes = [u32p, C.c_uint64, C.c_uint32, u32p, u32p]
         L.bfo_open_reduce_add.argtypes = [u32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, u32p, u32p, C.c_uint64, u32p]
+        L.bfo_open_eval_packed.argtypes = L.bfo_open_eval.argtypes
+        L.bfo_open_reduce_add_packed.argtypes = L.bfo_open_reduce_add.argtypes
         _AIR = L
     return _AIR
 
@@ -316,8 +322,13 @@ def air_chip_info(chip):
     return dict(main_w=info[0], prep_w=info[1], perm_w=info[2], n_constraints=info[3])
 
 
-def air_perm_trace(chip, main, prep, alpha, beta, timing=False):
-    """generate_permutation_trace on the CPU: (perm trace rows x 4*perm_w canonical, cumulative sum[, seconds of the C call])."""
+def air_packed_available():
+    return bool(air_lib().bfo_air_packed_available())
+
+
+def air_perm_trace(chip, main, prep, alpha, beta, timing=False, packed=None):
+    """generate_permutation_trace on the CPU: (perm trace rows x 4*perm_w canonical, cumulative sum[, seconds of the C call]).
+    packed: sixteen rows per step on AVX-512 (fast_air_packed.cpp); None = when the host and the shape allow, else the scalar arm."""
     import time
     inf = air_chip_info(chip)
     m = _u32(main)
@@ -325,15 +336,18 @@ def air_perm_trace(chip, main, prep, alpha, beta, timing=False):
     out = np.empty((m.shape[0], 4 * inf["perm_w"]), np.uint32)
     out.fill(0)  # touch the pages outside the timed call
     cs = np.zeros(4, np.uint32)
+    if packed is None:
+        packed = air_packed_available() and m.shape[0] >= 16 and m.shape[0] % 16 == 0
+    fn = air_lib().bfo_air_perm_trace_packed if packed else air_lib().bfo_air_perm_trace
     t = time.perf_counter()
-    rc = air_lib().bfo_air_perm_trace(int(chip), _p(m), _p(pr) if pr is not None else None, m.shape[0], _p(_u32(alpha)), _p(_u32(beta)), _p(out), _p(cs))
+    rc = fn(int(chip), _p(m), _p(pr) if pr is not None else None, m.shape[0], _p(_u32(alpha)), _p(_u32(beta)), _p(out), _p(cs))
     dt = time.perf_counter() - t
     if rc != 0:
         raise RuntimeError("bfo_air_perm_trace failed")
     return (out, cs, dt) if timing else (out, cs)
 
 
-def air_quotient(chip, main_lde, prep_lde, perm_lde, alpha_logup, beta, csum, alpha, timing=False):
+def air_quotient(chip, main_lde, prep_lde, perm_lde, alpha_logup, beta, csum, alpha, timing=False, packed=None):
     """quotient_values on the CPU from bit-reversed-row LDEs (2n rows): (2, n, 4) canonical chunk values[, seconds of the C call]."""
     import time
     inf = air_chip_info(chip)
@@ -342,37 +356,45 @@ def air_quotient(chip, main_lde, prep_lde, perm_lde, alpha_logup, beta, csum, al
     n = ml.shape[0] // 2
     out = np.empty((2, n, 4), np.uint32)
     out.fill(0)
+    if packed is None:
+        packed = air_packed_available() and n >= 8
+    fn = air_lib().bfo_air_quotient_packed if packed else air_lib().bfo_air_quotient
     t = time.perf_counter()
-    rc = air_lib().bfo_air_quotient(int(chip), _p(ml), _p(pl) if pl is not None else None, _p(ql), n, _p(_u32(alpha_logup)), _p(_u32(beta)), _p(_u32(csum)),
-                                    _p(_u32(alpha)), _p(out))
+    rc = fn(int(chip), _p(ml), _p(pl) if pl is not None else None, _p(ql), n, _p(_u32(alpha_logup)), _p(_u32(beta)), _p(_u32(csum)), _p(_u32(alpha)), _p(out))
     dt = time.perf_counter() - t
     if rc != 0:
         raise RuntimeError("bfo_air_quotient failed")
     return (out, dt) if timing else out
 
 
-def open_eval(lde, z, timing=False):
+def open_eval(lde, z, timing=False, packed=None):
     """Barycentric evaluation of every column of a committed matrix at the extension point z from its bit-reversed-row LDE (2n x w):
     (w, 4) canonical[, seconds]."""
     import time
     l = _u32(lde)
     out = np.zeros((l.shape[1], 4), np.uint32)
+    if packed is None:
+        packed = air_packed_available() and l.shape[0] >= 32 and l.shape[1] <= 256
+    fn = air_lib().bfo_open_eval_packed if packed else air_lib().bfo_open_eval
     t = time.perf_counter()
-    rc = air_lib().bfo_open_eval(_p(l), l.shape[0] // 2, l.shape[1], _p(_u32(z)), _p(out))
+    rc = fn(_p(l), l.shape[0] // 2, l.shape[1], _p(_u32(z)), _p(out))
     dt = time.perf_counter() - t
     if rc != 0:
         raise RuntimeError("bfo_open_eval failed")
     return (out, dt) if timing else out
 
 
-def open_reduce_add(lde, zs, ys, alpha, reduced_before, ro, timing=False):
+def open_reduce_add(lde, zs, ys, alpha, reduced_before, ro, timing=False, packed=None):
     """ro (h x 4 canonical, updated in place) += the reduced openings of one matrix at its npts <= 2 opening points."""
     import time
     l = _u32(lde)
     zs, ys = _u32(zs).reshape(-1, 4), _u32(ys)
     assert ro.dtype == np.uint32 and ro.flags.c_contiguous and ro.shape == (l.shape[0], 4)
+    if packed is None:
+        packed = air_packed_available() and l.shape[0] >= 16
+    fn = air_lib().bfo_open_reduce_add_packed if packed else air_lib().bfo_open_reduce_add
     t = time.perf_counter()
-    rc = air_lib().bfo_open_reduce_add(_p(l), l.shape[0], l.shape[1], zs.shape[0], _p(zs), _p(ys), _p(_u32(alpha)), int(reduced_before), _p(ro))
+    rc = fn(_p(l), l.shape[0], l.shape[1], zs.shape[0], _p(zs), _p(ys), _p(_u32(alpha)), int(reduced_before), _p(ro))
     dt = time.perf_counter() - t
     if rc != 0:
         raise RuntimeError("bfo_open_reduce_add failed")

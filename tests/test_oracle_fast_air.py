@@ -26,9 +26,10 @@ def test_perm_trace_and_quotient_match_numpy_oracle(oracle, code, stdin):
         n = main.shape[0]
         # permutation trace
         ref_perm, ref_cs = PR.generate_permutation_trace(chip, prep, main, (a_l, beta))
-        got_perm, got_cs = oracle.air_perm_trace(index, main, prep, a_l, beta)
-        assert (got_perm == PR.flatten_to_base(ref_perm)).all(), chip.name
-        assert (got_cs == ref_cs).all(), chip.name
+        for packed in ([False, True] if oracle.air_packed_available() and n >= 16 else [False]):  # scalar arm and the 16-rows-per-step AVX-512 arm
+            got_perm, got_cs = oracle.air_perm_trace(index, main, prep, a_l, beta, packed=packed)
+            assert (got_perm == PR.flatten_to_base(ref_perm)).all(), (chip.name, packed)
+            assert (got_cs == ref_cs).all(), (chip.name, packed)
         if n < 2:
             continue
         # quotient: LDEs on g * H_2n; the C arm reads bit-reversed rows, the numpy oracle natural order
@@ -37,9 +38,10 @@ def test_perm_trace_and_quotient_match_numpy_oracle(oracle, code, stdin):
         lde_br = lambda m: oracle.coset_lde_batch_bitrev(np.ascontiguousarray(m, np.uint32), 1, 3)
         flat = PR.flatten_to_base(ref_perm)
         ref_q = PR.quotient_values(chip, ref_cs, log_n, lde_nat(prep) if prep is not None else None, lde_nat(main), lde_nat(flat), (a_l, beta), alpha)
-        got_q = oracle.air_quotient(index, lde_br(main), lde_br(prep) if prep is not None else None, lde_br(flat), a_l, beta, ref_cs, alpha)
         ref_q = np.asarray(ref_q, np.uint64)
-        assert (got_q[0] == ref_q[0::2]).all() and (got_q[1] == ref_q[1::2]).all(), chip.name
+        for packed in ([False, True] if oracle.air_packed_available() and n >= 8 else [False]):
+            got_q = oracle.air_quotient(index, lde_br(main), lde_br(prep) if prep is not None else None, lde_br(flat), a_l, beta, ref_cs, alpha, packed=packed)
+            assert (got_q[0] == ref_q[0::2]).all() and (got_q[1] == ref_q[1::2]).all(), (chip.name, packed)
 
 
 def test_open_eval_matches_interpolate_coset(oracle):
@@ -52,8 +54,9 @@ def test_open_eval_matches_interpolate_coset(oracle):
         lde = oracle.coset_lde_batch_bitrev(m, 1, 3)
         low_nat = np.asarray(lde[:1 << log_n])[S.bitrev_perm(log_n)]
         ref = S.interpolate_coset(low_nat, S.GEN, z)
-        got = oracle.open_eval(lde, z)
-        assert (got == np.asarray(ref, np.uint64)).all(), (log_n, w)
+        for packed in ([False, True] if oracle.air_packed_available() and log_n >= 4 else [False]):
+            got = oracle.open_eval(lde, z, packed=packed)
+            assert (got == np.asarray(ref, np.uint64)).all(), (log_n, w, packed)
 
 
 def test_open_reduce_matches_numpy_formula(oracle):
@@ -70,6 +73,7 @@ def test_open_reduce_matches_numpy_formula(oracle):
     xs = S.f_mul(S.powers(S.two_adic_generator(log_h), h), S.GEN)[S.bitrev_perm(log_h)]
     ref = np.zeros((h, 4), U)
     got = np.zeros((h, 4), np.uint32)
+    got_p = np.zeros((h, 4), np.uint32)
     num = 0
     for lde, pts in mats:
         w = lde.shape[1]
@@ -85,8 +89,11 @@ def test_open_reduce_matches_numpy_formula(oracle):
             inv_den = S.e_inv(S.e_sub(z, S.e_from_base(xs)))
             ref = S.e_add(ref, S.e_mul(S.e_mul(S.e_sub(y_red, row_red), inv_den), off))
             num += w
-        oracle.open_reduce_add(lde, np.array(pts), np.array(ys_all), alpha, before, got)
+        oracle.open_reduce_add(lde, np.array(pts), np.array(ys_all), alpha, before, got, packed=False)
+        if oracle.air_packed_available():
+            oracle.open_reduce_add(lde, np.array(pts), np.array(ys_all), alpha, before, got_p, packed=True)
     assert (got == ref).all()
+    assert not oracle.air_packed_available() or (got_p == ref).all()
 
 
 @pytest.mark.parametrize("rollin", [False, True])
