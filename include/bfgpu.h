@@ -361,6 +361,14 @@ int32_t bfgpu_verify_shard_ex(const uint32_t vk_commit[8], const char* const* pr
                               const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries,
                               uint32_t pow_bits, const uint32_t* options, int32_t n_options, char* err, uint64_t err_len);
 
+/* `BfProver::verify` (crates/prover/src/verify.rs:10-36) on top of `StarkMachine::verify` (crates/stark/src/machine.rs:258-284): rejects
+ * a proof without the Cpu chip (MissingCpuInFirstShard) or with a Cpu log degree above MAX_CPU_LOG_DEGREE = 22
+ * (crates/core/machine/src/cpu/mod.rs:8; CpuLogDegreeTooLarge: <n>), then runs bfgpu_verify_shard_ex and reports its errors as
+ * "InvalidShardProof: <error>" (MachineVerificationError, machine.rs:391-416).  Host code only. */
+int32_t bfgpu_verify_core_proof(const uint32_t vk_commit[8], const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep,
+                                const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries,
+                                uint32_t pow_bits, const uint32_t* options, int32_t n_options, char* err, uint64_t err_len);
+
 /* Canonical proof serialiser: the bytes `bincode::serialize(&MachineProof { shard_proof })` writes for this proof
  * (crates/stark/src/types.rs:32-73,116-119; bincode 1.x defaults) — what the reference's `proofSize` counts
  * (crates/core/machine/src/utils/prove.rs:47-56) and what a Rust caller can `bincode::deserialize` into a `MachineProof`.  Host code

@@ -212,3 +212,45 @@ def test_transcript_options_native_verifier_matches_oracle(oracle, monkeypatch, 
     opts = dict(observe_opened_values=observe, fri_rollin=rollin)
     assert bf.verify_shard(pk.commit, pk.names, heights, words, *FRI, options=opts) is None
     assert bf.verify_shard(pk.commit, pk.names, heights, words, *FRI) is not None
+
+
+def test_core_proof_checks_of_the_prover_crate(hello):
+    """`BfProver::verify` (crates/prover/src/verify.rs:10-36): Cpu chip present, Cpu log degree <= MAX_CPU_LOG_DEGREE = 22
+    (crates/core/machine/src/cpu/mod.rs:8), then `StarkMachine::verify`, whose shard errors surface as InvalidShardProof
+    (machine.rs:281,391-416)."""
+    PR, S, pk, vk, proof, words = hello
+    heights = [t.shape[0] for t in pk.traces]
+    core = lambda w: bf.verify_core_proof(pk.commit, pk.names, heights, w, *FRI)  # noqa: E731
+    assert core(words) is None
+    order = sorted(proof["chip_ordering"], key=proof["chip_ordering"].get)
+    names = [c.name for c in chips]
+    n = len(order)
+    entries = [(int(words[25 + 6 * i]), int(words[25 + 6 * i + 1])) for i in range(n)]
+    assert [names[c] for c, _ in entries] == order  # the header layout this test edits
+    at = order.index("Cpu")
+    assert entries[at][1] == [c["log_degree"] for c in proof["opened_values"]][at]
+    # the Cpu entry renamed to another chip: the reference's `chip_ordering.contains_key("Cpu")` is false
+    other = names.index("Byte")
+    bad = words.copy()
+    bad[25 + 6 * at] = other
+    assert core(bad) == "MissingCpuInFirstShard"
+    # a proof cut off before the chip list holds no Cpu chip either
+    assert core(words[:20]) == "MissingCpuInFirstShard"
+    # log degree above 22: refused before the shard verifier looks at anything else
+    for ld in (23, 24, 0xFFFFFFFF):
+        bad = words.copy()
+        bad[25 + 6 * at + 1] = ld
+        assert core(bad) == f"CpuLogDegreeTooLarge: {ld}"
+    bad = words.copy()
+    bad[25 + 6 * at + 1] = 22  # allowed by this check, wrong for the proof
+    e = core(bad)
+    assert e is not None and e.startswith("InvalidShardProof: ")
+    # shard-level failures carry the reference's wrapper name and the same inner error as bfgpu_verify_shard
+    bad = _tweak(words, 3)
+    assert core(bad) == "InvalidShardProof: " + native(pk, bad)
+    # ProverClient.verify is this entry point
+    client = bf.ProverClient()
+    pv = bf.ProofWithPublicValues(words, None, [], [])
+    key = dict(commit=pk.commit, names=pk.names, heights=heights)
+    assert client.verify(pv, key, *FRI) is None
+    assert client.verify(bf.ProofWithPublicValues(bad, None, [], []), key, *FRI).startswith("InvalidShardProof: ")

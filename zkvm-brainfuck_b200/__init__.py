@@ -96,6 +96,8 @@ ABI = {
                            C.c_char_p, C.c_uint64]),
     "bfgpu_verify_shard_ex": (C.c_int32, [_u32p, C.POINTER(C.c_char_p), _u32p, C.c_int32, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                               _u32p, C.c_int32, C.c_char_p, C.c_uint64]),
+    "bfgpu_verify_core_proof": (C.c_int32, [_u32p, C.POINTER(C.c_char_p), _u32p, C.c_int32, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                _u32p, C.c_int32, C.c_char_p, C.c_uint64]),
     "bfgpu_shard_proof_to_bincode": (C.c_int32, [C.POINTER(C.c_char_p), _u32p, C.c_int32, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.c_void_p,
                                                   C.c_uint64, _u64p, C.c_char_p, C.c_uint64]),
     "bfgpu_dist_commit_begin": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u32p, C.c_int32, C.POINTER(C.c_void_p)]),
@@ -611,7 +613,7 @@ def _named_mats(named):
     return cn, arr, keep
 
 
-def verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1, num_queries=84, pow_bits=16, repr=REPR_CANONICAL, options=None):
+def verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1, num_queries=84, pow_bits=16, repr=REPR_CANONICAL, options=None, core=False):
     """`Verifier::verify_shard` (crates/stark/src/verifier.rs:27-216) in native host code, on the serialised proof of
     `CudaProver.open_raw` / `prove_program(raw=True)`.  vk = (preprocessed commitment, names and heights of the
     preprocessed traces in proving-key order: `pk.commit, pk.names, pk.heights`).  Returns None when the proof is
@@ -624,9 +626,17 @@ def verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1,
     opt = _u32([1, 0, 0])  # defaults of bfgpu_set_transcript_option
     for k, v in (options or {}).items():
         opt[Context.OPTIONS[k]] = int(v)
-    rc = lib().bfgpu_verify_shard_ex(com.ctypes.data_as(_u32p), names, logs.ctypes.data_as(_u32p), len(prep_names), words.ctypes.data_as(_u32p), words.size,
-                                     repr, log_blowup, num_queries, pow_bits, opt.ctypes.data_as(_u32p), 3, err, 256)
+    fn = lib().bfgpu_verify_core_proof if core else lib().bfgpu_verify_shard_ex
+    rc = fn(com.ctypes.data_as(_u32p), names, logs.ctypes.data_as(_u32p), len(prep_names), words.ctypes.data_as(_u32p), words.size,
+            repr, log_blowup, num_queries, pow_bits, opt.ctypes.data_as(_u32p), 3, err, 256)
     return None if rc == 0 else (err.value.decode() or f"error {rc}")
+
+
+def verify_core_proof(vk_commit, prep_names, prep_heights, proof_words, log_blowup=1, num_queries=84, pow_bits=16, repr=REPR_CANONICAL, options=None):
+    """`BfProver::verify` (crates/prover/src/verify.rs:10-36): the Cpu chip must be present (MissingCpuInFirstShard) with a log degree of
+    at most 22 (CpuLogDegreeTooLarge: n), then `StarkMachine::verify` -> `verify_shard`, whose errors read "InvalidShardProof: ...".
+    Returns None when accepted.  Needs no GPU."""
+    return verify_shard(vk_commit, prep_names, prep_heights, proof_words, log_blowup, num_queries, pow_bits, repr, options, core=True)
 
 
 def proof_to_bincode(prep_names, prep_heights, proof_words, log_blowup=1, repr=REPR_CANONICAL, field_repr=1):
@@ -969,10 +979,11 @@ class ProverClient:
         return _Action(run)
 
     def verify(self, proof, vk, log_blowup=1, num_queries=None, pow_bits=16):
-        """Returns None when accepted, else the reference's error name (`BfVerificationError`)."""
+        """`BfProver::verify` (crates/prover/src/verify.rs:10-36).  Returns None when accepted, else the reference's error name
+        (`MachineVerificationError`: MissingCpuInFirstShard, CpuLogDegreeTooLarge: n, InvalidShardProof: <VerificationError>)."""
         if num_queries is None:
             num_queries = int(os.environ.get("FRI_QUERIES", 84))  # kb31_poseidon2.rs:59-62
-        return verify_shard(vk["commit"], vk["names"], vk["heights"], proof.words, log_blowup, num_queries, pow_bits)
+        return verify_core_proof(vk["commit"], vk["names"], vk["heights"], proof.words, log_blowup, num_queries, pow_bits)
 
 
 class _ProgramOnly:

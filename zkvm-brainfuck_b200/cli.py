@@ -34,7 +34,7 @@ def _human(nbytes):
 
 
 def main(argv=None):
-    from . import ProverClient, Record, proof_to_bincode, verify_shard
+    from . import ProverClient, Record, proof_to_bincode, verify_core_proof
     ap = argparse.ArgumentParser(prog="bfprove", description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     sub = ap.add_subparsers(dest="cmd", required=True)
     e = sub.add_parser("execute")
@@ -82,7 +82,7 @@ def main(argv=None):
         blob = proof_to_bincode(vk["names"], vk["heights"], words, fri["log_blowup"])
         print(f"proofSize={_human(len(blob))} ({len(blob)} bytes; {words.size} field/shape words in the flat form)")
         return 0
-    err = verify_shard(np.array(vk["commit"], np.uint32), vk["names"], vk["heights"], words, fri["log_blowup"], fri["num_queries"], fri["pow_bits"])
+    err = verify_core_proof(np.array(vk["commit"], np.uint32), vk["names"], vk["heights"], words, fri["log_blowup"], fri["num_queries"], fri["pow_bits"])
     if err is None:
         print("accepted")
         return 0

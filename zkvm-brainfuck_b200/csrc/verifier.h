@@ -429,6 +429,46 @@ extern "C" int32_t bfgpu_verify_shard(const uint32_t vk_commit[8], const char* c
                                  err_len);
 }
 
+// `BfProver::verify` (crates/prover/src/verify.rs:10-36) above `StarkMachine::verify` (crates/stark/src/machine.rs:258-284): the two
+// checks the reference makes on the proof before the shard verifier runs — the Cpu chip must be in `chip_ordering`
+// (MissingCpuInFirstShard) and its log degree must not exceed MAX_CPU_LOG_DEGREE = 22 (crates/core/machine/src/cpu/mod.rs:8: the LogUp
+// multiplicities must not overflow; CpuLogDegreeTooLarge) — then `verify_shard`, whose errors come back as "InvalidShardProof: ...".
+extern "C" int32_t bfgpu_verify_core_proof(const uint32_t vk_commit[8], const char* const* prep_names, const uint32_t* prep_log_heights, int32_t n_prep,
+                                           const uint32_t* proof, uint64_t n_words, int repr, uint32_t log_blowup, uint32_t num_queries, uint32_t pow_bits,
+                                           const uint32_t* options, int32_t n_options, char* err, uint64_t err_len) {
+    constexpr uint32_t MAX_CPU_LOG_DEGREE = 22;
+    auto say = [&](const std::string& s) {
+        if (err && err_len) snprintf(err, (size_t)err_len, "%s", s.c_str());
+    };
+    if (!vk_commit || !proof) {
+        say("null argument");
+        return BFGPU_ERR_INVALID;
+    }
+    // header of the serialisation: three commitments (24 words), the chip count, then (chip, log_degree, cumulative sum[4]) per chip
+    const int cpu = chip_index("Cpu");
+    const uint64_t n_chips = n_words > 24 ? proof[24] : 0;
+    bool has_cpu = false;
+    uint32_t log_degree_cpu = 0;
+    for (uint64_t i = 0; i < n_chips && i < (uint64_t)air::NUM_CHIPS && 25 + 6 * i + 1 < n_words; i++)
+        if ((int)proof[25 + 6 * i] == cpu && !has_cpu) {
+            has_cpu = true;
+            log_degree_cpu = proof[25 + 6 * i + 1];
+        }
+    if (!has_cpu) {
+        say("MissingCpuInFirstShard");
+        return BFGPU_ERR_INVALID;
+    }
+    if (log_degree_cpu > MAX_CPU_LOG_DEGREE) {
+        say(verifier::fmt("CpuLogDegreeTooLarge: %u", log_degree_cpu));
+        return BFGPU_ERR_INVALID;
+    }
+    char inner[256] = {0};
+    int32_t rc = bfgpu_verify_shard_ex(vk_commit, prep_names, prep_log_heights, n_prep, proof, n_words, repr, log_blowup, num_queries, pow_bits, options,
+                                       n_options, inner, sizeof inner);
+    say(rc == BFGPU_OK ? std::string() : std::string("InvalidShardProof: ") + inner);
+    return rc;
+}
+
 // ---- canonical proof serialiser: the bytes `bincode::serialize(&MachineProof)` writes ------------------------------
 // The reference measures `proofSize` as the length of `bincode::serialize(&proof)` (crates/core/machine/src/utils/prove.rs:47-56) over
 // `MachineProof { shard_proof: ShardProof { commitment, opened_values, opening_proof, chip_ordering } }` (crates/stark/src/types.rs:32-73,
