@@ -1,4 +1,4 @@
-"""Hand-written per-row evaluators of the Cpu and Jump chips' AIRs, transcribed DIRECTLY from the reference's Rust
+"""Hand-written per-row evaluators of all eight chips' AIRs, transcribed DIRECTLY from the reference's Rust
 (no import of air/dsl.py or air/chips.py): test infrastructure that breaks the "one declarative description feeds the
 CUDA codegen, the oracle prover and both verifiers" blind spot.  tests/test_air_independent.py
 cross-checks air/chips.py against these on valid, corrupted and random rows.
@@ -10,6 +10,12 @@ Sources (reference, /root/reference/crates):
   core/machine/src/jump/air.rs:22-82, jump/cols.rs:11-31            JumpChip::eval and JumpCols
   core/machine/src/operations/is_zero.rs:45-62, koala_bear_word.rs:50-108   IsZeroOperation::eval, KoalaBearWordRangeChecker
   core/machine/src/memory/consistency/cols.rs:5-45                  MemoryReadWriteCols / MemoryWriteCols / MemoryAccessCols
+  core/machine/src/alu/mod.rs:23-38,157-192, operations/add.rs:41-75   AddSubChip::eval, AddSubCols, AddOperation::eval
+  core/machine/src/memory/instructions/air.rs:26-76, cols.rs:13-35  MemoryInstructionsChip::eval and its columns
+  core/machine/src/memory/memory.rs:22-44,131-145                   MemoryChip::eval (two entries per row)
+  core/machine/src/io/mod.rs:19-31,127-141                          IoChip::eval
+  core/machine/src/program/mod.rs:31-41,152-163, cpu/cols.rs:18-24  ProgramChip::eval (preprocessed pc + InstructionCols, main multiplicity)
+  core/machine/src/bytes/air.rs:22-44, bytes/cols.rs:13-30, executor/src/events/byte.rs:109-113   ByteChip::eval
   stark/src/air/builder.rs:31-33,52-229                             when_not = when_ne(c, 1); lookup tuples
   stark/src/word.rs:67-70                                           Word::reduce
   stark/src/lookup/lookup.rs:19-40, core/executor/src/opcode.rs:12-42   LookupKind, Opcode, ByteOpcode numbering
@@ -19,7 +25,7 @@ Every function works on Python ints mod p; rows are sequences of canonical resid
 P = 2130706433
 MEMORY, PROGRAM, ALU, JUMP, MEMINSTR, IO, BYTE = 1, 2, 3, 4, 5, 6, 7   # LookupKind
 U8RANGE, U16RANGE = 0, 1                                                # ByteOpcode
-LOOP_START, LOOP_END = 0, 1                                             # Opcode
+LOOP_START, LOOP_END, ADD, SUB, MEM_STEP_FORWARD, MEM_STEP_BACKWARD, INPUT, OUTPUT = range(8)   # Opcode
 
 
 class _Rec:
@@ -160,4 +166,100 @@ def jump_eval(local, nxt=None, is_first_row=0, is_last_row=0, is_transition=0):
     _word_range_check(b, l.next_pc, l.next_pc_rc, is_real)
     opcode = l.is_loop_start * LOOP_START + l.is_loop_end * LOOP_END
     b.receive(JUMP, [pc, npc, opcode, l.mv], is_real)
+    return b
+
+
+# ---- AddSubCols (alu/mod.rs:23-38): pc, AddOperation { value, carry }, operand_1, operand_2, is_add, is_sub ---------------------
+def addsub_eval(local, nxt=None, is_first_row=0, is_last_row=0, is_transition=0, prep=None):
+    """AddSubChip::eval (alu/mod.rs:157-192) with AddOperation::eval (operations/add.rs:41-75)."""
+    pc, value, carry, operand_1, operand_2, is_add, is_sub = [int(x) for x in local]
+    b = _Rec()
+    is_real = is_add + is_sub
+    b.boolean(is_add)
+    b.boolean(is_sub)
+    b.boolean(is_real)
+    overflow = operand_1 + operand_2 - value
+    b.zero(overflow * (overflow - 256), is_real)          # the carried and the plain result differ by zero or the base
+    b.zero(carry * (overflow - 256), is_real)
+    b.zero((carry - 1) * overflow, is_real)
+    b.boolean(carry, is_real)
+    b.boolean(is_real, is_real)
+    for v in (operand_1, operand_2, value):               # range_check_u8 (air/u8_air.rs:8-17)
+        b.send(BYTE, [U8RANGE, v, 0], is_real)
+    b.receive(ALU, [pc, ADD, value, operand_1], is_add)   # '+': next_mv = value, mv = operand_1
+    b.receive(ALU, [pc, SUB, operand_1, value], is_sub)   # '-': the addition runs backwards (next_mv + 1 = mv)
+    return b
+
+
+# ---- MemoryInstructionsCols (memory/instructions/cols.rs:13-35) -----------------------------------------------------------------
+class MemInstrRow:
+    def __init__(self, r):
+        r = [int(x) for x in r]
+        assert len(r) == 41
+        self.pc, self.clk = r[0], r[1]
+        self.mp, self.mp_rc = r[2:6], r[6:20]
+        self.next_mp, self.next_mp_rc = r[20:24], r[24:38]
+        self.is_step_forward, self.is_step_backward, self.is_real = r[38], r[39], r[40]
+
+
+def meminstr_eval(local, nxt, is_first_row=0, is_last_row=0, is_transition=0, prep=None):
+    """MemoryInstructionsChip::eval (memory/instructions/air.rs:26-76)."""
+    l, n, b = MemInstrRow(local), MemInstrRow(nxt), _Rec()
+    is_real = l.is_step_forward + l.is_step_backward
+    b.boolean(l.is_step_forward)
+    b.boolean(l.is_step_backward)
+    b.boolean(is_real)
+    mp, next_mp = _reduce(l.mp), _reduce(l.next_mp)
+    b.eq(next_mp, mp + 1, l.is_step_forward)
+    b.eq(next_mp, mp - 1, l.is_step_backward)
+    b.eq(next_mp, _reduce(n.mp), is_transition, n.is_real)
+    _word_range_check(b, l.mp, l.mp_rc, l.is_real)           # the range checks hang on the is_real COLUMN,
+    _word_range_check(b, l.next_mp, l.next_mp_rc, l.is_real)
+    opcode = l.is_step_forward * MEM_STEP_FORWARD + l.is_step_backward * MEM_STEP_BACKWARD
+    b.receive(MEMINSTR, [l.clk, l.pc, opcode, mp, next_mp], is_real)   # the lookup on the SUM of the two selectors
+    return b
+
+
+# ---- MemCols (memory/memory.rs:22-44): two SingleMemoryLocal { addr, initial_clk, final_clk, initial_value, final_value, is_real } --
+def memory_eval(local, nxt=None, is_first_row=0, is_last_row=0, is_transition=0, prep=None):
+    """MemoryChip::eval (memory/memory.rs:131-145): no constraints, one receive (initial access) and one send (final access) per entry."""
+    r, b = [int(x) for x in local], _Rec()
+    assert len(r) == 12
+    for k in range(2):
+        addr, initial_clk, final_clk, initial_value, final_value, is_real = r[6 * k:6 * k + 6]
+        b.receive(MEMORY, [initial_clk, addr, initial_value], is_real)
+        b.send(MEMORY, [final_clk, addr, final_value], is_real)
+    return b
+
+
+# ---- IoCols (io/mod.rs:19-31): pc, mp, mv, is_input, is_output -------------------------------------------------------------------
+def io_eval(local, nxt=None, is_first_row=0, is_last_row=0, is_transition=0, prep=None):
+    """IoChip::eval (io/mod.rs:127-141)."""
+    pc, mp, mv, is_input, is_output = [int(x) for x in local]
+    b = _Rec()
+    is_real = is_input + is_output
+    b.boolean(is_input)
+    b.boolean(is_output)
+    b.boolean(is_real)
+    b.receive(IO, [pc, is_input * INPUT + is_output * OUTPUT, mp, mv], is_real)
+    return b
+
+
+# ---- ProgramPreprocessedCols { pc, InstructionCols { opcode, op_a: Word } } + ProgramMultiplicityCols (program/mod.rs:31-41) --------
+def program_eval(local, nxt=None, is_first_row=0, is_last_row=0, is_transition=0, prep=None):
+    """ProgramChip::eval (program/mod.rs:152-163): receive_program (air/program.rs:31-42) lists the opcode twice."""
+    (multiplicity,), q, b = [int(x) for x in local], [int(x) for x in prep], _Rec()
+    assert len(q) == 6
+    pc, opcode, op_a = q[0], q[1], q[2:6]
+    b.receive(PROGRAM, [pc, opcode, opcode] + op_a, multiplicity)
+    return b
+
+
+# ---- BytePreprocessedCols { value_u8, value_u16 } + ByteMultCols { multiplicities[2] } (bytes/cols.rs:13-30) ---------------------
+def byte_eval(local, nxt=None, is_first_row=0, is_last_row=0, is_transition=0, prep=None):
+    """ByteChip::eval (bytes/air.rs:22-44), opcodes in ByteOpcode::all() order (executor/src/events/byte.rs:109-113)."""
+    mult, (value_u8, value_u16), b = [int(x) for x in local], [int(x) for x in prep], _Rec()
+    assert len(mult) == 2
+    b.receive(BYTE, [U8RANGE, value_u8, 0], mult[U8RANGE])
+    b.receive(BYTE, [U16RANGE, 0, value_u16], mult[U16RANGE])
     return b
