@@ -1,13 +1,13 @@
 #!/usr/bin/env python3
-"""tools/prove_bench.py — end-to-end shard-prove timings on the GPU (BASELINE.json configs 1-3), with the
-per-phase device times recorded by the library.  Usage: python tools/prove_bench.py [fibo hello loop20 loop22]"""
+"""tests/tools/prove_bench.py — end-to-end shard-prove timings on the GPU (BASELINE.json configs 1-3), with the
+per-phase device times recorded by the library.  Usage: python tests/tools/prove_bench.py [fibo hello loop20 loop22]"""
 import importlib
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""tools/prove_once.py <program> — setup + 2 proofs of one program (for ncu launch lists)."""
+"""tests/tools/prove_once.py <program> — setup + 2 proofs of one program (for ncu launch lists)."""
 import importlib, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import zkvm_brainfuck_b200 as bf
 ex = importlib.import_module("oracle.machine.executor")

@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
-"""tools/sanitize_lde.py — small coset LDEs and one small proof for compute-sanitizer runs (memcheck / racecheck / synccheck):
+"""tests/tools/sanitize_lde.py — small coset LDEs and one small proof for compute-sanitizer runs (memcheck / racecheck / synccheck):
 every instantiation family of the TMA passes (fused ingest, INV, TURN, FWD), the cluster tree top and the prover kernels, at
 sizes a sanitizer finishes in minutes; results are compared with the CPU oracle so a silent corruption shows as well."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import oracle

@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
-"""tools/stress_lde.py [reps] — repeat coset LDEs / commits of several shapes and compare every repetition bit for bit with the
+"""tests/tools/stress_lde.py [reps] — repeat coset LDEs / commits of several shapes and compare every repetition bit for bit with the
 first one (and the first one with the CPU oracle where it is small enough): a race in the shared-memory slot protocol of the TMA
 passes or in the cluster tree top would show up as a run-to-run difference.  (compute-sanitizer is not available on the GPU pool.)"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import oracle
