@@ -66,3 +66,13 @@ def test_rust_sys_crate_declares_every_symbol():
     assert open(g.OUT).read() == src, "run `python scripts/gen_rust_sys.py`"
     declared = set(re.findall(r"pub fn (bfgpu_[a-z_0-9]+)\(", src))
     assert declared == set(bf.ABI), (declared ^ set(bf.ABI))
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/bfgpu.h must compile as C99 (what cgo / bindgen / a C caller sees), warning-free, and as C++."""
+    import subprocess
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "bfgpu.h")
+    for cmd in (["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", hdr],
+                ["g++", "-fsyntax-only", "-x", "c++", "-std=c++17", "-Wall", "-Wextra", "-Werror", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
