@@ -2,6 +2,7 @@
  *
  *     gcc -std=c99 -Iinclude integration/c_caller.c -Lzkvm-brainfuck_b200 -lbfgpu -Wl,-rpath,$PWD/zkvm-brainfuck_b200 -o c_caller
  *     ./c_caller                       # program -> proof -> verify on device 0; without a GPU: execute only, then "no CPU fallback"
+ *     ./c_caller 20                    # the same, then 20 more proofs timed from this side of the ABI (ms per proof)
  *
  * The call sequence is the one `ProverClient::{execute, setup, prove, verify}` makes in the reference
  * (crates/sdk/src/lib.rs:19-140 -> crates/prover/src/lib.rs:46-104 -> crates/core/machine/src/utils/prove.rs:24-60):
@@ -11,16 +12,24 @@
  *   MachineProver::commit / open  bfgpu_machine_commit_record / bfgpu_machine_open
  *   BfProver::verify              bfgpu_verify_core_proof  (host)
  * tests/test_abi.py builds and runs it (the execute part everywhere, the proving part on a GPU box). */
+#define _POSIX_C_SOURCE 199309L /* clock_gettime under -std=c99 */
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "bfgpu.h"
 
 static const char* PROGRAM = "++++++++[>++++++++<-]>+.,.";  /* prints 'A', then echoes the input byte */
 
-int main(void) {
+static double now_ms(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
+int main(int argc, char** argv) {
     const uint8_t input[1] = {'z'};
     bfgpu_record* rec = NULL;
     if (bfgpu_execute(NULL, PROGRAM, input, 1, 0, &rec) != BFGPU_OK) {
@@ -78,6 +87,26 @@ int main(void) {
         rc = bfgpu_verify_core_proof(vk_commit, names, logs, 2, words, n_words, BFGPU_REPR_CANONICAL, 1, 84, 16, NULL, 0, err, sizeof err);
         printf("proof: %llu words, verifier: %s\n", (unsigned long long)n_words, rc == BFGPU_OK ? "accepted" : err);
         free(words);
+    }
+    if (rc == BFGPU_OK && argc > 1) { /* latency of execute -> commit -> open seen by a C caller (the proving key stays resident) */
+        const int reps = atoi(argv[1]);
+        const double t0 = now_ms();
+        for (int k = 0; k < reps && rc == BFGPU_OK; k++) {
+            bfgpu_record* r2 = NULL;
+            bfgpu_shard* s2 = NULL;
+            bfgpu_challenger* c2 = NULL;
+            bfgpu_shard_proof* p2 = NULL;
+            rc = bfgpu_execute(ctx, PROGRAM, input, 1, 0, &r2);
+            if (rc == BFGPU_OK) rc = bfgpu_challenger_create(ctx, &c2);
+            if (rc == BFGPU_OK) rc = bfgpu_pk_observe_into(pk, c2);
+            if (rc == BFGPU_OK) rc = bfgpu_machine_commit_record(ctx, r2, main_root, &s2);
+            if (rc == BFGPU_OK) rc = bfgpu_machine_open(ctx, pk, s2, c2, -1, &p2);
+            bfgpu_shard_proof_free(p2);
+            bfgpu_shard_free(s2);
+            bfgpu_challenger_free(c2);
+            bfgpu_record_free(r2);
+        }
+        if (rc == BFGPU_OK && reps > 0) printf("%d proofs from C: %.3f ms per proof\n", reps, (now_ms() - t0) / reps);
     }
 done:
     if (rc != BFGPU_OK) fprintf(stderr, "failed: %s\n", bfgpu_last_error(ctx));
