@@ -305,6 +305,30 @@ pub fn decode_shard_proof(words: &[u32], pk: &StarkProvingKey<SC>) -> ShardProof
     proof.shard_proof
 }
 
+/// `BfProver::verify` (crates/prover/src/verify.rs:10-36) by the library's host verifier, on the flat words of `bfgpu_machine_open`:
+/// the Cpu chip must be present with a log degree of at most 22, then `Verifier::verify_shard`.  For deployments that verify without
+/// the Rust verifier (and for comparing verdicts with it); `Err` carries the reference's error name
+/// (`MissingCpuInFirstShard`, `CpuLogDegreeTooLarge: n`, `InvalidShardProof: <VerificationError>`).
+pub fn verify_core_proof(vk: &StarkVerifyingKey<SC>, pk: &StarkProvingKey<SC>, words: &[u32], num_queries: u32) -> Result<(), String> {
+    let mut by_index: Vec<(&String, &usize)> = pk.chip_ordering.iter().collect();
+    by_index.sort_by_key(|(_, i)| **i);
+    let names: Vec<CString> = by_index.iter().map(|(n, _)| CString::new(n.as_str()).unwrap()).collect();
+    let name_ptrs: Vec<*const c_char> = names.iter().map(|c| c.as_ptr()).collect();
+    let logs: Vec<u32> = by_index.iter().map(|(_, i)| pk.traces[**i].height().trailing_zeros()).collect();
+    // Hash<F, F, 8> is [F; 8] and F is repr(transparent) over its Montgomery word
+    let commit: [u32; 8] = unsafe { core::mem::transmute_copy(&vk.commit) };
+    let mut err = [0 as c_char; 256];
+    let rc = unsafe {
+        sys::bfgpu_verify_core_proof(commit.as_ptr(), name_ptrs.as_ptr(), logs.as_ptr(), logs.len() as i32, words.as_ptr(), words.len() as u64,
+                                     sys::BFGPU_REPR_MONTY, 1, num_queries, 16, ptr::null(), 0, err.as_mut_ptr(), 256)
+    };
+    if rc == sys::BFGPU_OK {
+        Ok(())
+    } else {
+        Err(unsafe { CStr::from_ptr(err.as_ptr()) }.to_string_lossy().into_owned())
+    }
+}
+
 /// The pieces of the nested proof, spelled out once for readers who want to see the mapping (not used by `decode_shard_proof`):
 /// flat words [0, 24) = the three commitments; word 24 = number of chips; then per chip (index, log_degree, cumulative sum);
 /// then the opened values (preprocessed in proving-key order, main, permutation, quotient), the FRI commit-phase commitments,
