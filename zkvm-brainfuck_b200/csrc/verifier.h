@@ -237,12 +237,19 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
     const uint32_t pow_witness = rd.raw();  // canonical in the serialisation
     const uint32_t nq = rd.raw();
     if (!rd.ok || nq != num_queries) return "InvalidProofShape: query count";
-    if (pow_witness >= kb::P || !ch.check_witness(pow_bits, kb::to_mont(pow_witness))) return "InvalidPowWitness";
+    // every error of pcs.verify reaches the caller wrapped (verifier.rs: `.map_err(VerificationError::InvalidopeningArgument)`)
+    if (pow_witness >= kb::P || !ch.check_witness(pow_bits, kb::to_mont(pow_witness))) return "InvalidOpeningArgument:InvalidPowWitness";
     const unsigned log_max = n_commit + log_blowup;
     const uint32_t gen = kb::to_mont(kb::GEN);
+    bool index_word_differs = false;
     for (uint32_t qi = 0; qi < nq; qi++) {
         const uint32_t index = ch.sample_bits(log_max);
-        if (rd.raw() != index || !rd.ok) return "InvalidProofShape: query index";
+        // The serialisation carries the index for the reader's convenience; the reference's QueryProof does not, its verifier uses the
+        // sampled one.  So a transcript that went wrong fails where the reference fails (the Merkle openings no longer fit the sampled
+        // index: InputMmcsError); a proof that verifies but carries another index word is a second encoding of the same proof and is
+        // refused at the end.
+        if (rd.raw() != index) index_word_differs = true;
+        if (!rd.ok) return "InvalidProofShape: truncated query";
         // reduced openings per height (fri/two_adic_pcs.rs verify: open_input)
         std::map<unsigned, Ext, std::greater<unsigned>> ro;
         std::map<unsigned, Ext> apow;
@@ -318,6 +325,7 @@ static std::string verify(const uint32_t vk_commit_in[8], const std::vector<std:
         if (it != ro.end()) return "InvalidOpeningArgument:InvalidProofShape";
         if (!e_eq(folded, final_poly)) return "InvalidOpeningArgument:FinalPolyMismatch";
     }
+    if (index_word_differs) return "InvalidProofShape: query index";
     if (rd.pos != rd.n) return "InvalidProofShape: trailing words";
     // ---- constraints at zeta (verifier.rs:218-329) -----------------------------------------------------------------------------
     size_t qpos = 0;
